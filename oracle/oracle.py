@@ -1,0 +1,290 @@
+"""
+oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front end of the CPU oracle (oracle/liboracle.so, built by oracle/Makefile)
+plus the synthetic problem set-up shared by tests/ and bench.py's cpu_baseline leg.
+Nothing under varden_b200/ imports this module.
+
+Array convention: every box is a numpy array of shape (n0, n1, n2, ncomp), order='F',
+covering lo-ng .. hi+ng (+1 in the face direction); 2-D uses n2 == 1.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# FBoxLib bc_module codes (see orc_common.h)
+PERIODIC, INTERIOR, INLET, OUTLET, SYMMETRY, SLIP_WALL, NO_SLIP_WALL = -1, 0, 11, 12, 13, 14, 15
+REFLECT_ODD, REFLECT_EVEN, FOEXTRAP, EXT_DIR, HOEXTRAP = 20, 21, 22, 23, 24
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("dim", C.c_int), ("nscal", C.c_int), ("slope_order", C.c_int), ("use_minion", C.c_int),
+                ("boussinesq", C.c_int), ("stencil_order", C.c_int),
+                ("visc_coef", C.c_double), ("diff_coef", C.c_double),
+                ("bcval", C.c_double * 30),
+                ("mg_rel_eps", C.c_double), ("mg_bottom_eps", C.c_double),
+                ("mg_max_cycles", C.c_int), ("mg_nu1", C.c_int), ("mg_nu2", C.c_int), ("mg_verbose", C.c_int)]
+
+
+class OrcGeom(C.Structure):
+    _fields_ = [("nboxes", C.c_int), ("blo", C.POINTER(C.c_int)), ("bhi", C.POINTER(C.c_int)),
+                ("dlo", C.c_int * 3), ("dhi", C.c_int * 3), ("phys_bc", C.c_int * 6), ("dx", C.c_double * 3)]
+
+
+class Params:
+    """The probin values the path reads (src/_parameters)."""
+
+    def __init__(self, dim=3, nscal=2, slope_order=4, use_minion=False, boussinesq=0, stencil_order=2,
+                 visc_coef=0.0, diff_coef=0.0, bcval=None, mg_rel_eps=1e-10, mg_bottom_eps=1e-3,
+                 mg_max_cycles=100, mg_nu1=2, mg_nu2=2, mg_verbose=0):
+        self.dim, self.nscal, self.slope_order, self.use_minion = dim, nscal, slope_order, int(use_minion)
+        self.boussinesq, self.stencil_order = boussinesq, stencil_order
+        self.visc_coef, self.diff_coef = visc_coef, diff_coef
+        self.bcval = np.zeros((5, 3, 2)) if bcval is None else np.asarray(bcval, dtype=float).reshape(5, 3, 2)
+        self.mg_rel_eps, self.mg_bottom_eps = mg_rel_eps, mg_bottom_eps
+        self.mg_max_cycles, self.mg_nu1, self.mg_nu2, self.mg_verbose = mg_max_cycles, mg_nu1, mg_nu2, mg_verbose
+
+    def to_c(self):
+        p = OrcParams()
+        p.dim, p.nscal, p.slope_order, p.use_minion = self.dim, self.nscal, self.slope_order, self.use_minion
+        p.boussinesq, p.stencil_order = self.boussinesq, self.stencil_order
+        p.visc_coef, p.diff_coef = self.visc_coef, self.diff_coef
+        for i, v in enumerate(self.bcval.ravel()):
+            p.bcval[i] = v
+        p.mg_rel_eps, p.mg_bottom_eps = self.mg_rel_eps, self.mg_bottom_eps
+        p.mg_max_cycles, p.mg_nu1, p.mg_nu2, p.mg_verbose = self.mg_max_cycles, self.mg_nu1, self.mg_nu2, self.mg_verbose
+        return p
+
+
+class Geom:
+    """One AMR level: domain, physical BCs, dx and the box list (initialize.f90:198-215)."""
+
+    def __init__(self, dim, n_cell, phys_bc, prob_lo=(0., 0., 0.), prob_hi=(1., 1., 1.), max_grid_size=256, boxes=None):
+        self.dim = dim
+        self.n_cell = [int(n_cell[d]) if d < dim else 1 for d in range(3)]
+        self.dlo = [0, 0, 0]
+        self.dhi = [self.n_cell[d] - 1 if d < dim else 0 for d in range(3)]
+        self.phys_bc = np.zeros((3, 2), dtype=np.int32)
+        self.phys_bc[:dim, :] = np.asarray(phys_bc, dtype=np.int32).reshape(-1, 2)[:dim]
+        self.dx = [(prob_hi[d] - prob_lo[d]) / self.n_cell[d] if d < dim else 0.0 for d in range(3)]
+        self.prob_lo = list(prob_lo)
+        if boxes is None:
+            boxes = chop_domain(self.dlo, self.dhi, dim, max_grid_size)
+        self.boxes = boxes
+        self._blo = np.ascontiguousarray([b[0] for b in boxes], dtype=np.int32)
+        self._bhi = np.ascontiguousarray([b[1] for b in boxes], dtype=np.int32)
+
+    @property
+    def nboxes(self):
+        return len(self.boxes)
+
+    def to_c(self):
+        g = OrcGeom()
+        g.nboxes = self.nboxes
+        g.blo = self._blo.ctypes.data_as(C.POINTER(C.c_int))
+        g.bhi = self._bhi.ctypes.data_as(C.POINTER(C.c_int))
+        for d in range(3):
+            g.dlo[d], g.dhi[d], g.dx[d] = self.dlo[d], self.dhi[d], self.dx[d]
+        for i, v in enumerate(self.phys_bc.ravel()):
+            g.phys_bc[i] = int(v)
+        return g
+
+    def box_shape(self, ib, ng, face_dir=-1):
+        lo, hi = self.boxes[ib]
+        return tuple((hi[d] - lo[d] + 1 + 2 * ng + (1 if d == face_dir else 0)) if d < self.dim else 1 for d in range(3))
+
+
+def chop_domain(dlo, dhi, dim, max_grid_size):
+    """boxarray_maxsize: chop each direction into the fewest equal-ish pieces <= max_grid_size."""
+    cuts = []
+    for d in range(3):
+        if d >= dim:
+            cuts.append([(0, 0)])
+            continue
+        n = dhi[d] - dlo[d] + 1
+        npieces = (n + max_grid_size - 1) // max_grid_size
+        base, rem = divmod(n, npieces)
+        segs, s = [], dlo[d]
+        for p in range(npieces):
+            ln = base + (1 if p < rem else 0)
+            segs.append((s, s + ln - 1))
+            s += ln
+        cuts.append(segs)
+    boxes = []
+    for kz in cuts[2]:
+        for jy in cuts[1]:
+            for ix in cuts[0]:
+                boxes.append(([ix[0], jy[0], kz[0]], [ix[1], jy[1], kz[1]]))
+    return boxes
+
+
+def mf_alloc(geom, ng, ncomp, face_dir=-1, val=0.0):
+    return [np.full(geom.box_shape(ib, ng, face_dir) + (ncomp,), val, dtype=np.float64, order='F') for ib in range(geom.nboxes)]
+
+
+def _pp(mf):
+    """list of numpy arrays -> double**"""
+    if mf is None:
+        return None
+    arr = (C.c_void_p * len(mf))(*[a.ctypes.data for a in mf])
+    return C.cast(arr, C.POINTER(C.POINTER(C.c_double)))
+
+
+def valid(geom, a, ib, ng, face_dir=-1):
+    """view of the valid region of box ib"""
+    sl = []
+    for d in range(3):
+        if d < geom.dim:
+            n = a.shape[d]
+            sl.append(slice(ng, n - ng))
+        else:
+            sl.append(slice(None))
+    return a[tuple(sl)]
+
+
+def fill_boundary(geom, mf, ng, ncomp, face_dir=-1):
+    g = geom.to_c()
+    lib().orc_fill_boundary(C.byref(g), C.c_int(geom.dim), _pp(mf), C.c_int(ng), C.c_int(ncomp), C.c_int(face_dir))
+
+
+def fill_and_physbc(geom, params, mf, ng, ncomp_total, scomp, bccomp, nc, same_boundary=False):
+    g, p = geom.to_c(), params.to_c()
+    lib().orc_fill_and_physbc(C.byref(g), C.byref(p), _pp(mf), C.c_int(ng), C.c_int(ncomp_total), C.c_int(scomp),
+                              C.c_int(bccomp), C.c_int(nc), C.c_int(int(same_boundary)))
+
+
+def advance(geom, params, st, dt, mac_rel_eps=-1.0, want_phi=True):
+    """One pass of the hot path (advance_timestep.f90:66-124).  st: dict with uold,sold,gp,ext_vel_force,ext_scal_force[,lapu]."""
+    dim, nscal = geom.dim, params.nscal
+    g, p = geom.to_c(), params.to_c()
+    lapu = st.get("lapu") or mf_alloc(geom, 0, dim)
+    out = dict(unew=mf_alloc(geom, 3, dim), snew=mf_alloc(geom, 3, nscal), rhohalf=mf_alloc(geom, 1, 1),
+               umac=[mf_alloc(geom, 1, 1, d) for d in range(dim)], phi=mf_alloc(geom, 1, 1) if want_phi else None)
+    um = out["umac"] + [None] * (3 - dim)
+    res = C.c_double(0.0)
+    f = lib().orc_advance_mf
+    f.restype = C.c_int
+    cycles = f(C.byref(g), C.byref(p), _pp(st["uold"]), _pp(st["sold"]), _pp(st["gp"]), _pp(st["ext_vel_force"]),
+               _pp(st["ext_scal_force"]), _pp(lapu), _pp(out["unew"]), _pp(out["snew"]), _pp(out["rhohalf"]),
+               _pp(um[0]), _pp(um[1]), _pp(um[2]), _pp(out["phi"]), C.c_double(dt), C.c_double(mac_rel_eps), C.byref(res))
+    out["mac_cycles"], out["mac_resnorm"] = cycles, res.value
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic problems; initial data follows src/initdata.f90:195-200,261-274
+# ---------------------------------------------------------------------------------------------
+def _h(x):
+    return 0.02 * np.sin(4.0 * np.pi * x) + 0.01 * np.sin(8.0 * np.pi * x)
+
+
+def rt_state(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, seeded_velocity=True, params=None, phys_bc=None):
+    """Density-stratified Rayleigh-Taylor-type state: periodic in x(,y), no-slip walls in the last direction.
+
+    rho = rho_mid + rho_amp*tanh((z - 1/2 - h(x) - h(y))/0.01) with (rho_mid, rho_amp) giving the density ratio
+    (ratio 2 reproduces initdata.f90:270 exactly: 1.5 + 0.5 tanh).  A deterministic, not discretely
+    divergence-free velocity is seeded so that the MAC right-hand side is non-trivial.
+    """
+    if np.isscalar(n):
+        n = [n] * dim
+    if phys_bc is None:
+        phys_bc = [[PERIODIC, PERIODIC]] * (dim - 1) + [[NO_SLIP_WALL, NO_SLIP_WALL]]
+    geom = Geom(dim, n, phys_bc, max_grid_size=max_grid_size)
+    if params is None:
+        params = Params(dim=dim, nscal=2)
+    rho_lo, rho_hi = 1.0, float(ratio)
+    mid, amp = 0.5 * (rho_hi + rho_lo), 0.5 * (rho_hi - rho_lo)
+    st = dict(uold=mf_alloc(geom, 3, dim), sold=mf_alloc(geom, 3, params.nscal), gp=mf_alloc(geom, 1, dim),
+              ext_vel_force=mf_alloc(geom, 1, dim), ext_scal_force=mf_alloc(geom, 1, params.nscal))
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        ax = [(np.arange(lo[d], hi[d] + 1) + 0.5) * geom.dx[d] if d < dim else np.zeros(1) for d in range(3)]
+        X, Y, Z = np.meshgrid(ax[0], ax[1], ax[2], indexing='ij')
+        if dim == 3:
+            rho = mid + amp * np.tanh((Z - 0.5 - _h(X) - _h(Y)) / 0.01)
+        else:
+            rho = mid + amp * np.tanh((Y - 0.5 - _h(X)) / 0.01)
+        valid(geom, st["sold"][ib], ib, 3)[..., 0] = rho
+        valid(geom, st["sold"][ib], ib, 3)[..., 1] = 0.0
+        if seeded_velocity:
+            u = valid(geom, st["uold"][ib], ib, 3)
+            if dim == 3:
+                u[..., 0] = 0.1 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) * np.sin(np.pi * Z)
+                u[..., 1] = -0.1 * np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(np.pi * Z)
+                u[..., 2] = 0.05 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(2 * np.pi * Z)
+            else:
+                u[..., 0] = 0.1 * np.sin(2 * np.pi * X) * np.sin(np.pi * Y)
+                u[..., 1] = 0.05 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y)
+        st["ext_vel_force"][ib][..., dim - 1] = grav      # varden.f90:428-429
+    # path-boundary input state: ghost cells filled as varden.f90:291-300
+    fill_and_physbc(geom, params, st["uold"], 3, dim, 0, 0, dim)
+    fill_and_physbc(geom, params, st["sold"], 3, params.nscal, 0, dim, params.nscal)
+    fill_boundary(geom, st["gp"], 1, dim)
+    dt = 0.45 * geom.dx[0] / 0.1
+    return geom, params, st, dt
+
+
+def random_state(n, dim=3, max_grid_size=256, phys_bc=None, seed=0, params=None, umag=1.0):
+    """Randomised but smooth-ish state exercising all selects; any phys_bc combination."""
+    rng = np.random.default_rng(seed)
+    if np.isscalar(n):
+        n = [n] * dim
+    if phys_bc is None:
+        phys_bc = [[SLIP_WALL, SLIP_WALL]] * dim
+    geom = Geom(dim, n, phys_bc, max_grid_size=max_grid_size)
+    if params is None:
+        bcval = np.zeros((5, 3, 2))
+        bcval[0:3] = rng.uniform(-0.5, 0.5, size=(3, 3, 2)) * umag     # inflow velocities
+        bcval[3] = rng.uniform(1.0, 2.0, size=(3, 2))                  # rho_bc
+        bcval[4] = rng.uniform(0.0, 1.0, size=(3, 2))                  # trac_bc
+        params = Params(dim=dim, nscal=2, bcval=bcval)
+    nn = [geom.n_cell[d] for d in range(3)]
+    # global random fields (smoothed a little so that slopes/limiters take both branches)
+    def field(scale, offset=0.0):
+        f = rng.standard_normal(nn)
+        for d in range(dim):
+            f = 0.5 * f + 0.25 * (np.roll(f, 1, d) + np.roll(f, -1, d))
+        return offset + scale * f
+    U = [field(umag) for _ in range(dim)]
+    RHO = np.abs(field(0.5, 1.5)) + 0.2
+    TR = field(1.0)
+    GP = [field(0.3) for _ in range(dim)]
+    st = dict(uold=mf_alloc(geom, 3, dim), sold=mf_alloc(geom, 3, params.nscal), gp=mf_alloc(geom, 1, dim),
+              ext_vel_force=mf_alloc(geom, 1, dim), ext_scal_force=mf_alloc(geom, 1, params.nscal))
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        sl = tuple(slice(lo[d], hi[d] + 1) for d in range(3))
+        for c in range(dim):
+            valid(geom, st["uold"][ib], ib, 3)[..., c] = U[c][sl]
+            valid(geom, st["gp"][ib], ib, 1)[..., c] = GP[c][sl]
+        valid(geom, st["sold"][ib], ib, 3)[..., 0] = RHO[sl]
+        valid(geom, st["sold"][ib], ib, 3)[..., 1] = TR[sl]
+        st["ext_vel_force"][ib][..., dim - 1] = -9.8
+        st["ext_scal_force"][ib][..., 1] = 0.1
+    fill_and_physbc(geom, params, st["uold"], 3, dim, 0, 0, dim)
+    fill_and_physbc(geom, params, st["sold"], 3, params.nscal, 0, dim, params.nscal)
+    fill_boundary(geom, st["gp"], 1, dim)
+    # gp: the reference only fill_boundary's it (varden.f90:294); give the physical ghosts finite values
+    fill_and_physbc(geom, params, st["gp"], 1, dim, 0, dim + params.nscal + 1, dim, same_boundary=True)
+    umax = max(np.abs(u).max() for u in U)
+    dt = 0.4 * min(geom.dx[:dim]) / max(umax, 1e-3)
+    return geom, params, st, dt
