@@ -1,0 +1,147 @@
+/*
+ * vdn.h -- C ABI of the B200-native VARDEN hot path (advection + MAC projection).
+ *
+ * This is the drop-in boundary: plain `extern "C"`, pointers and sizes only, `int`
+ * status returns (0 = OK, non-zero = error, text via vdn_last_error).  Each entry point
+ * names the reference interface it replaces (file:line under BoxLib-Codes/VARDEN).
+ * The Fortran side keeps its module/procedure signatures and calls these through
+ * ISO_C_BINDING (see fortran/vdn_iso_c.f90 and INTEGRATION.md).
+ *
+ * Host array convention (what `dataptr(mf,i)` points at in the reference):
+ *   a(lo1-ng:hi1+ng, lo2-ng:hi2+ng, lo3-ng:hi3+ng, ncomp)   Fortran order, FP64,
+ *   face ("edge") multifabs in direction d have hi_d+1; 2-D has a unit third extent.
+ *
+ * Process model: one context per GPU / MPI rank.  A context owns the device mirror of
+ * the rank-local boxes, stored as ONE merged array per field over the rank's region
+ * (the bounding box of its boxes, which must tile it).  Not re-entrant per context.
+ */
+#ifndef VDN_H
+#define VDN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* physical BC codes = FBoxLib bc_module (define_bc_tower.f90:158-340, inputs bcx_lo ...) */
+#define VDN_BC_PERIODIC     (-1)
+#define VDN_BC_INTERIOR     0
+#define VDN_BC_INLET        11
+#define VDN_BC_OUTLET       12
+#define VDN_BC_SYMMETRY     13
+#define VDN_BC_SLIP_WALL    14
+#define VDN_BC_NO_SLIP_WALL 15
+
+/* Device-resident fields.  (ng, ncomp, centring) are fixed per field:
+ *   UOLD/UNEW ng3 dm comps; SOLD/SNEW ng3 nscal comps; GP, EXT_VEL_FORCE, VEL_FORCE ng1 dm comps;
+ *   EXT_SCAL_FORCE, SCAL_FORCE ng1 nscal comps; LAPU ng0 dm comps; MAC_RHS, RHOHALF, PHI ng1 1 comp;
+ *   UMAC_X/Y/Z face, ng1, 1 comp; RH ng0; BETA_X/Y/Z face ng0;
+ *   SEDGE_X/Y/Z, SFLUX_X/Y/Z face ng0 nscal comps; UEDGE_X/Y/Z face ng0 dm comps. */
+enum vdn_field {
+    VDN_UOLD = 0, VDN_SOLD, VDN_UNEW, VDN_SNEW, VDN_GP,
+    VDN_EXT_VEL_FORCE, VDN_EXT_SCAL_FORCE, VDN_LAPU,
+    VDN_UMAC_X, VDN_UMAC_Y, VDN_UMAC_Z,
+    VDN_MAC_RHS, VDN_RHOHALF, VDN_VEL_FORCE, VDN_SCAL_FORCE,
+    VDN_RH, VDN_PHI, VDN_BETA_X, VDN_BETA_Y, VDN_BETA_Z,
+    VDN_SEDGE_X, VDN_SEDGE_Y, VDN_SEDGE_Z,
+    VDN_SFLUX_X, VDN_SFLUX_Y, VDN_SFLUX_Z,
+    VDN_UEDGE_X, VDN_UEDGE_Y, VDN_UEDGE_Z,
+    VDN_NFIELDS
+};
+
+/* The probin values the path reads (src/_parameters; probin_module uses in slope.f90:15,
+ * velpred.f90:130, mkforce.f90:147, multifab_physbc.f90 u_bc..trac_bc). */
+typedef struct vdn_params {
+    int    nscal;              /* _parameters: nscal (2) */
+    int    slope_order;        /* 0, 2 or 4 (4) */
+    int    use_minion;         /* 0 */
+    int    boussinesq;         /* 0 */
+    int    stencil_order;      /* 2 (only 2 is implemented) */
+    int    mg_verbose;         /* >0: per-cycle residual log on stdout */
+    int    mg_nu1, mg_nu2;     /* pre/post smoothing sweeps (F_MG default 2,2) */
+    int    mg_max_cycles;      /* V-cycle cap (100) */
+    int    mg_max_bottom_iter; /* BiCGStab cap (100) */
+    double mg_bottom_eps;      /* mac_multigrid.f90:56 -> 1.d-3 */
+    double visc_coef, diff_coef;
+    double bc_val[5][3][2];    /* u_bc, v_bc, w_bc, rho_bc, trac_bc (dir, side): EXT_DIR constants */
+} vdn_params;
+
+typedef struct vdn_ctx vdn_ctx;
+
+/* Fill a vdn_params with the reference defaults (src/_parameters). */
+void vdn_params_default(vdn_params *p);
+
+/*
+ * Create the device mirror of one level's rank-local layout.
+ *   replaces: multifab_build / layout on the device side (advance_timestep.f90:66-80, macproject.f90:47-58)
+ *             and bc_tower_level_build (define_bc_tower.f90:62-105; BC tables are derived here from phys_bc).
+ * box_lo/box_hi: [nboxes][3] inclusive cell indices of the local boxes (lwb/upb of get_box);
+ * dom_lo/dom_hi: level problem domain; phys_bc[3][2]: bcx_lo.. codes; dx[3]; device: CUDA ordinal.
+ */
+int vdn_ctx_create(const vdn_params *prm, int dim, int nboxes, const int *box_lo, const int *box_hi,
+                   const int *dom_lo, const int *dom_hi, const int *phys_bc, const double *dx,
+                   int device, vdn_ctx **out);
+void vdn_ctx_destroy(vdn_ctx *ctx);
+const char *vdn_last_error(const vdn_ctx *ctx);   /* ctx may be NULL: last create error */
+
+/*
+ * Multi-GPU (one context per rank).  region_lo/hi: [nranks][3] cell bounds of every rank's region
+ * (a tensor-product decomposition of the domain); nccl_unique_id: 128 bytes from ncclGetUniqueId,
+ * broadcast by the caller (torch.distributed / MPI).   replaces: layout_build_ba + parallel (MPI) in FBoxLib.
+ */
+int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *region_lo, const int *region_hi,
+                     const void *nccl_unique_id);
+
+/* Path-boundary copies (SURVEY 8(b) "Copies"): host box array <-> region array, ghosts included
+ * where they lie outside the region's valid area.  `host` has `ng` ghosts and `ncomp` comps and
+ * must match the field's fixed (ng, ncomp). */
+int vdn_field_upload(vdn_ctx *ctx, int field, int ibox, const double *host, int ng, int ncomp);
+int vdn_field_download(vdn_ctx *ctx, int field, int ibox, double *host, int ng, int ncomp);
+int vdn_field_setval(vdn_ctx *ctx, int field, double val);       /* multifab setval(all=.true.) */
+int vdn_sync(vdn_ctx *ctx);
+
+/* ---- stage calls: same names / argument meaning as the reference module procedures ---- */
+
+/* multifab_fill_boundary (FBoxLib; call sites velpred.f90:110, macproject.f90:117,492) */
+int vdn_fill_boundary(vdn_ctx *ctx, int field);
+/* ml_restrict_and_fill for nlevs==1 = fill_boundary + multifab_physbc (multifab_physbc.f90:17).
+ * bccomp: 0-based index into the adv_bc table (0..dm-1 vel, dm.. scalars, dm+nscal press, dm+nscal+1 extrap). */
+int vdn_fill_and_physbc(vdn_ctx *ctx, int field, int bccomp, int same_boundary);
+
+/* mkvelforce (mkforce.f90:18): VEL_FORCE = ext [*s2] + (visc_coef*visc_fac*lapu - gp)/rho; rho_field = VDN_SOLD or VDN_RHOHALF */
+int vdn_mkvelforce(vdn_ctx *ctx, int rho_field, double visc_fac);
+/* mkscalforce (mkforce.f90:238): SCAL_FORCE, laps = 0 (diff_coef == 0 path) */
+int vdn_mkscalforce(vdn_ctx *ctx, double diff_fac);
+/* velpred (velpred.f90:16): UOLD, VEL_FORCE -> UMAC_* (+ fill_boundary) */
+int vdn_velpred(vdn_ctx *ctx, double dt);
+/* macproject (macproject.f90:20): UMAC_*, rho = SOLD comp 1, MAC_RHS -> projected UMAC_*, PHI.
+ * rel_eps <= 0 selects the reference's 1.d-10 (macproject.f90:92).  Returns 2 if not converged. */
+int vdn_macproject(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, double *resnorm);
+/* mkflux (mkflux.f90:16): is_vel=0: SOLD,SCAL_FORCE -> SEDGE_*,SFLUX_* (density conservative);
+ *                         is_vel=1: UOLD,VEL_FORCE,MAC_RHS -> UEDGE_* */
+int vdn_mkflux(vdn_ctx *ctx, int is_vel, double dt);
+/* update (update.f90:16) + ghost fill: is_vel=0 -> SNEW, is_vel=1 -> UNEW */
+int vdn_update(vdn_ctx *ctx, int is_vel, double dt);
+/* make_at_halftime (make_at_halftime.f90:18): RHOHALF = 0.5*(SOLD_1 + SNEW_1) + ghost fill */
+int vdn_make_at_halftime(vdn_ctx *ctx);
+
+/* The whole device-resident path advance_timestep.f90:95-124:
+ * advance_premac -> macproject -> scalar_advance -> make_at_halftime -> velocity_advance. */
+int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, double *mac_resnorm);
+
+/* ---- building blocks exposed for parity tests (macproject.f90 internal procedures) ---- */
+int vdn_divumac(vdn_ctx *ctx, double *rhmax);     /* RH = MAC_RHS - div(UMAC), macproject.f90:137 */
+int vdn_mk_mac_coeffs(vdn_ctx *ctx);              /* BETA_* from SOLD comp 1, macproject.f90:280 */
+int vdn_mac_solve(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, double *resnorm); /* mac_multigrid.f90:19 */
+int vdn_mkumac(vdn_ctx *ctx);                     /* macproject.f90:403 */
+
+/* ---- measurement: per-kernel-family CUDA-event timing on the launching stream ---- */
+int vdn_prof_enable(vdn_ctx *ctx, int on);        /* resets counters */
+int vdn_prof_count(vdn_ctx *ctx);                 /* number of kernel families seen */
+/* name (<=63 chars), launches, total device ms, algorithmic bytes (SURVEY 8(a) figure x cells) */
+int vdn_prof_get(vdn_ctx *ctx, int idx, char *name, long long *launches, double *ms, double *alg_bytes);
+long long vdn_launch_count(vdn_ctx *ctx);         /* kernels launched since creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

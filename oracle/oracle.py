@@ -288,3 +288,99 @@ def random_state(n, dim=3, max_grid_size=256, phys_bc=None, seed=0, params=None,
     umax = max(np.abs(u).max() for u in U)
     dt = 0.4 * min(geom.dx[:dim]) / max(umax, 1e-3)
     return geom, params, st, dt
+
+
+# ---------------------------------------------------------------------------------------------
+# stage-wise entry points (same call sequence as the reference module procedures)
+# ---------------------------------------------------------------------------------------------
+def _um3(umac, dim):
+    arr = (C.POINTER(C.POINTER(C.c_double)) * 3)()
+    for d in range(3):
+        arr[d] = _pp(umac[d]) if d < dim else None
+    return arr
+
+
+def mkvelforce(geom, params, vel_force, ext, gp, s, ng_s, ncomp_s, lapu, visc_fac):
+    g, p = geom.to_c(), params.to_c()
+    lib().orc_mkvelforce_mf(C.byref(g), C.byref(p), _pp(vel_force), _pp(ext), _pp(gp), _pp(s), C.c_int(ng_s), C.c_int(ncomp_s),
+                            _pp(lapu), C.c_double(visc_fac))
+
+
+def mkscalforce(geom, params, scal_force, ext, laps, diff_fac):
+    g, p = geom.to_c(), params.to_c()
+    lib().orc_mkscalforce_mf(C.byref(g), C.byref(p), _pp(scal_force), _pp(ext), _pp(laps), C.c_double(diff_fac))
+
+
+def velpred(geom, params, u, umac, force, dt):
+    g, p = geom.to_c(), params.to_c()
+    lib().orc_velpred_mf(C.byref(g), C.byref(p), _pp(u), _um3(umac, geom.dim), _pp(force), C.c_double(dt))
+
+
+def macproject(geom, params, umac, rho, mac_rhs, rel_eps=-1.0, want_phi=True):
+    g, p = geom.to_c(), params.to_c()
+    phi = mf_alloc(geom, 1, 1) if want_phi else None
+    res = C.c_double(0.0)
+    f = lib().orc_macproject_mf
+    f.restype = C.c_int
+    cyc = f(C.byref(g), C.byref(p), _um3(umac, geom.dim), _pp(rho), C.c_int(params.nscal), _pp(mac_rhs), _pp(phi),
+            C.c_double(rel_eps), C.byref(res))
+    return cyc, res.value, phi
+
+
+def mkflux(geom, params, sold, ncomp, sedge, flux, umac, force, mac_rhs, dt, is_vel, is_cons):
+    g, p = geom.to_c(), params.to_c()
+    ic = (C.c_int * 8)(*([int(x) for x in is_cons] + [0] * (8 - len(is_cons))))
+    lib().orc_mkflux_mf(C.byref(g), C.byref(p), _pp(sold), C.c_int(ncomp), _um3(sedge, geom.dim), _um3(flux, geom.dim),
+                        _um3(umac, geom.dim), _pp(force), _pp(mac_rhs), C.c_double(dt), C.c_int(int(is_vel)), ic)
+
+
+def update(geom, params, sold, ncomp, umac, sedge, flux, force, snew, dt, is_vel, is_cons):
+    g, p = geom.to_c(), params.to_c()
+    ic = (C.c_int * 8)(*([int(x) for x in is_cons] + [0] * (8 - len(is_cons))))
+    lib().orc_update_mf(C.byref(g), C.byref(p), _pp(sold), C.c_int(ncomp), _um3(umac, geom.dim), _um3(sedge, geom.dim),
+                        _um3(flux, geom.dim), _pp(force), _pp(snew), C.c_double(dt), C.c_int(int(is_vel)), ic)
+
+
+def make_at_halftime(geom, params, rhohalf, sold, snew):
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        lo_a = (C.c_int * 3)(*lo)
+        hi_a = (C.c_int * 3)(*hi)
+        lib().orc_make_at_halftime(rhohalf[ib].ctypes.data_as(C.POINTER(C.c_double)), sold[ib].ctypes.data_as(C.POINTER(C.c_double)),
+                                   snew[ib].ctypes.data_as(C.POINTER(C.c_double)), lo_a, hi_a, C.c_int(geom.dim), C.c_int(1), C.c_int(3))
+    fill_and_physbc(geom, params, rhohalf, 1, 1, 0, geom.dim, 1)
+
+
+def stagewise(geom, params, st, dt, mac_rel_eps=-1.0):
+    """The whole path with every intermediate kept (what the stage-wise GPU parity tests compare against)."""
+    dim, nscal = geom.dim, params.nscal
+    lapu = st.get("lapu") or mf_alloc(geom, 0, dim)
+    o = {}
+    o["vel_force_1"] = mf_alloc(geom, 1, dim)
+    mkvelforce(geom, params, o["vel_force_1"], st["ext_vel_force"], st["gp"], st["sold"], 3, nscal, lapu, 1.0)
+    o["umac_pred"] = [mf_alloc(geom, 1, 1, d, val=1.0e20) for d in range(dim)]
+    velpred(geom, params, st["uold"], o["umac_pred"], o["vel_force_1"], dt)
+    o["umac"] = [[a.copy(order='F') for a in o["umac_pred"][d]] for d in range(dim)]
+    mac_rhs = mf_alloc(geom, 1, 1)
+    o["mac_cycles"], o["mac_resnorm"], o["phi"] = macproject(geom, params, o["umac"], st["sold"], mac_rhs, mac_rel_eps)
+    o["scal_force_1"] = mf_alloc(geom, 1, nscal)
+    laps = mf_alloc(geom, 0, nscal)
+    mkscalforce(geom, params, o["scal_force_1"], st["ext_scal_force"], laps, 1.0)
+    o["sedge"] = [mf_alloc(geom, 0, nscal, d) for d in range(dim)]
+    o["sflux"] = [mf_alloc(geom, 0, nscal, d) for d in range(dim)]
+    divu = mf_alloc(geom, 1, 1)
+    is_cons_s = [1] + [0] * (nscal - 1)
+    mkflux(geom, params, st["sold"], nscal, o["sedge"], o["sflux"], o["umac"], o["scal_force_1"], divu, dt, False, is_cons_s)
+    o["scal_force_2"] = mf_alloc(geom, 1, nscal)
+    mkscalforce(geom, params, o["scal_force_2"], st["ext_scal_force"], laps, 0.0)
+    o["snew"] = mf_alloc(geom, 3, nscal)
+    update(geom, params, st["sold"], nscal, o["umac"], o["sedge"], o["sflux"], o["scal_force_2"], o["snew"], dt, False, is_cons_s)
+    o["rhohalf"] = mf_alloc(geom, 1, 1)
+    make_at_halftime(geom, params, o["rhohalf"], st["sold"], o["snew"])
+    o["uedge"] = [mf_alloc(geom, 0, dim, d) for d in range(dim)]
+    uflux = [mf_alloc(geom, 0, dim, d) for d in range(dim)]
+    mkflux(geom, params, st["uold"], dim, o["uedge"], uflux, o["umac"], o["vel_force_1"], mac_rhs, dt, True, [0] * dim)
+    o["vel_force_2"] = mf_alloc(geom, 1, dim)
+    mkvelforce(geom, params, o["vel_force_2"], st["ext_vel_force"], st["gp"], o["rhohalf"], 1, 1, lapu, 0.0)
+    o["unew"] = mf_alloc(geom, 3, dim)
+    update(geom, params, st["uold"], dim, o["umac"], o["uedge"], uflux, o["vel_force_2"], o["unew"], dt, True, [0] * dim)
+    return o

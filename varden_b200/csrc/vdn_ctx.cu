@@ -1,0 +1,390 @@
+// vdn_ctx.cu -- context, device field registry, path-boundary copies, profiler and the extern "C" ABI (include/vdn.h).
+#include "vdn_ctx.h"
+#include <algorithm>
+
+static std::string g_create_err;
+
+// ------------------------------------------------------------------------------------------
+// profiler: CUDA events on the launching stream, one (start, stop) pair per bracketed launch group
+// ------------------------------------------------------------------------------------------
+LaunchScope::LaunchScope(vdn_ctx *ctx, const char *name, double alg_bytes, int nlaunch) : c(ctx)
+{
+    c->launches += nlaunch;
+    if (!c->prof_on) return;
+    auto it = c->prof_idx.find(name);
+    if (it == c->prof_idx.end()) {
+        idx = (int)c->prof.size();
+        c->prof_idx[name] = idx;
+        ProfEntry e; e.name = name; c->prof.push_back(e);
+    } else idx = it->second;
+    c->prof[idx].launches += nlaunch;
+    c->prof[idx].bytes += alg_bytes;
+    auto get = [&]() { cudaEvent_t e; if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); } else VDN_CUDA(cudaEventCreate(&e)); return e; };
+    e0 = get(); e1 = get();
+    cudaEventRecord(e0, c->stream);
+}
+LaunchScope::~LaunchScope()
+{
+    if (idx < 0) return;
+    cudaEventRecord(e1, c->stream);
+    c->prof[idx].pending.emplace_back(e0, e1);
+    if (c->prof[idx].pending.size() > 4096) prof_collect(c);
+}
+void prof_collect(vdn_ctx *c)
+{
+    cudaStreamSynchronize(c->stream);
+    for (auto &p : c->prof) {
+        for (auto &pr : p.pending) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, pr.first, pr.second); p.ms += ms;
+            c->ev_pool.push_back(pr.first); c->ev_pool.push_back(pr.second);
+        }
+        p.pending.clear();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BC tables (define_bc_tower.f90:158-340), evaluated on the REGION faces
+// ------------------------------------------------------------------------------------------
+static void build_bc_tables(vdn_ctx *c)
+{
+    const int dm = c->dim, nscal = c->prm.nscal;
+    const int press = dm + nscal, extrap = press + 1;
+    for (int q = 0; q < 16; ++q) for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) c->adv_bc[q][d][s] = BC_INTERIOR;
+    for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) c->ell_bc[d][s] = ELL_INT;
+    for (int d = 0; d < dm; ++d) for (int s = 0; s < 2; ++s) {
+        const int p = c->geo.pbc[d][s];
+        auto set_vel = [&](int v) { for (int q = 0; q < dm; ++q) c->adv_bc[q][d][s] = v; };
+        auto set_scal = [&](int v) { for (int q = 0; q < nscal; ++q) c->adv_bc[dm + q][d][s] = v; };
+        if (p == BC_SLIP_WALL) {
+            set_vel(BC_HOEXTRAP); c->adv_bc[d][d][s] = BC_EXT_DIR; set_scal(BC_HOEXTRAP);
+            c->adv_bc[press][d][s] = BC_FOEXTRAP; c->adv_bc[extrap][d][s] = BC_FOEXTRAP; c->ell_bc[d][s] = ELL_NEU;
+        } else if (p == BC_NO_SLIP_WALL) {
+            set_vel(BC_EXT_DIR); set_scal(BC_HOEXTRAP);
+            c->adv_bc[press][d][s] = BC_FOEXTRAP; c->adv_bc[extrap][d][s] = BC_FOEXTRAP; c->ell_bc[d][s] = ELL_NEU;
+        } else if (p == BC_INLET) {
+            set_vel(BC_EXT_DIR); set_scal(BC_EXT_DIR);
+            c->adv_bc[press][d][s] = BC_FOEXTRAP; c->adv_bc[extrap][d][s] = BC_FOEXTRAP; c->ell_bc[d][s] = ELL_NEU;
+        } else if (p == BC_OUTLET) {
+            set_vel(BC_FOEXTRAP); set_scal(BC_FOEXTRAP);
+            c->adv_bc[press][d][s] = BC_EXT_DIR; c->adv_bc[extrap][d][s] = BC_FOEXTRAP; c->ell_bc[d][s] = ELL_DIR;
+        } else if (p == BC_SYMMETRY) {
+            set_vel(BC_REFLECT_EVEN); c->adv_bc[d][d][s] = BC_REFLECT_ODD; set_scal(BC_REFLECT_EVEN);
+            c->adv_bc[press][d][s] = BC_EXT_DIR; c->adv_bc[extrap][d][s] = BC_REFLECT_EVEN; c->ell_bc[d][s] = ELL_NEU;
+        } else if (p == BC_PERIODIC) {
+            c->ell_bc[d][s] = ELL_PER;
+        }
+    }
+}
+
+// sng = storage ghost width (>= ng).  RH and BETA_* are stored in the multigrid's padded layout (sng = 1, extent n+2
+// in every direction, which also holds the n+1 faces) so that MG level 0 can alias them without copies.
+static void alloc_field(vdn_ctx *c, int id, int ng, int nc, int fdir, int sng = -1)
+{
+    DField &f = c->f[id];
+    f.ng = ng; f.nc = nc; f.fdir = fdir;
+    const bool padded = sng >= 0;
+    if (sng < 0) sng = ng;
+    for (int d = 0; d < 3; ++d) {
+        f.ngd[d] = d < c->dim ? sng : 0;
+        f.ext[d] = d < c->dim ? c->geo.n[d] + 2 * sng + ((d == fdir && !padded) ? 1 : 0) : 1;
+    }
+    f.sy = f.ext[0]; f.sz = (long)f.ext[0] * f.ext[1]; f.cs = f.sz * f.ext[2];
+    f.bytes = (size_t)f.cs * nc * sizeof(double);
+    VDN_CUDA(cudaMalloc(&f.base, f.bytes));
+    VDN_CUDA(cudaMemsetAsync(f.base, 0, f.bytes, c->stream));
+}
+
+static void ctx_build(vdn_ctx *c, const vdn_params *prm, int dim, int nboxes, const int *box_lo, const int *box_hi,
+                      const int *dom_lo, const int *dom_hi, const int *phys_bc, const double *dx, int device)
+{
+    VDN_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+    VDN_REQUIRE(nboxes >= 1, "need at least one box");
+    VDN_REQUIRE(prm->nscal >= 1 && prm->nscal <= 8, "nscal out of range");
+    VDN_REQUIRE(prm->stencil_order == 2, "only stencil_order = 2 is implemented");
+    VDN_REQUIRE(prm->slope_order == 0 || prm->slope_order == 2 || prm->slope_order == 4, "slope_order must be 0, 2 or 4");
+    c->prm = *prm; c->dim = dim; c->device = device; c->nboxes = nboxes;
+    int ndev = 0;
+    VDN_CUDA(cudaGetDeviceCount(&ndev));
+    VDN_REQUIRE(ndev > 0, "no CUDA device: the hot path has no CPU fallback");
+    VDN_REQUIRE(device >= 0 && device < ndev, "bad device ordinal");
+    VDN_CUDA(cudaSetDevice(device));
+    VDN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int d = 0; d < 3; ++d) {
+        c->dom_lo[d] = d < dim ? dom_lo[d] : 0; c->dom_hi[d] = d < dim ? dom_hi[d] : 0;
+        c->dom_bc[d][0] = d < dim ? phys_bc[d * 2] : BC_INTERIOR; c->dom_bc[d][1] = d < dim ? phys_bc[d * 2 + 1] : BC_INTERIOR;
+        c->rlo[d] = 1 << 30; c->rhi[d] = -(1 << 30);
+    }
+    c->box_lo.resize(nboxes); c->box_hi.resize(nboxes);
+    long cells = 0;
+    for (int b = 0; b < nboxes; ++b) {
+        long bc = 1;
+        for (int d = 0; d < 3; ++d) {
+            c->box_lo[b][d] = d < dim ? box_lo[b * 3 + d] : 0; c->box_hi[b][d] = d < dim ? box_hi[b * 3 + d] : 0;
+            VDN_REQUIRE(c->box_hi[b][d] >= c->box_lo[b][d], "empty box");
+            c->rlo[d] = std::min(c->rlo[d], c->box_lo[b][d]); c->rhi[d] = std::max(c->rhi[d], c->box_hi[b][d]);
+            bc *= c->box_hi[b][d] - c->box_lo[b][d] + 1;
+        }
+        cells += bc;
+    }
+    Geo &g = c->geo;
+    memset(&g, 0, sizeof g);
+    g.dim = dim;
+    long rc = 1;
+    for (int d = 0; d < 3; ++d) { g.n[d] = c->rhi[d] - c->rlo[d] + 1; rc *= g.n[d]; g.h[d] = d < dim ? dx[d] : 1.0; }
+    VDN_REQUIRE(rc == cells, "the local boxes must tile their bounding box (tensor-product layout)");
+    // tensor-product cuts
+    for (int d = 0; d < 3; ++d) {
+        std::vector<int> cuts;
+        for (int b = 0; b < nboxes; ++b) cuts.push_back(c->box_lo[b][d] - c->rlo[d]);
+        std::sort(cuts.begin(), cuts.end()); cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+        VDN_REQUIRE((int)cuts.size() <= VDN_MAXCUT, "too many boxes per direction on one rank");
+        g.nb[d] = (int)cuts.size();
+        for (int q = 0; q < g.nb[d]; ++q) g.cut[d][q] = cuts[q];
+        g.cut[d][g.nb[d]] = g.n[d];
+    }
+    VDN_REQUIRE(g.nb[0] * g.nb[1] * g.nb[2] == nboxes, "boxes are not a tensor-product chop of the region");
+    for (int b = 0; b < nboxes; ++b) for (int d = 0; d < 3; ++d) {
+        int l = c->box_lo[b][d] - c->rlo[d], h = c->box_hi[b][d] - c->rlo[d];
+        int q = g.box1(d, l);
+        VDN_REQUIRE(g.cut[d][q] == l && g.cut[d][q + 1] == h + 1, "boxes are not a tensor-product chop of the region");
+    }
+    // region-face BCs (single rank: the region is the domain; vdn_ctx_set_comm refines this)
+    for (int d = 0; d < 3; ++d) {
+        for (int s = 0; s < 2; ++s) {
+            bool at_dom = s == 0 ? (c->rlo[d] == c->dom_lo[d]) : (c->rhi[d] == c->dom_hi[d]);
+            g.pbc[d][s] = (d < dim && at_dom) ? c->dom_bc[d][s] : BC_INTERIOR;
+        }
+        bool per = d < dim && c->dom_bc[d][0] == BC_PERIODIC;
+        if (per) VDN_REQUIRE(c->dom_bc[d][1] == BC_PERIODIC, "periodic BC must be set on both sides");
+        c->wrap[d] = per && c->rlo[d] == c->dom_lo[d] && c->rhi[d] == c->dom_hi[d];
+        if (d < dim) VDN_REQUIRE(g.n[d] >= 4, "region must be at least 4 cells wide in every direction");
+    }
+    build_bc_tables(c);
+
+    const int dm = dim, ns = prm->nscal;
+    alloc_field(c, VDN_UOLD, 3, dm, -1); alloc_field(c, VDN_SOLD, 3, ns, -1);
+    alloc_field(c, VDN_UNEW, 3, dm, -1); alloc_field(c, VDN_SNEW, 3, ns, -1);
+    alloc_field(c, VDN_GP, 1, dm, -1);
+    alloc_field(c, VDN_EXT_VEL_FORCE, 1, dm, -1); alloc_field(c, VDN_EXT_SCAL_FORCE, 1, ns, -1);
+    alloc_field(c, VDN_LAPU, 0, dm, -1);
+    for (int d = 0; d < dm; ++d) alloc_field(c, VDN_UMAC_X + d, 1, 1, d);
+    alloc_field(c, VDN_MAC_RHS, 1, 1, -1); alloc_field(c, VDN_RHOHALF, 1, 1, -1);
+    alloc_field(c, VDN_VEL_FORCE, 1, dm, -1); alloc_field(c, VDN_SCAL_FORCE, 1, ns, -1);
+    alloc_field(c, VDN_RH, 0, 1, -1, 1); alloc_field(c, VDN_PHI, 1, 1, -1);
+    for (int d = 0; d < dm; ++d) alloc_field(c, VDN_BETA_X + d, 0, 1, d, 1);
+    // edge states: the scalar and velocity phases never overlap, so SEDGE aliases the first nscal comps of UEDGE
+    const int ne = std::max(dm, ns);
+    for (int d = 0; d < dm; ++d) {
+        alloc_field(c, VDN_UEDGE_X + d, 0, ne, d);
+        c->f[VDN_SEDGE_X + d] = c->f[VDN_UEDGE_X + d]; c->f[VDN_SEDGE_X + d].nc = ns;
+        c->f[VDN_UEDGE_X + d].nc = dm;
+        alloc_field(c, VDN_SFLUX_X + d, 0, 1, d);        // only the conservative comp (density) carries a flux
+    }
+    // Godunov scratch arena (S-layout: cells -1..n, faces 0..n)
+    c->nscr = 36;
+    c->s_sy = g.n[0] + 2; c->s_sz = (long)c->s_sy * (g.n[1] + 2);
+    c->s_n = c->s_sz * (dim == 3 ? g.n[2] + 2 : 1);
+    c->s_off = 1 + c->s_sy + (dim == 3 ? c->s_sz : 0);
+    VDN_CUDA(cudaMalloc(&c->scratch, sizeof(double) * c->s_n * c->nscr));
+    VDN_CUDA(cudaMemsetAsync(c->scratch, 0, sizeof(double) * c->s_n * c->nscr, c->stream));
+    VDN_CUDA(cudaMalloc(&c->d_eps, sizeof(double) * std::max(nboxes, 1)));
+    VDN_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 64));
+    VDN_CUDA(cudaMallocHost(&c->h_pin, sizeof(double) * 64));
+    // umac = 1.d20 (advance_timestep.f90:76-77)
+    for (int d = 0; d < dm; ++d) st_setval(c, VDN_UMAC_X + d, 1.0e20);
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+static void ctx_free(vdn_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->mg) mg_destroy(c->mg);
+    if (c->comm) comm_destroy(c->comm);
+    for (int i = 0; i < VDN_NFIELDS; ++i) {
+        if (i >= VDN_SEDGE_X && i <= VDN_SEDGE_Z) continue;      // aliases UEDGE
+        if (c->f[i].base) cudaFree(c->f[i].base);
+    }
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->d_eps) cudaFree(c->d_eps);
+    if (c->d_red) cudaFree(c->d_red);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->stage) cudaFreeHost(c->stage);
+    for (auto &p : c->prof) for (auto &pr : p.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// copy between a host box array and the region array: valid cells of the box plus the ghost cells that lie
+// outside the region's valid area (ghosts inside it are other boxes' valid cells).
+static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int ncomp, bool upload)
+{
+    VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS, "bad field id");
+    VDN_REQUIRE(ibox >= 0 && ibox < c->nboxes, "bad box index");
+    DField &f = c->f[field];
+    VDN_REQUIRE(f.base != nullptr, "field not allocated for this dimension");
+    VDN_REQUIRE(ng == f.ng && ncomp == f.nc, "host (ng, ncomp) does not match the field's fixed layout");
+    VDN_CUDA(cudaSetDevice(c->device));
+    int hext[3], clo[3], chi[3], hlo[3];
+    for (int d = 0; d < 3; ++d) {
+        const int lo = c->box_lo[ibox][d], hi = c->box_hi[ibox][d];
+        if (d >= c->dim) { hext[d] = 1; clo[d] = 0; chi[d] = 0; hlo[d] = 0; continue; }
+        const int nod = (d == f.fdir) ? 1 : 0;
+        hext[d] = hi - lo + 1 + 2 * ng + nod; hlo[d] = lo - ng;
+        clo[d] = lo - (lo == c->rlo[d] ? ng : 0);
+        chi[d] = hi + nod + (hi == c->rhi[d] ? ng : 0);
+    }
+    cudaMemcpy3DParms p; memset(&p, 0, sizeof p);
+    const size_t hplane = (size_t)hext[0] * hext[1], dplane = (size_t)f.ext[0] * f.ext[1];
+    for (int comp = 0; comp < ncomp; ++comp) {
+        double *hp = host + (size_t)comp * hplane * hext[2];
+        double *dp = f.base + (size_t)comp * f.cs;
+        cudaPitchedPtr hptr = make_cudaPitchedPtr(hp, sizeof(double) * hext[0], hext[0], hext[1]);
+        cudaPitchedPtr dptr = make_cudaPitchedPtr(dp, sizeof(double) * f.ext[0], f.ext[0], f.ext[1]);
+        cudaPos hpos = make_cudaPos(sizeof(double) * (clo[0] - hlo[0]), clo[1] - hlo[1], clo[2] - hlo[2]);
+        cudaPos dpos = make_cudaPos(sizeof(double) * (clo[0] - c->rlo[0] + f.ngd[0]), clo[1] - c->rlo[1] + f.ngd[1], clo[2] - c->rlo[2] + f.ngd[2]);
+        p.extent = make_cudaExtent(sizeof(double) * (chi[0] - clo[0] + 1), chi[1] - clo[1] + 1, chi[2] - clo[2] + 1);
+        if (upload) { p.srcPtr = hptr; p.srcPos = hpos; p.dstPtr = dptr; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+        else        { p.srcPtr = dptr; p.srcPos = dpos; p.dstPtr = hptr; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+        VDN_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+        (void)hplane; (void)dplane;
+    }
+    if (!upload) VDN_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// one pass of the hot path, advance_timestep.f90:95-124
+static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles, double *resnorm)
+{
+    // advance_timestep.f90:76-77 builds umac = 1.d20 every step; here the 1.d20 poison is set once at context creation:
+    // the only faces that keep it (ghost faces outside non-periodic boundaries) are never written afterwards.
+    // advance_premac (advance_premac.f90:44-51)
+    st_mkvelforce(c, VDN_SOLD, 1.0);
+    st_velpred(c, dt);
+    // macproject (macproject.f90:20-133)
+    st_divumac(c, false);
+    st_mk_mac_coeffs(c);
+    st_setval(c, VDN_PHI, 0.0);
+    int rc = st_mac_solve(c, mac_rel_eps > 0 ? mac_rel_eps : 1.0e-10, -1.0, cycles, resnorm);
+    st_mkumac(c);
+    // scalar_advance (scalar_advance.f90:96-119)
+    st_mkscalforce(c, 1.0);
+    st_mkflux(c, 0, dt);
+    st_mkscalforce(c, 0.0);
+    st_update(c, 0, dt);
+    // make_at_halftime (advance_timestep.f90:114)
+    st_make_at_halftime(c);
+    // velocity_advance (velocity_advance.f90:70-93)
+    st_mkvelforce(c, VDN_SOLD, 1.0);
+    st_mkflux(c, 1, dt);
+    st_mkvelforce(c, VDN_RHOHALF, 0.0);
+    st_update(c, 1, dt);
+    if (rc != 0) throw VdnError("MAC multigrid did not converge within mg_max_cycles");
+}
+
+// ------------------------------------------------------------------------------------------
+// extern "C" ABI
+// ------------------------------------------------------------------------------------------
+#define VDN_TRY(ctx, body) \
+    if (!(ctx)) return 1; \
+    try { VDN_CUDA(cudaSetDevice((ctx)->device)); body; return 0; } \
+    catch (const std::exception &e) { (ctx)->err = e.what(); return 1; } \
+    catch (...) { (ctx)->err = "unknown error"; return 1; }
+
+extern "C" {
+
+void vdn_params_default(vdn_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->nscal = 2; p->slope_order = 4; p->use_minion = 0; p->boussinesq = 0; p->stencil_order = 2;
+    p->mg_verbose = 0; p->mg_nu1 = 2; p->mg_nu2 = 2; p->mg_max_cycles = 100; p->mg_max_bottom_iter = 100;
+    p->mg_bottom_eps = 1.0e-3; p->visc_coef = 0.0; p->diff_coef = 0.0;
+}
+
+int vdn_ctx_create(const vdn_params *prm, int dim, int nboxes, const int *box_lo, const int *box_hi,
+                   const int *dom_lo, const int *dom_hi, const int *phys_bc, const double *dx, int device, vdn_ctx **out)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    vdn_ctx *c = new vdn_ctx();
+    try { ctx_build(c, prm, dim, nboxes, box_lo, box_hi, dom_lo, dom_hi, phys_bc, dx, device); *out = c; return 0; }
+    catch (const std::exception &e) { g_create_err = e.what(); ctx_free(c); return 1; }
+}
+void vdn_ctx_destroy(vdn_ctx *ctx) { ctx_free(ctx); }
+const char *vdn_last_error(const vdn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int vdn_field_upload(vdn_ctx *ctx, int field, int ibox, const double *host, int ng, int ncomp)
+{ VDN_TRY(ctx, box_copy(ctx, field, ibox, const_cast<double *>(host), ng, ncomp, true)) }
+int vdn_field_download(vdn_ctx *ctx, int field, int ibox, double *host, int ng, int ncomp)
+{ VDN_TRY(ctx, box_copy(ctx, field, ibox, host, ng, ncomp, false)) }
+int vdn_field_setval(vdn_ctx *ctx, int field, double val)
+{ VDN_TRY(ctx, { VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS && ctx->f[field].base, "bad field id"); st_setval(ctx, field, val); }) }
+int vdn_sync(vdn_ctx *ctx) { VDN_TRY(ctx, VDN_CUDA(cudaStreamSynchronize(ctx->stream))) }
+
+int vdn_fill_boundary(vdn_ctx *ctx, int field)
+{ VDN_TRY(ctx, { VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS && ctx->f[field].base, "bad field id"); st_fill_boundary(ctx, field); }) }
+int vdn_fill_and_physbc(vdn_ctx *ctx, int field, int bccomp, int same_boundary)
+{ VDN_TRY(ctx, { VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS && ctx->f[field].base, "bad field id");
+                 VDN_REQUIRE(bccomp >= 0 && bccomp + (same_boundary ? 1 : ctx->f[field].nc) <= ctx->dim + ctx->prm.nscal + 2, "bccomp out of range");
+                 st_fill_boundary(ctx, field); st_physbc(ctx, field, bccomp, same_boundary != 0); }) }
+
+int vdn_mkvelforce(vdn_ctx *ctx, int rho_field, double visc_fac) { VDN_TRY(ctx, st_mkvelforce(ctx, rho_field, visc_fac)) }
+int vdn_mkscalforce(vdn_ctx *ctx, double diff_fac) { VDN_TRY(ctx, st_mkscalforce(ctx, diff_fac)) }
+int vdn_velpred(vdn_ctx *ctx, double dt) { VDN_TRY(ctx, st_velpred(ctx, dt)) }
+int vdn_mkflux(vdn_ctx *ctx, int is_vel, double dt) { VDN_TRY(ctx, st_mkflux(ctx, is_vel, dt)) }
+int vdn_update(vdn_ctx *ctx, int is_vel, double dt) { VDN_TRY(ctx, st_update(ctx, is_vel, dt)) }
+int vdn_make_at_halftime(vdn_ctx *ctx) { VDN_TRY(ctx, st_make_at_halftime(ctx)) }
+
+int vdn_divumac(vdn_ctx *ctx, double *rhmax)
+{ VDN_TRY(ctx, { double v = st_divumac(ctx, rhmax != nullptr); if (rhmax) *rhmax = v; }) }
+int vdn_mk_mac_coeffs(vdn_ctx *ctx) { VDN_TRY(ctx, st_mk_mac_coeffs(ctx)) }
+int vdn_mkumac(vdn_ctx *ctx) { VDN_TRY(ctx, st_mkumac(ctx)) }
+
+int vdn_mac_solve(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, double *resnorm)
+{
+    if (!ctx) return 1;
+    try {
+        VDN_CUDA(cudaSetDevice(ctx->device));
+        int rc = st_mac_solve(ctx, rel_eps > 0 ? rel_eps : 1.0e-10, abs_eps, ncycles, resnorm);
+        if (rc) { ctx->err = "MAC multigrid did not converge within mg_max_cycles"; return 2; }
+        return 0;
+    } catch (const std::exception &e) { ctx->err = e.what(); return 1; }
+}
+
+int vdn_macproject(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, double *resnorm)
+{
+    if (!ctx) return 1;
+    try {
+        VDN_CUDA(cudaSetDevice(ctx->device));
+        // macproject.f90:60-67 computes umac_norm only for the (overridden) abs tolerance; skipped like the reference's "HACK"
+        st_divumac(ctx, false);
+        st_mk_mac_coeffs(ctx);
+        st_setval(ctx, VDN_PHI, 0.0);
+        int rc = st_mac_solve(ctx, rel_eps > 0 ? rel_eps : 1.0e-10, abs_eps, ncycles, resnorm);
+        st_mkumac(ctx);
+        if (rc) { ctx->err = "MAC multigrid did not converge within mg_max_cycles"; return 2; }
+        return 0;
+    } catch (const std::exception &e) { ctx->err = e.what(); return 1; }
+}
+
+int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, double *mac_resnorm)
+{ VDN_TRY(ctx, advance_impl(ctx, dt, mac_rel_eps, mac_cycles, mac_resnorm)) }
+
+int vdn_prof_enable(vdn_ctx *ctx, int on)
+{ VDN_TRY(ctx, { prof_collect(ctx); ctx->prof.clear(); ctx->prof_idx.clear(); ctx->prof_on = on != 0; }) }
+int vdn_prof_count(vdn_ctx *ctx) { if (!ctx) return 0; prof_collect(ctx); return (int)ctx->prof.size(); }
+int vdn_prof_get(vdn_ctx *ctx, int idx, char *name, long long *launches, double *ms, double *alg_bytes)
+{
+    if (!ctx || idx < 0 || idx >= (int)ctx->prof.size()) return 1;
+    prof_collect(ctx);
+    const ProfEntry &p = ctx->prof[idx];
+    if (name) { strncpy(name, p.name.c_str(), 63); name[63] = 0; }
+    if (launches) *launches = p.launches;
+    if (ms) *ms = p.ms;
+    if (alg_bytes) *alg_bytes = p.bytes;
+    return 0;
+}
+long long vdn_launch_count(vdn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

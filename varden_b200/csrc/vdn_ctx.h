@@ -1,0 +1,82 @@
+// vdn_ctx.h -- host-side context of the B200 VARDEN hot path.
+#pragma once
+#include "vdn_common.cuh"
+#include <array>
+
+struct Range { int lo[3], hi[3]; };   // inclusive local index range
+
+struct ProfEntry { std::string name; long long launches = 0; double ms = 0.0; double bytes = 0.0;
+                   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; };
+
+struct MG;      // vdn_mg.cu
+struct Comm;    // vdn_comm.cu
+
+struct vdn_ctx {
+    vdn_params prm;
+    int dim = 3, device = 0;
+    cudaStream_t stream = nullptr;
+    Geo geo;
+    int nboxes = 0;
+    std::vector<std::array<int, 3>> box_lo, box_hi;    // global indices of the local reference boxes
+    int rlo[3], rhi[3];                                 // region (global indices)
+    int dom_lo[3], dom_hi[3], dom_bc[3][2];
+    DField f[VDN_NFIELDS];
+    int adv_bc[16][3][2];                               // [comp][d][side] on the region faces
+    int ell_bc[3][2];                                   // pressure elliptic BC on the region faces
+    bool wrap[3];                                       // periodic and owned by this rank alone in that direction
+    // Godunov scratch arena: NSCR arrays in the S-layout (cells -1..n, faces 0..n)
+    double *scratch = nullptr; int nscr = 0; long s_sy = 0, s_sz = 0, s_n = 0, s_off = 0;
+    double *d_eps = nullptr;                            // per-box eps
+    double *d_red = nullptr;                            // reduction scratch (device)
+    double *h_pin = nullptr;                            // pinned host scalars
+    double *stage = nullptr; size_t stage_bytes = 0;    // pinned staging buffer for pageable uploads
+    std::string err;
+    long long launches = 0;
+    bool prof_on = false;
+    std::vector<ProfEntry> prof;
+    std::map<std::string, int> prof_idx;
+    std::vector<cudaEvent_t> ev_pool;
+    MG *mg = nullptr;
+    Comm *comm = nullptr;
+
+    View S(int q) const { View v; v.sy = s_sy; v.sz = s_sz; v.cs = s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
+    long ncells() const { return (long)geo.n[0] * geo.n[1] * geo.n[2]; }
+};
+
+// ---- profiling-aware launch bracket ----
+struct LaunchScope {
+    vdn_ctx *c; int idx = -1; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LaunchScope(vdn_ctx *ctx, const char *name, double alg_bytes, int nlaunch = 1);
+    ~LaunchScope();
+};
+void prof_collect(vdn_ctx *c);
+
+static inline dim3 grid3(const Range &r, dim3 b)
+{
+    return dim3(cdiv(r.hi[0] - r.lo[0] + 1, b.x), cdiv(r.hi[1] - r.lo[1] + 1, b.y), cdiv(r.hi[2] - r.lo[2] + 1, b.z));
+}
+static inline Range mk_range(int l0, int h0, int l1, int h1, int l2, int h2)
+{
+    Range r; r.lo[0] = l0; r.hi[0] = h0; r.lo[1] = l1; r.hi[1] = h1; r.lo[2] = l2; r.hi[2] = h2; return r;
+}
+
+// ---- stage implementations (each in its own .cu) ----
+void st_fill_boundary(vdn_ctx *c, int field);
+void st_physbc(vdn_ctx *c, int field, int bccomp, bool same_boundary);
+void st_mkvelforce(vdn_ctx *c, int rho_field, double visc_fac);
+void st_mkscalforce(vdn_ctx *c, double diff_fac);
+void st_velpred(vdn_ctx *c, double dt);
+void st_mkflux(vdn_ctx *c, int is_vel, double dt);
+void st_update(vdn_ctx *c, int is_vel, double dt);
+void st_make_at_halftime(vdn_ctx *c);
+double st_divumac(vdn_ctx *c, bool want_norm);
+void st_mk_mac_coeffs(vdn_ctx *c);
+void st_mkumac(vdn_ctx *c);
+int  st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm);
+void st_setval(vdn_ctx *c, int field, double val);
+double st_absmax_valid(vdn_ctx *c, int field);           // norm_inf over valid cells/faces, all comps
+void mg_destroy(MG *mg);
+void comm_destroy(Comm *cm);
+void comm_exchange(vdn_ctx *c, int field, int d);         // halo exchange along d with the neighbour ranks (vdn_comm.cu)
+double comm_allreduce_max(vdn_ctx *c, double v);
+double comm_allreduce_sum(vdn_ctx *c, double v);

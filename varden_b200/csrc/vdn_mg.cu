@@ -1,0 +1,374 @@
+// vdn_mg.cu -- MAC multigrid on the device: solves -div(beta grad phi) = rh on the rank's region.
+//
+// Replaces mac_multigrid (mac_multigrid.f90:19-66) -> ml_cc_solve (FBoxLib F_MG, third party, absent from the
+// reference tree).  The algorithm is the one that call selects: V-cycles of red-black Gauss-Seidel (nu1 = nu2 = 2),
+// cell-average restriction, piecewise-constant prolongation, BiCGStab bottom solve (bottom_solver_eps = 1e-3),
+// stencil_order = 2 Dirichlet ghost, stop at |r|_inf <= eps*|rh|_inf.  F_MG's source is not available, so results
+// are matched to the solver tolerance (parity bar: 10x eps), not bit-wise.
+//
+// Layout: every level uses one padded layout (n+2 per direction, index (i+1) + sy*(j+1) + sz*(k+1)) shared by
+// phi, rhs, res and the three face-coefficient arrays (b_d[idx] = beta on the LOW d-face of cell idx), so a
+// stencil needs one index.  Level 0 aliases the context's PHI / RH / BETA_* fields (no copies).
+// Physical BCs are synthesised in the stencil (Neumann: no flux; Dirichlet: 3*phi0 - phi1/3 one-sided), periodic
+// directions owned by one rank wrap by index, so a single GPU needs no ghost-fill launches at all.
+#include "vdn_ctx.h"
+
+enum : int { M_GHOST = 0, M_NEU = 1, M_DIR = 2, M_WRAP = 3 };
+
+struct Lev {
+    int n[3];
+    long s[3];              // strides (1, sy, sz)
+    long ntot, off;         // allocation size and offset of cell (0,0,0)
+    double h2inv[3];
+    int mode[3][2];
+    int par0;               // parity of the global index of local cell (0,0,0)
+    double *phi, *rhs, *res, *b[3];
+};
+
+struct MG {
+    int dim = 3, nlev = 0;
+    std::vector<Lev> L;
+    std::vector<double *> owned;     // device allocations to free
+    bool singular = false;
+    double *bot[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // BiCGStab vectors on the bottom level
+    double *d_norm = nullptr;
+    double h0[3];
+};
+
+namespace {
+
+const dim3 BLK(64, 4, 1);
+
+template <int DIM>
+__device__ __forceinline__ void cell_op(const Lev &L, const double *__restrict__ x, long c, const int (&ix)[3], double &Ax, double &dg)
+{
+    const double x0 = x[c];
+    double a = 0.0, g = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const long st = L.s[d];
+        const double h2 = L.h2inv[d];
+        const double blo = L.b[d][c], bhi = L.b[d][c + st];
+        const bool at_lo = ix[d] == 0, at_hi = ix[d] == L.n[d] - 1;
+        const int mlo = L.mode[d][0], mhi = L.mode[d][1];
+        if (at_lo && mlo == M_NEU) { }
+        else if (at_lo && mlo == M_DIR) { a += blo * (3.0 * x0 - x[c + st] / 3.0) * h2; g += 3.0 * blo * h2; }
+        else { const double xm = (at_lo && mlo == M_WRAP) ? x[c + (long)(L.n[d] - 1) * st] : x[c - st]; a += blo * (x0 - xm) * h2; g += blo * h2; }
+        if (at_hi && mhi == M_NEU) { }
+        else if (at_hi && mhi == M_DIR) { a += bhi * (3.0 * x0 - x[c - st] / 3.0) * h2; g += 3.0 * bhi * h2; }
+        else { const double xp = (at_hi && mhi == M_WRAP) ? x[c - (long)(L.n[d] - 1) * st] : x[c + st]; a += bhi * (x0 - xp) * h2; g += bhi * h2; }
+    }
+    Ax = a; dg = g;
+}
+
+// one colour half-sweep; thread per colour cell
+template <int DIM>
+__global__ void k_gsrb(Lev L, int color)
+{
+    const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (j >= L.n[1]) return;
+    const int i = 2 * i2 + ((j + k + color + L.par0) & 1);
+    if (i >= L.n[0]) return;
+    const long c = L.off + i + L.s[1] * j + L.s[2] * k;
+    const int ix[3] = { i, j, k };
+    double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+    if (dg != 0.0) L.phi[c] += (L.rhs[c] - Ax) / dg;
+}
+
+// res = rhs - A phi; optional inf-norm via atomicMax on the bit pattern
+template <int DIM>
+__global__ void k_residual(Lev L, double *nrm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    double r = 0.0;
+    if (i < L.n[0] && j < L.n[1]) {
+        const long c = L.off + i + L.s[1] * j + L.s[2] * k;
+        const int ix[3] = { i, j, k };
+        double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+        r = L.rhs[c] - Ax;
+        L.res[c] = r;
+        r = fabs(r);
+    }
+    if (nrm) {
+        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && r > 0.0)
+            atomicMax((unsigned long long *)nrm, (unsigned long long)__double_as_longlong(r));
+    }
+}
+
+// coarse rhs = average of the fine residual; coarse phi = 0
+template <int DIM>
+__global__ void k_restrict(Lev F, Lev C)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= C.n[0] || j >= C.n[1]) return;
+    const long cf = F.off + 2 * i + F.s[1] * (2 * j) + F.s[2] * (DIM == 3 ? 2 * k : 0);
+    double s = F.res[cf] + F.res[cf + 1] + F.res[cf + F.s[1]] + F.res[cf + F.s[1] + 1];
+    if (DIM == 3) s += F.res[cf + F.s[2]] + F.res[cf + F.s[2] + 1] + F.res[cf + F.s[2] + F.s[1]] + F.res[cf + F.s[2] + F.s[1] + 1];
+    const long cc = C.off + i + C.s[1] * j + C.s[2] * k;
+    C.rhs[cc] = s * (DIM == 3 ? 0.125 : 0.25);
+    C.phi[cc] = 0.0;
+}
+
+// fine phi += piecewise-constant prolongation of coarse phi
+template <int DIM>
+__global__ void k_prolong(Lev F, Lev C)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= F.n[0] || j >= F.n[1]) return;
+    const long cf = F.off + i + F.s[1] * j + F.s[2] * k;
+    const long cc = C.off + (i >> 1) + C.s[1] * (j >> 1) + C.s[2] * (DIM == 3 ? (k >> 1) : 0);
+    F.phi[cf] += C.phi[cc];
+}
+
+// coarse face coefficient = arithmetic mean of the fine faces it covers
+template <int DIM>
+__global__ void k_coarsen_beta(Lev F, Lev C, int d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= C.n[0] + (d == 0) || j >= C.n[1] + (d == 1)) return;
+    const long cf = F.off + 2 * i + F.s[1] * (2 * j) + F.s[2] * (DIM == 3 ? 2 * k : 0);
+    double s;
+    if (DIM == 2) {
+        const long t = F.s[1 - d];
+        s = 0.5 * (F.b[d][cf] + F.b[d][cf + t]);
+    } else {
+        const long ta = F.s[(d + 1) % 3], tb = F.s[(d + 2) % 3];
+        s = 0.25 * (F.b[d][cf] + F.b[d][cf + ta] + F.b[d][cf + tb] + F.b[d][cf + ta + tb]);
+    }
+    C.b[d][C.off + i + C.s[1] * j + C.s[2] * k] = s;
+}
+
+// ---- bottom solver: BiCGStab in ONE CTA (the coarsest level is a handful of cells); dot products use
+// warp-shuffle + shared-memory block reductions ----
+__device__ double block_sum(double v, double *sm)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double t = (l < nw) ? sm[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;      // every thread of every warp holds the total
+}
+struct BotVec { double *r, *rh, *p, *v, *s, *t; };
+
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_bottom(Lev L, BotVec w, int maxit, double eps, int singular)
+{
+    __shared__ double sm[32];
+    const long nc = (long)L.n[0] * L.n[1] * L.n[2];
+    const int nt = blockDim.x, tid = threadIdx.x;
+#define CELL(q, c, ix) const int ix##0 = (int)((q) % L.n[0]), ix##1 = (int)(((q) / L.n[0]) % L.n[1]), ix##2 = (int)((q) / ((long)L.n[0] * L.n[1])); \
+                       const long c = L.off + ix##0 + L.s[1] * ix##1 + L.s[2] * ix##2; const int ix[3] = { ix##0, ix##1, ix##2 };
+    if (singular) {         // project the null space out of the right-hand side
+        double s = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; s += L.rhs[c]; }
+        s = block_sum(s, sm) / (double)nc;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.rhs[c] -= s; }
+    }
+    double bn = 0.0;
+    for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; const double b = L.rhs[c]; L.phi[c] = 0.0; w.r[c] = b; w.rh[c] = b; w.p[c] = b; bn += b * b; }
+    bn = sqrt(block_sum(bn, sm));
+    double rho = 1.0, alpha = 1.0, omega = 1.0;
+    if (bn > 0.0)
+    for (int it = 0; it < maxit; ++it) {
+        double rho1 = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; rho1 += w.rh[c] * w.r[c]; }
+        rho1 = block_sum(rho1, sm);
+        if (rho1 == 0.0) break;
+        if (it > 0) {
+            const double beta = (rho1 / rho) * (alpha / omega);
+            for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; w.p[c] = w.r[c] + beta * (w.p[c] - omega * w.v[c]); }
+        }
+        __syncthreads();
+        double den = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) double Ax, dg; cell_op<DIM>(L, w.p, c, ix, Ax, dg); w.v[c] = Ax; den += w.rh[c] * Ax; }
+        den = block_sum(den, sm);
+        if (den == 0.0) break;
+        alpha = rho1 / den;
+        double sn = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; const double s = w.r[c] - alpha * w.v[c]; w.s[c] = s; sn += s * s; }
+        sn = sqrt(block_sum(sn, sm));
+        if (sn <= eps * bn) { for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] += alpha * w.p[c]; } break; }
+        __syncthreads();
+        double ts = 0.0, tt = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) double Ax, dg; cell_op<DIM>(L, w.s, c, ix, Ax, dg); w.t[c] = Ax; ts += Ax * w.s[c]; tt += Ax * Ax; }
+        ts = block_sum(ts, sm); tt = block_sum(tt, sm);
+        if (tt == 0.0) { for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] += alpha * w.p[c]; } break; }
+        omega = ts / tt;
+        double rn = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] += alpha * w.p[c] + omega * w.s[c]; const double r = w.s[c] - omega * w.t[c]; w.r[c] = r; rn += r * r; }
+        rn = sqrt(block_sum(rn, sm));
+        rho = rho1;
+        if (rn <= eps * bn || omega == 0.0) break;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (singular) {
+        double s = 0.0;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; s += L.phi[c]; }
+        s = block_sum(s, sm) / (double)nc;
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] -= s; }
+    }
+#undef CELL
+}
+
+template <class F> void for_dim(int dim, F f) { if (dim == 3) f(std::integral_constant<int, 3>()); else f(std::integral_constant<int, 2>()); }
+
+dim3 cgrid(int nx, int ny, int nz) { return dim3(cdiv(nx, BLK.x), cdiv(ny, BLK.y), nz); }
+
+void mg_build(vdn_ctx *c)
+{
+    MG *m = new MG(); c->mg = m;
+    m->dim = c->dim;
+    const Geo &g = c->geo;
+    // level count: halve while every direction stays even and >= 2 afterwards (F_MG min_width = 2)
+    int nn[3] = { g.n[0], g.n[1], g.n[2] };
+    int nlev = 1;
+    for (;;) {
+        bool ok = true;
+        for (int d = 0; d < c->dim; ++d) if (nn[d] % 2 != 0 || nn[d] / 2 < 2) ok = false;
+        if (!ok) break;
+        for (int d = 0; d < c->dim; ++d) nn[d] /= 2;
+        ++nlev;
+    }
+    m->nlev = nlev; m->L.resize(nlev);
+    m->singular = true;
+    for (int d = 0; d < c->dim; ++d) for (int s = 0; s < 2; ++s) if (c->dom_bc[d][s] == BC_OUTLET) m->singular = false;
+    int n[3] = { g.n[0], g.n[1], g.n[2] };
+    double h[3] = { g.h[0], g.h[1], g.h[2] };
+    int glo[3] = { c->rlo[0], c->rlo[1], c->rlo[2] };
+    for (int l = 0; l < nlev; ++l) {
+        Lev &L = m->L[l];
+        for (int d = 0; d < 3; ++d) { L.n[d] = n[d]; L.h2inv[d] = 1.0 / (h[d] * h[d]); }
+        L.s[0] = 1; L.s[1] = n[0] + 2; L.s[2] = (long)(n[0] + 2) * (n[1] + 2);
+        L.ntot = L.s[2] * (c->dim == 3 ? n[2] + 2 : 1);
+        L.off = 1 + L.s[1] + (c->dim == 3 ? L.s[2] : 0);
+        L.par0 = (glo[0] + glo[1] + (c->dim == 3 ? glo[2] : 0)) & 1;
+        for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) {
+            int e = d < c->dim ? c->ell_bc[d][s] : ELL_NEU;
+            L.mode[d][s] = e == ELL_NEU ? M_NEU : e == ELL_DIR ? M_DIR : (e == ELL_PER && c->wrap[d]) ? M_WRAP : M_GHOST;
+        }
+        auto dalloc = [&](long cnt) { double *p; VDN_CUDA(cudaMalloc(&p, sizeof(double) * cnt)); VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cnt, c->stream)); m->owned.push_back(p); return p; };
+        if (l == 0) {
+            // level 0 aliases the context fields; they were allocated with the same padded layout
+            L.phi = c->f[VDN_PHI].base; L.rhs = c->f[VDN_RH].base;
+            for (int d = 0; d < c->dim; ++d) L.b[d] = c->f[VDN_BETA_X + d].base;
+            VDN_REQUIRE(c->f[VDN_RH].sy == L.s[1] && c->f[VDN_PHI].sy == L.s[1] && c->f[VDN_BETA_X].sy == L.s[1], "level-0 layout mismatch");
+        } else {
+            L.phi = dalloc(L.ntot); L.rhs = dalloc(L.ntot);
+            for (int d = 0; d < c->dim; ++d) L.b[d] = dalloc(L.ntot);
+        }
+        for (int d = c->dim; d < 3; ++d) L.b[d] = nullptr;
+        L.res = dalloc(L.ntot);
+        for (int d = 0; d < c->dim; ++d) { n[d] /= 2; h[d] *= 2.0; glo[d] /= 2; }
+    }
+    for (int q = 0; q < 6; ++q) { VDN_CUDA(cudaMalloc(&m->bot[q], sizeof(double) * m->L[nlev - 1].ntot)); VDN_CUDA(cudaMemsetAsync(m->bot[q], 0, sizeof(double) * m->L[nlev - 1].ntot, c->stream)); }
+    VDN_CUDA(cudaMalloc(&m->d_norm, 64));
+}
+
+void smooth(vdn_ctx *c, MG *m, int l, int sweeps)
+{
+    Lev &L = m->L[l];
+    const double cells = (double)L.n[0] * L.n[1] * L.n[2];
+    for (int s = 0; s < sweeps; ++s)
+        for (int color = 0; color < 2; ++color) {
+            // one colour half-sweep = R phi 8 + rhs 4 + beta 24 (3-D), W phi 4 = 40 B/cell
+            LaunchScope ls(c, l == 0 ? "mg_gsrb_l0" : "mg_gsrb_coarse", cells * (m->dim == 3 ? 40.0 : 32.0));
+            dim3 gr(cdiv((L.n[0] + 1) / 2, BLK.x), cdiv(L.n[1], BLK.y), L.n[2]);
+            for_dim(m->dim, [&](auto D) { k_gsrb<decltype(D)::value><<<gr, BLK, 0, c->stream>>>(L, color); });
+        }
+}
+void residual(vdn_ctx *c, MG *m, int l, double *nrm)
+{
+    Lev &L = m->L[l];
+    const double cells = (double)L.n[0] * L.n[1] * L.n[2];
+    LaunchScope ls(c, l == 0 ? "mg_residual_l0" : "mg_residual_coarse", cells * (m->dim == 3 ? 48.0 : 40.0));
+    if (nrm) VDN_CUDA(cudaMemsetAsync(nrm, 0, 8, c->stream));
+    for_dim(m->dim, [&](auto D) { k_residual<decltype(D)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, nrm); });
+}
+
+void vcycle(vdn_ctx *c, MG *m, int l)
+{
+    Lev &L = m->L[l];
+    if (l == m->nlev - 1) {
+        LaunchScope ls(c, "mg_bottom", 0.0);
+        BotVec w = { m->bot[0], m->bot[1], m->bot[2], m->bot[3], m->bot[4], m->bot[5] };
+        long nc = (long)L.n[0] * L.n[1] * L.n[2];
+        int nt = nc >= 1024 ? 1024 : (int)std::max<long>(32, ((nc + 31) / 32) * 32);
+        for_dim(m->dim, [&](auto D) { k_bottom<decltype(D)::value><<<1, nt, 0, c->stream>>>(L, w, c->prm.mg_max_bottom_iter, c->prm.mg_bottom_eps, m->singular ? 1 : 0); });
+        return;
+    }
+    Lev &C = m->L[l + 1];
+    smooth(c, m, l, c->prm.mg_nu1);
+    residual(c, m, l, nullptr);
+    {
+        LaunchScope ls(c, l == 0 ? "mg_restrict_l0" : "mg_restrict_coarse", (double)L.n[0] * L.n[1] * L.n[2] * 9.0);
+        for_dim(m->dim, [&](auto D) { k_restrict<decltype(D)::value><<<cgrid(C.n[0], C.n[1], C.n[2]), BLK, 0, c->stream>>>(L, C); });
+    }
+    vcycle(c, m, l + 1);
+    {
+        LaunchScope ls(c, l == 0 ? "mg_prolong_l0" : "mg_prolong_coarse", (double)L.n[0] * L.n[1] * L.n[2] * 17.0);
+        for_dim(m->dim, [&](auto D) { k_prolong<decltype(D)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, C); });
+    }
+    smooth(c, m, l, c->prm.mg_nu2);
+}
+
+} // namespace
+
+void mg_destroy(MG *m)
+{
+    if (!m) return;
+    for (double *p : m->owned) cudaFree(p);
+    for (int q = 0; q < 6; ++q) if (m->bot[q]) cudaFree(m->bot[q]);
+    if (m->d_norm) cudaFree(m->d_norm);
+    delete m;
+}
+
+// Solve with RH / BETA_* as right-hand side / coefficients and PHI as initial guess and result.
+int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm)
+{
+    if (!c->mg) mg_build(c);
+    MG *m = c->mg;
+    // coefficient hierarchy
+    for (int l = 1; l < m->nlev; ++l) {
+        Lev &F = m->L[l - 1], &C = m->L[l];
+        LaunchScope ls(c, "mg_coarsen_beta", 0.0, m->dim);
+        for (int d = 0; d < m->dim; ++d)
+            for_dim(m->dim, [&](auto D) { k_coarsen_beta<decltype(D)::value><<<cgrid(C.n[0] + (d == 0), C.n[1] + (d == 1), C.n[2] + (d == 2 ? 1 : 0)), BLK, 0, c->stream>>>(F, C, d); });
+    }
+    VDN_CUDA(cudaGetLastError());
+    const double bnorm = st_absmax_valid(c, VDN_RH);
+    auto res_norm = [&]() {
+        residual(c, m, 0, m->d_norm);
+        VDN_CUDA(cudaMemcpyAsync(c->h_pin, m->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
+        VDN_CUDA(cudaStreamSynchronize(c->stream));
+        return comm_allreduce_max(c, c->h_pin[0]);
+    };
+    double rn = res_norm();
+    int cyc = 0;
+    if (c->prm.mg_verbose) printf("vdn_mg: levels %d  |rh| = %.6e  initial |r| = %.6e\n", m->nlev, bnorm, rn);
+    auto converged = [&](double r) { return r <= rel_eps * bnorm || r <= abs_eps; };
+    while (bnorm > 0.0 && !converged(rn) && cyc < c->prm.mg_max_cycles) {
+        vcycle(c, m, 0);
+        VDN_CUDA(cudaGetLastError());
+        rn = res_norm();
+        ++cyc;
+        if (c->prm.mg_verbose) printf("vdn_mg: cycle %2d  |r|/|rh| = %.6e\n", cyc, rn / bnorm);
+    }
+    if (ncycles) *ncycles = cyc;
+    if (resnorm) *resnorm = bnorm > 0.0 ? rn / bnorm : 0.0;
+    return (bnorm > 0.0 && !converged(rn)) ? 1 : 0;
+}

@@ -1,0 +1,414 @@
+// vdn_stream.cu -- streaming / glue kernels of the hot path (compiled with -fmad=false):
+//   update_3d/_2d          update.f90:186-278, :113-184
+//   mkvelforce/mkscalforce mkforce.f90:144-236, :333-402 (valid cells; ghosts by fill + FOEXTRAP, :75-76)
+//   make_at_halftime       make_at_halftime.f90:95-115
+//   divumac                macproject.f90:137-225, kernel :250-278
+//   mk_mac_coeffs          macproject.f90:280-336, kernel :361-401
+//   mkumac                 macproject.f90:403-505, kernel :578-645
+//   multifab_fill_boundary (FBoxLib; periodic wrap inside the rank's region, NCCL halo between ranks)
+//   multifab_physbc        multifab_physbc.f90:238-561
+// All of them are pure HBM streaming: one thread per cell, i fastest (coalesced 256 B per warp row).
+#include "vdn_ctx.h"
+
+namespace {
+
+constexpr double HALF = 0.5, ZERO = 0.0, TWO = 2.0;
+const dim3 BLK(64, 4, 1);
+
+#define THREAD_IJK(r)                                                            \
+    const int i = (r).lo[0] + blockIdx.x * blockDim.x + threadIdx.x;             \
+    const int j = (r).lo[1] + blockIdx.y * blockDim.y + threadIdx.y;             \
+    const int k = (r).lo[2] + blockIdx.z;                                        \
+    if (i > (r).hi[0] || j > (r).hi[1]) return;
+
+// ---------------- update ----------------
+struct UpdArgs { Range r; int dim, ncomp, is_vel, cons_mask; View sold, snew, force, mac[3], sedge[3], flux[3]; double dt, dx[3]; };
+template <int DIM>
+__global__ void k_update(UpdArgs a)
+{
+    THREAD_IJK(a.r)
+    const double ubar = HALF * (a.mac[0](i, j, k) + a.mac[0](i + 1, j, k));
+    const double vbar = HALF * (a.mac[1](i, j, k) + a.mac[1](i, j + 1, k));
+    double wbar = ZERO;
+    if (DIM == 3) wbar = HALF * (a.mac[2](i, j, k) + a.mac[2](i, j, k + 1));
+    for (int c = 0; c < a.ncomp; ++c) {
+        double adv;
+        if (!a.is_vel && ((a.cons_mask >> c) & 1)) {
+            adv = (a.flux[0](i + 1, j, k, c) - a.flux[0](i, j, k, c)) / a.dx[0]
+                + (a.flux[1](i, j + 1, k, c) - a.flux[1](i, j, k, c)) / a.dx[1];
+            if (DIM == 3) adv = adv + (a.flux[2](i, j, k + 1, c) - a.flux[2](i, j, k, c)) / a.dx[2];
+        } else {
+            adv = ubar * (a.sedge[0](i + 1, j, k, c) - a.sedge[0](i, j, k, c)) / a.dx[0]
+                + vbar * (a.sedge[1](i, j + 1, k, c) - a.sedge[1](i, j, k, c)) / a.dx[1];
+            if (DIM == 3) adv = adv + wbar * (a.sedge[2](i, j, k + 1, c) - a.sedge[2](i, j, k, c)) / a.dx[2];
+        }
+        a.snew(i, j, k, c) = a.sold(i, j, k, c) - a.dt * adv + a.dt * a.force(i, j, k, c);
+    }
+}
+
+// ---------------- forces ----------------
+struct VfArgs { Range r; int dim, nscal_s, boussinesq; View vf, ext, gp, s, lapu; double visc; };
+__global__ void k_mkvelforce(VfArgs a)
+{
+    THREAD_IJK(a.r)
+    const double rho = a.s(i, j, k, 0);
+    const double tr = a.nscal_s > 1 ? a.s(i, j, k, 1) : ZERO;
+    for (int c = 0; c < a.dim; ++c) {
+        double f = a.boussinesq == 1 ? tr * a.ext(i, j, k, c) : a.ext(i, j, k, c);
+        double ll = a.visc * a.lapu(i, j, k, c);      // visc = visc_coef*visc_fac
+        a.vf(i, j, k, c) = f + (ll - a.gp(i, j, k, c)) / rho;
+    }
+}
+struct SfArgs { Range r; int nscal; View sf, ext; };
+__global__ void k_mkscalforce(SfArgs a)        // laps == 0 on this path (diff_coef == 0): ext + 0
+{
+    THREAD_IJK(a.r)
+    a.sf(i, j, k, 0) = ZERO;
+    for (int c = 1; c < a.nscal; ++c) a.sf(i, j, k, c) = a.ext(i, j, k, c) + ZERO;
+}
+struct HtArgs { Range r; View rh, ro, rn; };
+__global__ void k_halftime(HtArgs a)
+{
+    THREAD_IJK(a.r)
+    a.rh(i, j, k) = HALF * (a.ro(i, j, k) + a.rn(i, j, k));
+}
+
+// ---------------- macproject glue ----------------
+struct DivArgs { Range r; int dim; View mac[3], mrhs, rh; double dxinv[3]; double *nrm; };
+template <int DIM>
+__global__ void k_divumac(DivArgs a)
+{
+    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = a.r.lo[2] + blockIdx.z;
+    double v = ZERO;
+    if (i <= a.r.hi[0] && j <= a.r.hi[1]) {
+        double d = (a.mac[0](i + 1, j, k) - a.mac[0](i, j, k)) * a.dxinv[0]
+                 + (a.mac[1](i, j + 1, k) - a.mac[1](i, j, k)) * a.dxinv[1];
+        if (DIM == 3) d = d + (a.mac[2](i, j, k + 1) - a.mac[2](i, j, k)) * a.dxinv[2];
+        v = d * (-1.0) + a.mrhs(i, j, k);
+        a.rh(i, j, k) = v;
+        v = fabs(v);
+    }
+    if (a.nrm) {
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
+            atomicMax((unsigned long long *)a.nrm, (unsigned long long)__double_as_longlong(v));
+    }
+}
+struct CoefArgs { Range r; int d; View rho, beta; };
+__global__ void k_mk_mac_coeffs(CoefArgs a)
+{
+    THREAD_IJK(a.r)
+    const double *p = &a.rho(i, j, k);
+    a.beta(i, j, k) = TWO / (p[0] + p[-a.rho.st(a.d)]);
+}
+struct UmacArgs { Range r; int d, n, bclo, bchi; View mac, phi, beta; double dx; };
+__global__ void k_mkumac(UmacArgs a)
+{
+    THREAD_IJK(a.r)
+    const int ix[3] = { i, j, k };
+    const long st = a.phi.st(a.d);
+    const double *p = &a.phi(i, j, k);
+    double g;
+    if (ix[a.d] == 0 && a.bclo == ELL_NEU) return;
+    if (ix[a.d] == a.n && a.bchi == ELL_NEU) return;
+    if (ix[a.d] == 0 && a.bclo == ELL_DIR)      g = (3.0 * p[0] - p[st] / 3.0) / a.dx;
+    else if (ix[a.d] == a.n && a.bchi == ELL_DIR) g = -(3.0 * p[-st] - p[-2 * st] / 3.0) / a.dx;
+    else                                         g = (p[0] - p[-st]) / a.dx;
+    a.mac(i, j, k) = a.mac(i, j, k) - a.beta(i, j, k) * g;
+}
+
+// ---------------- ghost fills ----------------
+// periodic wrap along d inside the region (the rank owns the whole periodic extent in d).
+// Cell data: ghost -g <- n-g, n-1+g <- g-1.  Face data normal to d (nodal in d): faces 0..n valid,
+// ghost face -g <- face n-g, ghost face n+g <- face g.
+struct WrapArgs { Range r; int d, n, ng, nodal, ncomp; View v; };
+__global__ void k_wrap(WrapArgs a)     // range covers the transverse extents and g = 1..ng along d (index lo[d]..hi[d] = 1..ng)
+{
+    THREAD_IJK(a.r)
+    int ix[3] = { i, j, k };
+    const int g = ix[a.d];
+    const long st = a.v.st(a.d);
+    ix[a.d] = 0;
+    double *p0 = &a.v(ix[0], ix[1], ix[2]);
+    for (int c = 0; c < a.ncomp; ++c) {
+        double *p = p0 + a.v.cs * c;
+        if (!a.nodal) { p[-(long)g * st] = p[(long)(a.n - g) * st]; p[(long)(a.n - 1 + g) * st] = p[(long)(g - 1) * st]; }
+        else          { p[-(long)g * st] = p[(long)(a.n - g) * st]; p[(long)(a.n + g) * st] = p[(long)g * st]; }
+    }
+}
+// physical BC ghost fill along d (both sides) for one comp; ranges as multifab_physbc.f90
+struct PbcArgs { Range r; int d, n, ng; int bc[2]; int full_lo[3], full_hi[3]; double val[2]; View v; };
+__global__ void k_physbc(PbcArgs a)    // range: transverse extents (full ghosted); index along d unused (lo=hi=0)
+{
+    THREAD_IJK(a.r)
+    int ix[3] = { i, j, k };
+    ix[a.d] = 0;
+    const long st = a.v.st(a.d);
+    double *p0 = &a.v(ix[0], ix[1], ix[2]);
+    // restricted transverse range for the extrapolating / reflecting types: skip ghost rows in directions > d on
+    // non-interior sides (encoded by the caller in full_lo/full_hi = the restricted range)
+    bool in_restricted = true;
+    for (int t = 0; t < 3; ++t) if (t != a.d && (ix[t] < a.full_lo[t] || ix[t] > a.full_hi[t])) in_restricted = false;
+    for (int side = 0; side < 2; ++side) {
+        const int b = a.bc[side];
+        if (b == BC_INTERIOR || b == BC_PERIODIC) continue;
+        double *e = side == 0 ? p0 : p0 + (long)(a.n - 1) * st;     // first interior cell
+        const long o = side == 0 ? -st : st;                         // outward
+        if (b == BC_EXT_DIR) {
+            for (int g = 1; g <= a.ng; ++g) e[o * g] = a.val[side];
+        } else if (!in_restricted) {
+            continue;
+        } else if (b == BC_FOEXTRAP) {
+            const double v = e[0];
+            for (int g = 1; g <= a.ng; ++g) e[o * g] = v;
+        } else if (b == BC_HOEXTRAP) {
+            const double v = (15.0 * e[0] - 10.0 * e[-o] + 3.0 * e[-2 * o]) * 0.125;
+            for (int g = 1; g <= a.ng; ++g) e[o * g] = v;
+        } else if (b == BC_REFLECT_EVEN) {
+            for (int g = 1; g <= a.ng; ++g) e[o * g] = e[-o * (g - 1)];
+        } else if (b == BC_REFLECT_ODD) {
+            for (int g = 1; g <= a.ng; ++g) e[o * g] = -e[-o * (g - 1)];
+        }
+    }
+}
+
+struct SetArgs { double *p; long n; double v; };
+__global__ void k_setval(SetArgs a)
+{
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < a.n; t += (long)gridDim.x * blockDim.x) a.p[t] = a.v;
+}
+struct AmaxArgs { Range r; int ncomp; View v; double *out; };
+__global__ void k_absmax(AmaxArgs a)
+{
+    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = a.r.lo[2] + blockIdx.z;
+    double m = ZERO;
+    if (i <= a.r.hi[0] && j <= a.r.hi[1])
+        for (int c = 0; c < a.ncomp; ++c) m = fmax(m, fabs(a.v(i, j, k, c)));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
+        atomicMax((unsigned long long *)a.out, (unsigned long long)__double_as_longlong(m));
+}
+
+Range valid_range(const vdn_ctx *c, int fdir)
+{
+    const Geo &g = c->geo;
+    return mk_range(0, g.n[0] - 1 + (fdir == 0), 0, g.n[1] - 1 + (fdir == 1), 0, g.n[2] - 1 + (fdir == 2));
+}
+
+} // namespace
+
+void st_setval(vdn_ctx *c, int field, double val)
+{
+    DField &f = c->f[field];
+    LaunchScope ls(c, "setval", (double)f.bytes);
+    SetArgs a; a.p = f.base; a.n = (long)(f.bytes / 8); a.v = val;
+    k_setval<<<1184, 256, 0, c->stream>>>(a);
+    VDN_CUDA(cudaGetLastError());
+}
+
+double st_absmax_valid(vdn_ctx *c, int field)
+{
+    DField &f = c->f[field];
+    LaunchScope ls(c, "norm_inf", (double)c->ncells() * 8.0 * f.nc);
+    VDN_CUDA(cudaMemsetAsync(c->d_red, 0, 8, c->stream));
+    AmaxArgs a; a.r = valid_range(c, f.fdir); a.ncomp = f.nc; a.v = f.view(); a.out = c->d_red;
+    k_absmax<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+    VDN_CUDA(cudaMemcpyAsync(c->h_pin, c->d_red, 8, cudaMemcpyDeviceToHost, c->stream));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_allreduce_max(c, c->h_pin[0]);
+}
+
+void st_update(vdn_ctx *c, int is_vel, double dt)
+{
+    const int dim = c->dim;
+    UpdArgs a; a.r = valid_range(c, -1); a.dim = dim; a.is_vel = is_vel;
+    a.ncomp = is_vel ? dim : c->prm.nscal;
+    a.cons_mask = is_vel ? 0 : 1;                                   // scalar_advance.f90:54-57: density only
+    a.sold = c->f[is_vel ? VDN_UOLD : VDN_SOLD].view(); a.snew = c->f[is_vel ? VDN_UNEW : VDN_SNEW].view();
+    a.force = c->f[is_vel ? VDN_VEL_FORCE : VDN_SCAL_FORCE].view();
+    for (int d = 0; d < 3; ++d) {
+        const int dd = d < dim ? d : 0;
+        a.mac[d] = c->f[VDN_UMAC_X + dd].view();
+        a.sedge[d] = c->f[(is_vel ? VDN_UEDGE_X : VDN_SEDGE_X) + dd].view();
+        a.flux[d] = c->f[(is_vel ? VDN_UEDGE_X : VDN_SFLUX_X) + dd].view();
+        a.dx[d] = c->geo.h[dd];
+    }
+    a.dt = dt;
+    {
+        // velocity 168 B/cell, scalars 120 B/cell (3-D)
+        double bpc = is_vel ? 8.0 * (dim + dim + dim * dim + dim + dim) : 8.0 * (2 + dim + dim + dim + 2 + 2);
+        LaunchScope ls(c, is_vel ? "update_vel" : "update_scal", (double)c->ncells() * bpc);
+        if (dim == 3) k_update<3><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        else          k_update<2><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    // ml_restrict_and_fill (update.f90:103-107)
+    const int fld = is_vel ? VDN_UNEW : VDN_SNEW;
+    st_fill_boundary(c, fld);
+    st_physbc(c, fld, is_vel ? 0 : dim, false);
+}
+
+void st_mkvelforce(vdn_ctx *c, int rho_field, double visc_fac)
+{
+    VDN_REQUIRE(rho_field == VDN_SOLD || rho_field == VDN_RHOHALF, "mkvelforce: rho_field must be SOLD or RHOHALF");
+    VfArgs a; a.r = valid_range(c, -1); a.dim = c->dim; a.boussinesq = c->prm.boussinesq;
+    a.vf = c->f[VDN_VEL_FORCE].view(); a.ext = c->f[VDN_EXT_VEL_FORCE].view(); a.gp = c->f[VDN_GP].view();
+    a.s = c->f[rho_field].view(); a.nscal_s = c->f[rho_field].nc; a.lapu = c->f[VDN_LAPU].view();
+    a.visc = c->prm.visc_coef * visc_fac;
+    {
+        LaunchScope ls(c, "mkvelforce", (double)c->ncells() * 8.0 * (3 * c->dim + 1 + c->dim));
+        k_mkvelforce<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    st_fill_boundary(c, VDN_VEL_FORCE);
+    st_physbc(c, VDN_VEL_FORCE, c->dim + c->prm.nscal + 1, true);      // bcomp = extrap_comp, same_boundary (mkforce.f90:75-76)
+}
+
+void st_mkscalforce(vdn_ctx *c, double diff_fac)
+{
+    (void)diff_fac;
+    VDN_REQUIRE(c->prm.diff_coef == 0.0, "mkscalforce: diff_coef > 0 (explicit diffusive term) is outside the device path");
+    SfArgs a; a.r = valid_range(c, -1); a.nscal = c->prm.nscal; a.sf = c->f[VDN_SCAL_FORCE].view(); a.ext = c->f[VDN_EXT_SCAL_FORCE].view();
+    {
+        LaunchScope ls(c, "mkscalforce", (double)c->ncells() * 8.0 * (2 * c->prm.nscal - 1));
+        k_mkscalforce<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    st_fill_boundary(c, VDN_SCAL_FORCE);
+    st_physbc(c, VDN_SCAL_FORCE, c->dim + c->prm.nscal + 1, true);
+}
+
+void st_make_at_halftime(vdn_ctx *c)
+{
+    HtArgs a; a.r = valid_range(c, -1); a.rh = c->f[VDN_RHOHALF].view(); a.ro = c->f[VDN_SOLD].view(); a.rn = c->f[VDN_SNEW].view();
+    {
+        LaunchScope ls(c, "make_at_halftime", (double)c->ncells() * 24.0);
+        k_halftime<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    st_fill_boundary(c, VDN_RHOHALF);
+    st_physbc(c, VDN_RHOHALF, c->dim, false);                           // bcomp = dm + in_comp (make_at_halftime.f90:64-65)
+}
+
+double st_divumac(vdn_ctx *c, bool want_norm)
+{
+    DivArgs a; a.r = valid_range(c, -1); a.dim = c->dim;
+    for (int d = 0; d < 3; ++d) { const int dd = d < c->dim ? d : 0; a.mac[d] = c->f[VDN_UMAC_X + dd].view(); a.dxinv[d] = 1.0 / c->geo.h[dd]; }
+    a.mrhs = c->f[VDN_MAC_RHS].view(); a.rh = c->f[VDN_RH].view();
+    a.nrm = want_norm ? c->d_red : nullptr;
+    if (want_norm) VDN_CUDA(cudaMemsetAsync(c->d_red, 0, 8, c->stream));
+    {
+        LaunchScope ls(c, "divumac", (double)c->ncells() * 8.0 * (c->dim + 2));      // a6: 40 B/cell in 3-D
+        if (c->dim == 3) k_divumac<3><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        else             k_divumac<2><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    if (!want_norm) return 0.0;
+    VDN_CUDA(cudaMemcpyAsync(c->h_pin, c->d_red, 8, cudaMemcpyDeviceToHost, c->stream));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_allreduce_max(c, c->h_pin[0]);
+}
+
+void st_mk_mac_coeffs(vdn_ctx *c)
+{
+    LaunchScope ls(c, "mk_mac_coeffs", (double)c->ncells() * 8.0 * (1 + c->dim), c->dim);   // a7: 32 B/cell
+    for (int d = 0; d < c->dim; ++d) {
+        CoefArgs a; a.r = valid_range(c, d); a.d = d; a.rho = c->f[VDN_SOLD].view(); a.beta = c->f[VDN_BETA_X + d].view();
+        k_mk_mac_coeffs<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+    }
+    VDN_CUDA(cudaGetLastError());
+}
+
+void st_mkumac(vdn_ctx *c)
+{
+    {
+        LaunchScope ls(c, "mkumac", (double)c->ncells() * 8.0 * (1 + 3 * c->dim), c->dim);    // a9: 80 B/cell
+        for (int d = 0; d < c->dim; ++d) {
+            UmacArgs a; a.r = valid_range(c, d); a.d = d; a.n = c->geo.n[d];
+            a.bclo = c->ell_bc[d][0]; a.bchi = c->ell_bc[d][1];
+            a.mac = c->f[VDN_UMAC_X + d].view(); a.phi = c->f[VDN_PHI].view(); a.beta = c->f[VDN_BETA_X + d].view();
+            a.dx = c->geo.h[d];
+            k_mkumac<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        }
+        VDN_CUDA(cudaGetLastError());
+    }
+    for (int d = 0; d < c->dim; ++d) st_fill_boundary(c, VDN_UMAC_X + d);       // macproject.f90:491-493
+}
+
+// multifab_fill_boundary on the merged region: direction by direction (x, then y over the x-ghosted range,
+// then z over the x,y-ghosted range) so that edge and corner ghost cells receive the diagonal images.
+void st_fill_boundary(vdn_ctx *c, int field)
+{
+    DField &f = c->f[field];
+    if (f.ng == 0) return;
+    const Geo &g = c->geo;
+    for (int d = 0; d < c->dim; ++d) {
+        if (c->wrap[d]) {
+            WrapArgs a; a.d = d; a.n = g.n[d]; a.ng = f.ng; a.nodal = (f.fdir == d); a.ncomp = f.nc; a.v = f.view();
+            int lo[3], hi[3];
+            for (int t = 0; t < 3; ++t) {
+                if (t >= c->dim) { lo[t] = 0; hi[t] = 0; }
+                else if (t < d) { lo[t] = -f.ng; hi[t] = g.n[t] - 1 + (f.fdir == t) + f.ng; }      // already filled directions: full
+                else            { lo[t] = 0;     hi[t] = g.n[t] - 1 + (f.fdir == t); }              // not yet: valid only
+            }
+            lo[d] = 1; hi[d] = f.ng;
+            a.r = mk_range(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+            LaunchScope ls(c, "fill_boundary", 0.0);
+            k_wrap<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+            VDN_CUDA(cudaGetLastError());
+        } else if (c->comm) {
+            comm_exchange(c, field, d);
+        }
+    }
+}
+
+// multifab_physbc (multifab_physbc.f90:17-61): per component, x faces, then y over the full x range, then z.
+void st_physbc(vdn_ctx *c, int field, int bccomp, bool same_boundary)
+{
+    DField &f = c->f[field];
+    VDN_REQUIRE(f.fdir < 0, "physbc applies to cell-centred fields");
+    if (f.ng == 0) return;
+    const Geo &g = c->geo;
+    const int dim = c->dim;
+    for (int comp = 0; comp < f.nc; ++comp) {
+        const int bcc = same_boundary ? bccomp : bccomp + comp;
+        const int (*bc)[2] = c->adv_bc[bcc];
+        bool any = false;
+        for (int d = 0; d < dim; ++d) for (int s = 0; s < 2; ++s) if (bc[d][s] != BC_INTERIOR && bc[d][s] != BC_PERIODIC) any = true;
+        if (!any) continue;
+        // EXT_DIR constant slot: icomp = bcc+1; 2-D: 1,2 vel, 3 rho, 4 trac; 3-D: 1..3, 4, 5
+        const int icomp = bcc + 1;
+        int slot;
+        if (dim == 2) slot = (icomp == 1) ? 0 : (icomp == 2) ? 1 : (icomp == 3) ? 3 : (icomp == 4) ? 4 : -1;
+        else          slot = (icomp >= 1 && icomp <= 5) ? icomp - 1 : -1;
+        for (int d = 0; d < dim; ++d) {
+            if ((bc[d][0] == BC_INTERIOR || bc[d][0] == BC_PERIODIC) && (bc[d][1] == BC_INTERIOR || bc[d][1] == BC_PERIODIC)) continue;
+            PbcArgs a; a.d = d; a.n = g.n[d]; a.ng = f.ng; a.v = f.view().comp(comp);
+            for (int s = 0; s < 2; ++s) {
+                a.bc[s] = bc[d][s];
+                a.val[s] = slot >= 0 ? c->prm.bc_val[slot][d][s] : 0.0;
+                if (a.bc[s] == BC_EXT_DIR && slot < 0) a.bc[s] = BC_INTERIOR;      // no branch in the reference => untouched
+            }
+            int lo[3], hi[3];
+            for (int t = 0; t < 3; ++t) {
+                if (t >= dim) { lo[t] = 0; hi[t] = 0; a.full_lo[t] = 0; a.full_hi[t] = 0; continue; }
+                lo[t] = -f.ng; hi[t] = g.n[t] - 1 + f.ng;
+                if (t < d) { a.full_lo[t] = lo[t]; a.full_hi[t] = hi[t]; }
+                else {   // t > d: skip ghost rows on non-interior sides (ngylo.. logic, multifab_physbc.f90:254-276)
+                    const bool il = (bc[t][0] == BC_INTERIOR || bc[t][0] == BC_PERIODIC);
+                    const bool ih = (bc[t][1] == BC_INTERIOR || bc[t][1] == BC_PERIODIC);
+                    a.full_lo[t] = il ? lo[t] : 0; a.full_hi[t] = ih ? hi[t] : g.n[t] - 1;
+                }
+            }
+            lo[d] = 0; hi[d] = 0; a.full_lo[d] = 0; a.full_hi[d] = 0;
+            a.r = mk_range(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+            LaunchScope ls(c, "physbc", 0.0);
+            k_physbc<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+            VDN_CUDA(cudaGetLastError());
+        }
+    }
+}
