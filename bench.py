@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""
+bench.py -- throughput of the VARDEN advection + MAC-projection hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 256] [--ratio 2]
+
+A "step" is one pass of the path advance_timestep.f90:95-124 (advance_premac -> macproject -> scalar_advance ->
+make_at_halftime -> velocity_advance) over the synthetic density-stratified Rayleigh-Taylor state of SURVEY 8(d).
+N=1 workload = BASELINE.json configs[1]: 3-D 256^3 single level, density ratio 2:1, FP64, one B200.
+Metric = Gcell-updates/s (cells x steps / device time).  Prints ONE JSON line (see the task contract) with
+  value     : inputs resident in HBM, device time by CUDA events on the library's stream (max over ranks)
+  e2e       : through the C ABI from pinned HOST buffers: H2D of uold/sold/gp/ext forces + step + D2H of unew/snew/rhohalf
+  roofline  : dominant kernel family: algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (C restatement, OpenMP, all host cores) on a bounded sample of the same workload
+--impl reference times that CPU restatement alone (the reference Fortran cannot be built here: no Fortran compiler,
+FBoxLib absent) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Gcell-updates/s per step (advect+MAC proj)"
+UNIT = "Gcell-updates/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_oracle_rate(n_sample, ratio, steps=1):
+    """time the CPU oracle (OpenMP C restatement) on a bounded sample: the same problem at n_sample^3"""
+    from oracle import oracle as O
+    geom, P, st, dt = O.rt_state(n_sample, dim=3, max_grid_size=256, ratio=ratio)
+    O.advance(geom, P, st, dt)         # warm (page-in, thread pool)
+    t0 = time.perf_counter()
+    cyc = 0
+    for _ in range(steps):
+        out = O.advance(geom, P, st, dt)
+        cyc = out["mac_cycles"]
+    t = time.perf_counter() - t0
+    return geom.ncells * steps / t / 1e9, t, cyc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    ns = args.cpu_n
+    vals = []
+    for _ in range(args.warmup):
+        cpu_oracle_rate(ns, args.ratio, 1) if False else None     # the oracle call itself does one warm pass
+    t_tot = 0.0
+    for _ in range(args.steps):
+        v, t, cyc = cpu_oracle_rate(ns, args.ratio, 1)
+        vals.append(v); t_tot += t
+    value = float(np.mean(vals))
+    sample = "same RT problem at %d^3 (one pass per step), %d V-cycles" % (ns, cyc)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D %d^3 single-level RT ratio %g:1 (bounded CPU sample %d^3)" % (args.n, args.ratio, ns)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample + "; C/OpenMP restatement of the reference loops (oracle/), not the Fortran binary"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=256, help="cells per direction of the N=1 workload")
+    ap.add_argument("--ratio", type=float, default=2.0)
+    ap.add_argument("--cpu-n", type=int, default=96, help="grid size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-grid-size", type=int, default=256)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import ctypes as C
+    import varden_b200 as V
+    from varden_b200.problems import rt_problem, mf_alloc
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        print("bench.py: WORLD_SIZE (%d) != --gpus (%d); launch with torchrun for N>1" % (world, args.gpus), file=sys.stderr)
+        if args.gpus > 1 and world == 1:
+            sys.exit(2)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU arm is not wired in this revision")
+
+    n = args.n
+    geom, st, dt = rt_problem(n, dim=3, max_grid_size=args.max_grid_size, ratio=args.ratio)
+    dim, nscal = 3, 2
+    prm = V.default_params()
+    ctx = V.Context(3, geom.boxes, geom.dlo, geom.dhi, geom.phys_bc, geom.dx, params=prm, device=local)
+
+    # ---- pinned host buffers = what the Fortran driver would hand over (ghosts filled as varden.f90:291-300) ----
+    spec_in = [("UOLD", "uold", 3, dim), ("SOLD", "sold", 3, nscal), ("GP", "gp", 1, dim),
+               ("EXT_VEL_FORCE", "ext_vel_force", 1, dim), ("EXT_SCAL_FORCE", "ext_scal_force", 1, nscal)]
+    spec_out = [("UNEW", 3, dim), ("SNEW", 3, nscal), ("RHOHALF", 1, 1)]
+
+    def pinned_like(a):
+        t = torch.empty(a.size, dtype=torch.float64).pin_memory()
+        v = t.numpy().reshape(a.shape, order='F')
+        return t, v
+
+    host_in, host_out, keep = {}, {}, []
+    for fld, key, ng, nc in spec_in:
+        host_in[fld] = []
+        for a in st[key]:
+            t, v = pinned_like(a); v[...] = a; keep.append(t); host_in[fld].append(v)
+        ctx.upload_mf(fld, host_in[fld], ng, nc)
+    ctx.fill_and_physbc("UOLD", 0)
+    ctx.fill_and_physbc("SOLD", dim)
+    ctx.fill_boundary("GP")
+    for fld, key, ng, nc in spec_in[:3]:
+        ctx.download_mf(fld, host_in[fld], ng, nc)          # host copies now carry the path-boundary ghost cells
+    for fld, ng, nc in spec_out:
+        host_out[fld] = []
+        for ib in range(geom.nboxes):
+            t, v = pinned_like(np.empty(geom.box_shape(ib, ng) + (nc,), order='F')); keep.append(t); host_out[fld].append(v)
+    h2d = sum(v.nbytes for fld in host_in for v in host_in[fld])
+    d2h = sum(v.nbytes for fld in host_out for v in host_out[fld])
+
+    def step_resident():
+        return ctx.advance(dt)
+
+    def step_e2e():
+        for fld, key, ng, nc in spec_in:
+            ctx.upload_mf(fld, host_in[fld], ng, nc)
+        r = ctx.advance(dt)
+        for fld, ng, nc in spec_out:
+            ctx.download_mf(fld, host_out[fld], ng, nc)
+        return r
+
+    # ---- resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        cyc, res = step_resident()
+    ctx.sync()
+    ctx.prof_enable(True)
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    xs = torch.cuda.ExternalStream(ctx.stream_ptr())        # the library's launching stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record(xs)
+    for _ in range(args.steps):
+        cyc, res = step_resident()
+    ev1.record(xs)
+    ctx.sync()
+    torch.cuda.synchronize()
+    wall_host = time.perf_counter() - t0
+    wall = ev0.elapsed_time(ev1) / 1e3                       # device time by CUDA events on the launching stream
+    launches = ctx.launch_count() - l0
+    prof = ctx.prof_report()
+    ctx.prof_enable(False)
+    dev_ms = sum(p["ms"] for p in prof.values())
+    # one in-order stream; the host only syncs for the per-V-cycle residual norm, so event time ~ host wall time
+    ms_per_step = 1e3 * wall / args.steps
+    value = geom.ncells * args.steps / wall / 1e9
+
+    # ---- e2e timing (host buffers, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(xs)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(xs)
+        ctx.sync()
+        t_e = e0.elapsed_time(e1) / 1e3
+        e2e = {"value": geom.ncells * args.steps / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * t_e / args.steps}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel family ----
+    peak, peak_src = measured_peak()
+    fam = {}
+    for name, p in prof.items():
+        if p["ms"] <= 0:
+            continue
+        fam[name] = {"launches": p["launches"], "ms_total": p["ms"], "share": p["ms"] / dev_ms if dev_ms else None,
+                     "alg_gb": p["alg_bytes"] / 1e9, "gbs": (p["alg_bytes"] / 1e9) / (p["ms"] / 1e3) if p["alg_bytes"] > 0 else None}
+        if fam[name]["gbs"] is not None:
+            fam[name]["frac"] = fam[name]["gbs"] / peak
+    top = max(fam, key=lambda k: fam[k]["ms_total"]) if fam else None
+    roof = None
+    if top:
+        t = fam[top]
+        roof = {"bound": "hbm", "kernel": top, "achieved": t["gbs"], "peak": peak, "unit": "GB/s", "frac": (t["gbs"] / peak) if t["gbs"] else None,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": t["ms_total"] / max(t["launches"], 1), "share_of_step": t["share"]}
+
+    cpu = None
+    if not args.no_cpu:
+        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
+        v, t, ccyc = cpu_oracle_rate(args.cpu_n, args.ratio, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "same RT problem at %d^3, one pass (%.1f s, %d V-cycles); C/OpenMP restatement of the reference loops, not the Fortran binary"
+                         % (args.cpu_n, t, ccyc)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D %d^3 single-level variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, "
+                                   "MAC rel tol 1e-10, %d box(es)" % (n, args.ratio, geom.nboxes),
+                       "l2_policy": "inputs (%.1f GB of fields) exceed the 126 MB L2; no explicit flush" % (45 * 8 * (n + 6) ** 3 / 1e9),
+                       "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
+                       "host_wall_ms_per_step": 1e3 * wall_host / args.steps},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "kernels": fam}
+    print(json.dumps(line))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,7 +35,9 @@ extern "C" {
  *   UOLD/UNEW ng3 dm comps; SOLD/SNEW ng3 nscal comps; GP, EXT_VEL_FORCE, VEL_FORCE ng1 dm comps;
  *   EXT_SCAL_FORCE, SCAL_FORCE ng1 nscal comps; LAPU ng0 dm comps; MAC_RHS, RHOHALF, PHI ng1 1 comp;
  *   UMAC_X/Y/Z face, ng1, 1 comp; RH ng0; BETA_X/Y/Z face ng0;
- *   SEDGE_X/Y/Z, SFLUX_X/Y/Z face ng0 nscal comps; UEDGE_X/Y/Z face ng0 dm comps. */
+ *   SEDGE_X/Y/Z face ng0 nscal comps; SFLUX_X/Y/Z face ng0 1 comp (density, the only conservative comp:
+ *   scalar_advance.f90:54-57; the reference's other flux comps stay 0); UEDGE_X/Y/Z face ng0 dm comps.
+ *   SEDGE_* and UEDGE_* share storage (the scalar and velocity phases never overlap). */
 enum vdn_field {
     VDN_UOLD = 0, VDN_SOLD, VDN_UNEW, VDN_SNEW, VDN_GP,
     VDN_EXT_VEL_FORCE, VDN_EXT_SCAL_FORCE, VDN_LAPU,
@@ -98,6 +100,8 @@ int vdn_field_upload(vdn_ctx *ctx, int field, int ibox, const double *host, int 
 int vdn_field_download(vdn_ctx *ctx, int field, int ibox, double *host, int ng, int ncomp);
 int vdn_field_setval(vdn_ctx *ctx, int field, double val);       /* multifab setval(all=.true.) */
 int vdn_sync(vdn_ctx *ctx);
+/* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
+void *vdn_get_stream(vdn_ctx *ctx);
 
 /* ---- stage calls: same names / argument meaning as the reference module procedures ---- */
 

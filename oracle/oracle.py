@@ -11,9 +11,12 @@ covering lo-ng .. hi+ng (+1 in the face direction); 2-D uses n2 == 1.
 import ctypes as C
 import os
 import subprocess
+import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+if os.path.dirname(_HERE) not in sys.path:
+    sys.path.insert(0, os.path.dirname(_HERE))
 
 # FBoxLib bc_module codes (see orc_common.h)
 PERIODIC, INTERIOR, INLET, OUTLET, SYMMETRY, SLIP_WALL, NO_SLIP_WALL = -1, 0, 11, 12, 13, 14, 15
@@ -77,70 +80,22 @@ class Params:
         return p
 
 
-class Geom:
-    """One AMR level: domain, physical BCs, dx and the box list (initialize.f90:198-215)."""
-
-    def __init__(self, dim, n_cell, phys_bc, prob_lo=(0., 0., 0.), prob_hi=(1., 1., 1.), max_grid_size=256, boxes=None):
-        self.dim = dim
-        self.n_cell = [int(n_cell[d]) if d < dim else 1 for d in range(3)]
-        self.dlo = [0, 0, 0]
-        self.dhi = [self.n_cell[d] - 1 if d < dim else 0 for d in range(3)]
-        self.phys_bc = np.zeros((3, 2), dtype=np.int32)
-        self.phys_bc[:dim, :] = np.asarray(phys_bc, dtype=np.int32).reshape(-1, 2)[:dim]
-        self.dx = [(prob_hi[d] - prob_lo[d]) / self.n_cell[d] if d < dim else 0.0 for d in range(3)]
-        self.prob_lo = list(prob_lo)
-        if boxes is None:
-            boxes = chop_domain(self.dlo, self.dhi, dim, max_grid_size)
-        self.boxes = boxes
-        self._blo = np.ascontiguousarray([b[0] for b in boxes], dtype=np.int32)
-        self._bhi = np.ascontiguousarray([b[1] for b in boxes], dtype=np.int32)
-
-    @property
-    def nboxes(self):
-        return len(self.boxes)
-
-    def to_c(self):
-        g = OrcGeom()
-        g.nboxes = self.nboxes
-        g.blo = self._blo.ctypes.data_as(C.POINTER(C.c_int))
-        g.bhi = self._bhi.ctypes.data_as(C.POINTER(C.c_int))
-        for d in range(3):
-            g.dlo[d], g.dhi[d], g.dx[d] = self.dlo[d], self.dhi[d], self.dx[d]
-        for i, v in enumerate(self.phys_bc.ravel()):
-            g.phys_bc[i] = int(v)
-        return g
-
-    def box_shape(self, ib, ng, face_dir=-1):
-        lo, hi = self.boxes[ib]
-        return tuple((hi[d] - lo[d] + 1 + 2 * ng + (1 if d == face_dir else 0)) if d < self.dim else 1 for d in range(3))
+from varden_b200.problems import Geom, chop_domain, mf_alloc, valid, rt_problem  # noqa: E402  (shared problem set-up)
 
 
-def chop_domain(dlo, dhi, dim, max_grid_size):
-    """boxarray_maxsize: chop each direction into the fewest equal-ish pieces <= max_grid_size."""
-    cuts = []
+def _geom_to_c(self):
+    g = OrcGeom()
+    g.nboxes = self.nboxes
+    g.blo = self._blo.ctypes.data_as(C.POINTER(C.c_int))
+    g.bhi = self._bhi.ctypes.data_as(C.POINTER(C.c_int))
     for d in range(3):
-        if d >= dim:
-            cuts.append([(0, 0)])
-            continue
-        n = dhi[d] - dlo[d] + 1
-        npieces = (n + max_grid_size - 1) // max_grid_size
-        base, rem = divmod(n, npieces)
-        segs, s = [], dlo[d]
-        for p in range(npieces):
-            ln = base + (1 if p < rem else 0)
-            segs.append((s, s + ln - 1))
-            s += ln
-        cuts.append(segs)
-    boxes = []
-    for kz in cuts[2]:
-        for jy in cuts[1]:
-            for ix in cuts[0]:
-                boxes.append(([ix[0], jy[0], kz[0]], [ix[1], jy[1], kz[1]]))
-    return boxes
+        g.dlo[d], g.dhi[d], g.dx[d] = self.dlo[d], self.dhi[d], self.dx[d]
+    for i, v in enumerate(self.phys_bc.ravel()):
+        g.phys_bc[i] = int(v)
+    return g
 
 
-def mf_alloc(geom, ng, ncomp, face_dir=-1, val=0.0):
-    return [np.full(geom.box_shape(ib, ng, face_dir) + (ncomp,), val, dtype=np.float64, order='F') for ib in range(geom.nboxes)]
+Geom.to_c = _geom_to_c
 
 
 def _pp(mf):
@@ -195,52 +150,15 @@ def advance(geom, params, st, dt, mac_rel_eps=-1.0, want_phi=True):
 # ---------------------------------------------------------------------------------------------
 # synthetic problems; initial data follows src/initdata.f90:195-200,261-274
 # ---------------------------------------------------------------------------------------------
-def _h(x):
-    return 0.02 * np.sin(4.0 * np.pi * x) + 0.01 * np.sin(8.0 * np.pi * x)
-
-
 def rt_state(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, seeded_velocity=True, params=None, phys_bc=None):
-    """Density-stratified Rayleigh-Taylor-type state: periodic in x(,y), no-slip walls in the last direction.
-
-    rho = rho_mid + rho_amp*tanh((z - 1/2 - h(x) - h(y))/0.01) with (rho_mid, rho_amp) giving the density ratio
-    (ratio 2 reproduces initdata.f90:270 exactly: 1.5 + 0.5 tanh).  A deterministic, not discretely
-    divergence-free velocity is seeded so that the MAC right-hand side is non-trivial.
-    """
-    if np.isscalar(n):
-        n = [n] * dim
-    if phys_bc is None:
-        phys_bc = [[PERIODIC, PERIODIC]] * (dim - 1) + [[NO_SLIP_WALL, NO_SLIP_WALL]]
-    geom = Geom(dim, n, phys_bc, max_grid_size=max_grid_size)
+    """rt_problem (varden_b200/problems.py) + the path-boundary ghost fill of varden.f90:291-300."""
     if params is None:
         params = Params(dim=dim, nscal=2)
-    rho_lo, rho_hi = 1.0, float(ratio)
-    mid, amp = 0.5 * (rho_hi + rho_lo), 0.5 * (rho_hi - rho_lo)
-    st = dict(uold=mf_alloc(geom, 3, dim), sold=mf_alloc(geom, 3, params.nscal), gp=mf_alloc(geom, 1, dim),
-              ext_vel_force=mf_alloc(geom, 1, dim), ext_scal_force=mf_alloc(geom, 1, params.nscal))
-    for ib, (lo, hi) in enumerate(geom.boxes):
-        ax = [(np.arange(lo[d], hi[d] + 1) + 0.5) * geom.dx[d] if d < dim else np.zeros(1) for d in range(3)]
-        X, Y, Z = np.meshgrid(ax[0], ax[1], ax[2], indexing='ij')
-        if dim == 3:
-            rho = mid + amp * np.tanh((Z - 0.5 - _h(X) - _h(Y)) / 0.01)
-        else:
-            rho = mid + amp * np.tanh((Y - 0.5 - _h(X)) / 0.01)
-        valid(geom, st["sold"][ib], ib, 3)[..., 0] = rho
-        valid(geom, st["sold"][ib], ib, 3)[..., 1] = 0.0
-        if seeded_velocity:
-            u = valid(geom, st["uold"][ib], ib, 3)
-            if dim == 3:
-                u[..., 0] = 0.1 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y) * np.sin(np.pi * Z)
-                u[..., 1] = -0.1 * np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(np.pi * Z)
-                u[..., 2] = 0.05 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y) * np.sin(2 * np.pi * Z)
-            else:
-                u[..., 0] = 0.1 * np.sin(2 * np.pi * X) * np.sin(np.pi * Y)
-                u[..., 1] = 0.05 * np.sin(2 * np.pi * X) * np.sin(2 * np.pi * Y)
-        st["ext_vel_force"][ib][..., dim - 1] = grav      # varden.f90:428-429
-    # path-boundary input state: ghost cells filled as varden.f90:291-300
+    geom, st, dt = rt_problem(n, dim=dim, max_grid_size=max_grid_size, ratio=ratio, grav=grav, nscal=params.nscal,
+                              seeded_velocity=seeded_velocity, phys_bc=phys_bc)
     fill_and_physbc(geom, params, st["uold"], 3, dim, 0, 0, dim)
     fill_and_physbc(geom, params, st["sold"], 3, params.nscal, 0, dim, params.nscal)
     fill_boundary(geom, st["gp"], 1, dim)
-    dt = 0.45 * geom.dx[0] / 0.1
     return geom, params, st, dt
 
 

@@ -112,6 +112,7 @@ def test_one_step_end_to_end(case):
 def test_ten_steps():
     """all fields within 1e-8 relative after 10 steps at the reference's MAC tolerance (1e-10)"""
     geom, P, st, dt = O.rt_state(32, dim=3, max_grid_size=16)
+    dt = 0.2 * dt          # hgproject is outside the path: keep the un-projected, gravity-accelerated velocity within CFL for 10 steps
     dim, nscal = geom.dim, P.nscal
     ctx = make_ctx(geom, P)
     upload_state(ctx, geom, P, st)
@@ -128,7 +129,8 @@ def test_ten_steps():
     e_u = relerr(geom, un, ref["unew"], 3)
     e_s = relerr(geom, sn, ref["snew"], 3)
     ctx.close()
-    print("10 steps: unew %.2e snew %.2e" % (e_u, e_s))
+    ndiff = sum(int((O.valid(geom, a, ib, 3) != O.valid(geom, b, ib, 3)).sum()) for ib, (a, b) in enumerate(zip(un, ref["unew"])))
+    print("10 steps: unew %.2e snew %.2e (unew entries differing bitwise: %d)" % (e_u, e_s, ndiff))
     assert e_u <= TOL_10STEP and e_s <= TOL_10STEP
 
 

@@ -31,16 +31,21 @@ def relerr(geom, got, ref, ng, face_dir=-1, comps=None, full=None):
             a, b = O.valid(geom, a, ib, ng, face_dir), O.valid(geom, b, ib, ng, face_dir)
         if comps is not None:
             a, b = a[..., comps], b[..., comps]
+        if not np.all(np.isfinite(b)):                   # a non-finite reference means the test itself is broken
+            return np.inf
         m = np.isfinite(b) & (np.abs(b) < 1e19)          # skip the 1.d20 poison in umac ghost faces (compared separately)
         if not np.array_equal(np.abs(b) >= 1e19, np.abs(a) >= 1e19):
             return np.inf
         if m.any():
-            num = max(num, float(np.abs(a[m] - b[m]).max()))
+            d = np.abs(a[m] - b[m])
+            if not np.all(np.isfinite(d)):          # NaN/inf anywhere (e.g. cells a download did not write) is a failure
+                return np.inf
+            num = max(num, float(d.max()))
             den = max(den, float(np.abs(b[m]).max()))
     return num / den if den > 0 else num
 
 
 def download_like(ctx, geom, field, ref, ng, ncomp):
-    out = [np.full_like(a, np.nan) if geom.nboxes == 1 else a.copy(order='F') for a in ref]
+    out = [np.full_like(a, np.nan) for a in ref]      # NaN prefill: anything the download does not write stays visible
     ctx.download_mf(field, out, ng, ncomp)
     return out

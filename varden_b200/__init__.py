@@ -24,7 +24,7 @@ F = {name: i for i, name in enumerate(FIELDS)}
 
 ABI_SYMBOLS = [
     "vdn_params_default", "vdn_ctx_create", "vdn_ctx_destroy", "vdn_last_error", "vdn_ctx_set_comm",
-    "vdn_field_upload", "vdn_field_download", "vdn_field_setval", "vdn_sync",
+    "vdn_field_upload", "vdn_field_download", "vdn_field_setval", "vdn_sync", "vdn_get_stream",
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
@@ -57,6 +57,7 @@ def load_library():
         _lib = C.CDLL(LIB_PATH)
         _lib.vdn_last_error.restype = C.c_char_p
         _lib.vdn_launch_count.restype = C.c_longlong
+        _lib.vdn_get_stream.restype = C.c_void_p
     return _lib
 
 
@@ -145,6 +146,9 @@ class Context:
 
     def sync(self):
         self._chk(self.lib.vdn_sync(self.h))
+
+    def stream_ptr(self):
+        return int(self.lib.vdn_get_stream(self.h))
 
     # ---- stage calls (reference procedure names) ----
     def fill_boundary(self, field):

@@ -78,4 +78,24 @@ struct DField {
     long ncell() const { return (long)ext[0] * ext[1] * ext[2]; }
 };
 
+#ifdef __CUDACC__
+// block-wide max of non-negative values, then ONE atomicMax per block on the bit pattern (non-negative doubles order
+// like their bit patterns).  Every thread of the block must call it (no early returns before it).
+__device__ __forceinline__ void block_atomic_max(double v, double *out)
+{
+    __shared__ double sm_max_[32];
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int tid = threadIdx.z * blockDim.y * blockDim.x + threadIdx.y * blockDim.x + threadIdx.x;
+    const int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+    if ((tid & 31) == 0) sm_max_[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        v = tid < nw ? sm_max_[tid] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (tid == 0 && v > *(volatile double *)out)
+            atomicMax((unsigned long long *)out, (unsigned long long)__double_as_longlong(v));
+    }
+}
+#endif
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

@@ -321,6 +321,7 @@ int vdn_field_download(vdn_ctx *ctx, int field, int ibox, double *host, int ng, 
 int vdn_field_setval(vdn_ctx *ctx, int field, double val)
 { VDN_TRY(ctx, { VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS && ctx->f[field].base, "bad field id"); st_setval(ctx, field, val); }) }
 int vdn_sync(vdn_ctx *ctx) { VDN_TRY(ctx, VDN_CUDA(cudaStreamSynchronize(ctx->stream))) }
+void *vdn_get_stream(vdn_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int vdn_fill_boundary(vdn_ctx *ctx, int field)
 { VDN_TRY(ctx, { VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS && ctx->f[field].base, "bad field id"); st_fill_boundary(ctx, field); }) }

@@ -33,6 +33,8 @@ struct MG {
     double *bot[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // BiCGStab vectors on the bottom level
     double *d_norm = nullptr;
     double h0[3];
+    cudaGraphExec_t coarse_graph = nullptr;     // levels 1..bottom of one V-cycle (latency-bound launches), captured once
+    int coarse_graph_launches = 0;
 };
 
 namespace {
@@ -93,11 +95,7 @@ __global__ void k_residual(Lev L, double *nrm)
         L.res[c] = r;
         r = fabs(r);
     }
-    if (nrm) {
-        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
-        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && r > 0.0)
-            atomicMax((unsigned long long *)nrm, (unsigned long long)__double_as_longlong(r));
-    }
+    if (nrm) block_atomic_max(r, nrm);
 }
 
 // coarse rhs = average of the fine residual; coarse phi = 0
@@ -318,7 +316,11 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         LaunchScope ls(c, l == 0 ? "mg_restrict_l0" : "mg_restrict_coarse", (double)L.n[0] * L.n[1] * L.n[2] * 9.0);
         for_dim(m->dim, [&](auto D) { k_restrict<decltype(D)::value><<<cgrid(C.n[0], C.n[1], C.n[2]), BLK, 0, c->stream>>>(L, C); });
     }
-    vcycle(c, m, l + 1);
+    if (l == 0 && m->coarse_graph) {
+        LaunchScope ls(c, "mg_coarse_levels_graph", 0.0, m->coarse_graph_launches);
+        VDN_CUDA(cudaGraphLaunch(m->coarse_graph, c->stream));
+    } else
+        vcycle(c, m, l + 1);
     {
         LaunchScope ls(c, l == 0 ? "mg_prolong_l0" : "mg_prolong_coarse", (double)L.n[0] * L.n[1] * L.n[2] * 17.0);
         for_dim(m->dim, [&](auto D) { k_prolong<decltype(D)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, C); });
@@ -328,9 +330,27 @@ void vcycle(vdn_ctx *c, MG *m, int l)
 
 } // namespace
 
+// capture levels 1..bottom of the V-cycle into a CUDA graph: ~70 tiny launches become one
+static void mg_capture_coarse(vdn_ctx *c, MG *m)
+{
+    if (m->nlev < 3 || m->coarse_graph) return;
+    const bool prof = c->prof_on; c->prof_on = false;
+    const long long l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    VDN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    try { vcycle(c, m, 1); } catch (...) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); c->prof_on = prof; throw; }
+    VDN_CUDA(cudaStreamEndCapture(c->stream, &g));
+    m->coarse_graph_launches = (int)(c->launches - l0);
+    c->launches = l0;
+    c->prof_on = prof;
+    VDN_CUDA(cudaGraphInstantiate(&m->coarse_graph, g, 0));
+    cudaGraphDestroy(g);
+}
+
 void mg_destroy(MG *m)
 {
     if (!m) return;
+    if (m->coarse_graph) cudaGraphExecDestroy(m->coarse_graph);
     for (double *p : m->owned) cudaFree(p);
     for (int q = 0; q < 6; ++q) if (m->bot[q]) cudaFree(m->bot[q]);
     if (m->d_norm) cudaFree(m->d_norm);
@@ -340,7 +360,7 @@ void mg_destroy(MG *m)
 // Solve with RH / BETA_* as right-hand side / coefficients and PHI as initial guess and result.
 int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm)
 {
-    if (!c->mg) mg_build(c);
+    if (!c->mg) { mg_build(c); mg_capture_coarse(c, c->mg); }
     MG *m = c->mg;
     // coefficient hierarchy
     for (int l = 1; l < m->nlev; ++l) {

@@ -90,11 +90,7 @@ __global__ void k_divumac(DivArgs a)
         a.rh(i, j, k) = v;
         v = fabs(v);
     }
-    if (a.nrm) {
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
-            atomicMax((unsigned long long *)a.nrm, (unsigned long long)__double_as_longlong(v));
-    }
+    if (a.nrm) block_atomic_max(v, a.nrm);
 }
 struct CoefArgs { Range r; int d; View rho, beta; };
 __global__ void k_mk_mac_coeffs(CoefArgs a)
@@ -188,9 +184,7 @@ __global__ void k_absmax(AmaxArgs a)
     double m = ZERO;
     if (i <= a.r.hi[0] && j <= a.r.hi[1])
         for (int c = 0; c < a.ncomp; ++c) m = fmax(m, fabs(a.v(i, j, k, c)));
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
-        atomicMax((unsigned long long *)a.out, (unsigned long long)__double_as_longlong(m));
+    block_atomic_max(m, a.out);
 }
 
 Range valid_range(const vdn_ctx *c, int fdir)
@@ -325,6 +319,8 @@ void st_mk_mac_coeffs(vdn_ctx *c)
 
 void st_mkumac(vdn_ctx *c)
 {
+    // the solver leaves phi's periodic / rank-boundary ghost cells stale (it wraps by index); the box-boundary faces need them
+    st_fill_boundary(c, VDN_PHI);
     {
         LaunchScope ls(c, "mkumac", (double)c->ncells() * 8.0 * (1 + 3 * c->dim), c->dim);    // a9: 80 B/cell
         for (int d = 0; d < c->dim; ++d) {
