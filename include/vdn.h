@@ -92,6 +92,12 @@ const char *vdn_last_error(const vdn_ctx *ctx);   /* ctx may be NULL: last creat
  */
 int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *region_lo, const int *region_hi,
                      const void *nccl_unique_id);
+/* rank 0 creates the 128-byte id (ncclGetUniqueId) that the caller broadcasts to every rank */
+int vdn_nccl_unique_id(void *out128);
+/* host-only: neighbour ranks nbr[3][2] (-1 = physical boundary, own rank = periodic self-wrap), process grid and this
+ * rank's coordinates for a tensor-product decomposition.  Returns 2 if the regions are not such a decomposition. */
+int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo, const int *region_hi,
+                  const int *dom_lo, const int *dom_hi, const int *phys_bc, int *nbr, int *pgrid, int *pcoord);
 
 /* Path-boundary copies (SURVEY 8(b) "Copies"): host box array <-> region array, ghosts included
  * where they lie outside the region's valid area.  `host` has `ng` ghosts and `ncomp` comps and

@@ -1,0 +1,77 @@
+"""
+Multi-GPU parity worker (launched by torchrun, one rank per GPU): every rank runs its region of the domain through
+libvdn.so with NCCL halo exchange / all-reduce / coarse-level agglomeration and compares its boxes with the CPU oracle
+of the WHOLE domain.  Exit code 0 = parity within tolerance on every rank.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import oracle as O          # noqa: E402
+import varden_b200 as V                  # noqa: E402
+from varden_b200 import parallel as PAR  # noqa: E402
+from util import relerr                  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="rt3d")
+    ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--tol", type=float, default=1e-10)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, NS, IN, OUT, PER = O.SLIP_WALL, O.NO_SLIP_WALL, O.INLET, O.OUTLET, O.PERIODIC
+    n = args.n
+    if args.case == "rt3d":
+        geom, P, st, dt = O.rt_state(n, dim=3, max_grid_size=n // 2)
+    elif args.case == "rand3d":
+        geom, P, st, dt = O.random_state(n, dim=3, max_grid_size=n // 2, phys_bc=[[IN, OUT], [PER, PER], [NS, W]], seed=7)
+    elif args.case == "per3d":
+        geom, P, st, dt = O.random_state(n, dim=3, max_grid_size=n // 2, phys_bc=[[PER, PER]] * 3, seed=8)
+    elif args.case == "rt2d":
+        geom, P, st, dt = O.rt_state(n, dim=2, max_grid_size=n // 2)
+    else:
+        raise SystemExit("unknown case")
+    dim, nscal = geom.dim, P.nscal
+    ref = O.advance(geom, P, st, dt, mac_rel_eps=1e-13)
+    ids, rlo, rhi, pg = PAR.partition(geom, world)
+    mine = ids[rank]
+    sub = geom.subset(mine)
+    prm = V.default_params(nscal=nscal, bc_val=P.bcval)
+    ctx = V.Context(dim, sub.boxes, geom.dlo, geom.dhi, geom.phys_bc, geom.dx, params=prm, device=local)
+    PAR.init_comm(ctx, rank, world, rlo, rhi)
+    pick = lambda mf: [mf[i] for i in mine]
+    ctx.upload_mf("UOLD", pick(st["uold"]), 3, dim)
+    ctx.upload_mf("SOLD", pick(st["sold"]), 3, nscal)
+    ctx.upload_mf("GP", pick(st["gp"]), 1, dim)
+    ctx.upload_mf("EXT_VEL_FORCE", pick(st["ext_vel_force"]), 1, dim)
+    ctx.upload_mf("EXT_SCAL_FORCE", pick(st["ext_scal_force"]), 1, nscal)
+    ncyc, res = ctx.advance(dt, mac_rel_eps=1e-13)
+    errs = {}
+    for fld, key, ng, nc in (("SNEW", "snew", 3, nscal), ("UNEW", "unew", 3, dim), ("RHOHALF", "rhohalf", 1, 1)):
+        got = [np.full_like(a, np.nan) for a in pick(ref[key])]
+        ctx.download_mf(fld, got, ng, nc)
+        errs[key] = relerr(sub, got, pick(ref[key]), ng, full=False)
+    ctx.close()
+    worst = torch.tensor([max(errs.values())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("mgpu %s n=%d world=%d pgrid=%s: vcycles %d res %.2e  worst rel err %.3e  (rank0: %s)"
+              % (args.case, n, world, pg, ncyc, res, worst.item(), {k: "%.1e" % v for k, v in errs.items()}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if worst.item() <= args.tol else 1)
+
+
+if __name__ == "__main__":
+    main()

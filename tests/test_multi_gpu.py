@@ -1,0 +1,28 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 GPUs on the box; skipped otherwise): torchrun + tests/mgpu_worker.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("case,n", [("rt3d", 64), ("rand3d", 32), ("per3d", 32), ("rt2d", 64)])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_parity(case, n, world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    if case == "rt2d" and world == 8:
+        pytest.skip("2-D: 4 boxes")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--n", str(n)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0

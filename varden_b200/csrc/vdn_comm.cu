@@ -1,20 +1,260 @@
-// vdn_comm.cu -- inter-rank plumbing (halo exchange, scalar all-reduces).  Single-rank contexts never
-// reach the exchange; the reductions are the identity.  The multi-GPU implementation (NCCL send/recv over
-// NVLink, one rank per GPU) replaces FBoxLib's MPI-based multifab_fill_boundary / parallel_reduce.
+// vdn_comm.cu -- inter-rank plumbing of the hot path: one rank per GPU, NCCL over NVLink/NVSwitch.
+//
+// Replaces FBoxLib's MPI layer for this path:
+//   multifab_fill_boundary between boxes of different ranks  -> pack kernel + grouped ncclSend/ncclRecv + unpack kernel,
+//       direction by direction (x, then y over the x-ghosted range, then z) so edge/corner ghosts need no diagonal messages
+//   norm_inf / parallel_reduce (macproject.f90:65,203; F_MG residual norms) -> ncclAllReduce(double, MAX/SUM)
+//   F_MG coarse levels -> agglomeration: ncclAllGather of the coarse right-hand side / coefficients, every GPU then
+//       finishes the V-cycle locally on the whole coarse domain (no scatter step needed)
+// The decomposition must be a tensor-product grid of rectangular regions (what boxarray_maxsize + a block map gives).
 #include "vdn_ctx.h"
+#include "vdn_comm.h"
+#include <nccl.h>
+#include <algorithm>
 
-struct Comm { int rank = 0, nranks = 1; };
+#define VDN_NCCL(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+    char b_[512]; snprintf(b_, sizeof b_, "%s:%d NCCL error %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+    throw VdnError(b_); } } while (0)
 
-void comm_destroy(Comm *cm) { delete cm; }
-void comm_exchange(vdn_ctx *c, int field, int d) { (void)c; (void)field; (void)d; }
-double comm_allreduce_max(vdn_ctx *c, double v) { (void)c; return v; }
-double comm_allreduce_sum(vdn_ctx *c, double v) { (void)c; return v; }
+struct Comm {
+    int rank = 0, nranks = 1;
+    ncclComm_t nccl = nullptr;
+    int nbr[3][2];                 // neighbour rank per (dir, side); -1 = none (physical boundary); == rank = periodic self
+    int pgrid[3] = {1, 1, 1}, pcoord[3] = {0, 0, 0};
+    std::vector<int> rlo, rhi;     // all regions [nranks][3]
+    double *sbuf = nullptr, *rbuf = nullptr; size_t buf_doubles = 0;
+    double *d_scal = nullptr;
+};
+
+// ---- host-only planning (testable without a GPU) ----
+extern "C" int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo, const int *region_hi,
+                             const int *dom_lo, const int *dom_hi, const int *phys_bc, int *nbr, int *pgrid, int *pcoord)
+{
+    if (rank < 0 || rank >= nranks) return 1;
+    const int *mlo = &region_lo[rank * 3], *mhi = &region_hi[rank * 3];
+    for (int d = 0; d < 3; ++d) { pgrid[d] = 1; pcoord[d] = 0; nbr[d * 2] = nbr[d * 2 + 1] = -1; }
+    for (int d = 0; d < dim; ++d) {
+        // process-grid extent and my coordinate along d: distinct lower bounds among regions sharing my transverse extents
+        std::vector<int> los;
+        for (int r = 0; r < nranks; ++r) {
+            bool same = true;
+            for (int t = 0; t < dim; ++t) if (t != d && (region_lo[r * 3 + t] != mlo[t] || region_hi[r * 3 + t] != mhi[t])) same = false;
+            if (same) los.push_back(region_lo[r * 3 + d]);
+        }
+        std::sort(los.begin(), los.end());
+        pgrid[d] = (int)los.size();
+        for (int q = 0; q < pgrid[d]; ++q) if (los[q] == mlo[d]) pcoord[d] = q;
+        const bool per = phys_bc[d * 2] == BC_PERIODIC;
+        for (int s = 0; s < 2; ++s) {
+            int want;                               // the lower (s=1) / upper (s=0) bound the neighbour must have along d
+            bool wrapd = false;
+            if (s == 1) { want = mhi[d] + 1; if (mhi[d] == dom_hi[d]) { if (!per) continue; want = dom_lo[d]; wrapd = true; } }
+            else        { want = mlo[d] - 1; if (mlo[d] == dom_lo[d]) { if (!per) continue; want = dom_hi[d]; wrapd = true; } }
+            (void)wrapd;
+            int found = -1;
+            for (int r = 0; r < nranks; ++r) {
+                bool same = true;
+                for (int t = 0; t < dim; ++t) if (t != d && (region_lo[r * 3 + t] != mlo[t] || region_hi[r * 3 + t] != mhi[t])) same = false;
+                if (!same) continue;
+                if (s == 1 ? region_lo[r * 3 + d] == want : region_hi[r * 3 + d] == want) found = r;
+            }
+            if (found < 0) return 2;               // not a tensor-product decomposition
+            nbr[d * 2 + s] = found;
+        }
+    }
+    long cells = 0, dom = 1;
+    for (int r = 0; r < nranks; ++r) { long c = 1; for (int d = 0; d < dim; ++d) c *= region_hi[r * 3 + d] - region_lo[r * 3 + d] + 1; cells += c; }
+    for (int d = 0; d < dim; ++d) dom *= dom_hi[d] - dom_lo[d] + 1;
+    if (cells != dom || pgrid[0] * pgrid[1] * pgrid[2] != nranks) return 2;
+    return 0;
+}
+
+extern "C" int vdn_nccl_unique_id(void *out128)
+{
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, 128);
+    return 0;
+}
+
+// ---- pack / unpack of up to 6 rectangular segments in one launch ----
+struct Seg { int lo[3], n[3]; long off; };
+struct PackArgs { View v; int nc; int nseg; Seg seg[6]; double *buf; int unpack; };
+__global__ void k_pack(PackArgs a)
+{
+    const Seg &s = a.seg[blockIdx.y];
+    const long per = (long)s.n[0] * s.n[1] * s.n[2];
+    const long tot = per * a.nc;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t / per); const long q = t - (long)c * per;
+        const int i = s.lo[0] + (int)(q % s.n[0]), j = s.lo[1] + (int)((q / s.n[0]) % s.n[1]), k = s.lo[2] + (int)(q / ((long)s.n[0] * s.n[1]));
+        if (a.unpack) a.v(i, j, k, c) = a.buf[s.off + t]; else a.buf[s.off + t] = a.v(i, j, k, c);
+    }
+}
+
+static void launch_pack(vdn_ctx *c, PackArgs &a)
+{
+    if (a.nseg == 0) return;
+    long mx = 0;
+    for (int q = 0; q < a.nseg; ++q) mx = std::max(mx, (long)a.seg[q].n[0] * a.seg[q].n[1] * a.seg[q].n[2] * a.nc);
+    dim3 gr((unsigned)std::min<long>(1184, (mx + 255) / 256), a.nseg);
+    k_pack<<<gr, 256, 0, c->stream>>>(a);
+    VDN_CUDA(cudaGetLastError());
+}
+
+static void ensure_buf(vdn_ctx *c, size_t doubles)
+{
+    Comm *cm = c->comm;
+    if (doubles <= cm->buf_doubles) return;
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+    if (cm->sbuf) cudaFree(cm->sbuf);
+    if (cm->rbuf) cudaFree(cm->rbuf);
+    cm->buf_doubles = doubles + doubles / 4;
+    VDN_CUDA(cudaMalloc(&cm->sbuf, sizeof(double) * cm->buf_doubles));
+    VDN_CUDA(cudaMalloc(&cm->rbuf, sizeof(double) * cm->buf_doubles));
+}
+
+// Exchange along the directions in `dirs` (bit mask) of an array described by (v, n, ng, nc, fdir).
+// grow_prev: transverse range includes ghosts in directions < d (the x->y->z cascade that fills corners).
+void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fdir, int dmask, bool grow_prev)
+{
+    Comm *cm = c->comm;
+    if (!cm || ng == 0) return;
+    PackArgs ps; ps.v = v; ps.nc = nc; ps.nseg = 0; ps.unpack = 0;
+    PackArgs pu = ps; pu.unpack = 1;
+    struct Msg { int peer; long off, cnt; };
+    std::vector<Msg> sends, recvs;
+    long soff = 0, roff = 0;
+    for (int d = 0; d < dim; ++d) {
+        if (!((dmask >> d) & 1)) continue;
+        const int nod = (fdir == d) ? 1 : 0;
+        int tlo[3], tn[3];
+        for (int t = 0; t < 3; ++t) {
+            if (t >= dim) { tlo[t] = 0; tn[t] = 1; continue; }
+            const int ext = n[t] + (fdir == t ? 1 : 0);
+            if (grow_prev && t < d) { tlo[t] = -ng; tn[t] = ext + 2 * ng; } else { tlo[t] = 0; tn[t] = ext; }
+        }
+        Msg rcv_of_side[2]; bool has[2] = { false, false };
+        for (int s = 0; s < 2; ++s) {
+            const int peer = cm->nbr[d][s];
+            if (peer < 0 || peer == cm->rank) continue;
+            Seg snd, rcv;
+            for (int t = 0; t < 3; ++t) { snd.lo[t] = rcv.lo[t] = tlo[t]; snd.n[t] = rcv.n[t] = tn[t]; }
+            snd.n[d] = rcv.n[d] = ng;
+            if (s == 0) { snd.lo[d] = nod ? 1 : 0;  rcv.lo[d] = -ng; }                       // to/from the lo neighbour
+            else        { snd.lo[d] = n[d] - ng;    rcv.lo[d] = n[d] + nod; }                // to/from the hi neighbour
+            const long cnt = (long)snd.n[0] * snd.n[1] * snd.n[2] * nc;
+            snd.off = soff; rcv.off = roff;
+            ps.seg[ps.nseg++] = snd; pu.seg[pu.nseg++] = rcv;
+            sends.push_back({ peer, soff, cnt });
+            rcv_of_side[s] = { peer, roff, cnt }; has[s] = true;
+            soff += cnt; roff += cnt;
+        }
+        // messages to one peer are matched in issue order: sends go (lo, hi), receives (hi, lo), so that with a single
+        // peer on both sides (2 ranks along a periodic direction) its lo slab lands in my hi ghost and vice versa
+        if (has[1]) recvs.push_back(rcv_of_side[1]);
+        if (has[0]) recvs.push_back(rcv_of_side[0]);
+    }
+    if (ps.nseg == 0) return;
+    ensure_buf(c, (size_t)std::max(soff, roff));
+    ps.buf = cm->sbuf; pu.buf = cm->rbuf;
+    launch_pack(c, ps);
+    VDN_NCCL(ncclGroupStart());
+    for (const Msg &m : sends) VDN_NCCL(ncclSend(cm->sbuf + m.off, (size_t)m.cnt, ncclDouble, m.peer, cm->nccl, c->stream));
+    for (const Msg &m : recvs) VDN_NCCL(ncclRecv(cm->rbuf + m.off, (size_t)m.cnt, ncclDouble, m.peer, cm->nccl, c->stream));
+    VDN_NCCL(ncclGroupEnd());
+    launch_pack(c, pu);
+}
+
+void comm_exchange(vdn_ctx *c, int field, int d)
+{
+    DField &f = c->f[field];
+    LaunchScope ls(c, "halo_exchange", 0.0, 2);
+    comm_halo(c, f.view(), c->geo.n, c->dim, f.ng, f.nc, f.fdir, 1 << d, true);
+}
+
+static double allreduce(vdn_ctx *c, double v, ncclRedOp_t op)
+{
+    Comm *cm = c->comm;
+    if (!cm || cm->nranks == 1) return v;
+    c->h_pin[8] = v;
+    VDN_CUDA(cudaMemcpyAsync(cm->d_scal, &c->h_pin[8], 8, cudaMemcpyHostToDevice, c->stream));
+    VDN_NCCL(ncclAllReduce(cm->d_scal, cm->d_scal, 1, ncclDouble, op, cm->nccl, c->stream));
+    VDN_CUDA(cudaMemcpyAsync(&c->h_pin[9], cm->d_scal, 8, cudaMemcpyDeviceToHost, c->stream));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+    return c->h_pin[9];
+}
+double comm_allreduce_max(vdn_ctx *c, double v) { return allreduce(c, v, ncclMax); }
+double comm_allreduce_sum(vdn_ctx *c, double v) { return allreduce(c, v, ncclSum); }
+
+int comm_rank(const vdn_ctx *c) { return c->comm ? c->comm->rank : 0; }
+int comm_nranks(const vdn_ctx *c) { return c->comm ? c->comm->nranks : 1; }
+const int *comm_pgrid(const vdn_ctx *c) { return c->comm->pgrid; }
+const int *comm_pcoord(const vdn_ctx *c) { return c->comm->pcoord; }
+bool comm_has_neighbor(const vdn_ctx *c, int d, int s) { return c->comm && c->comm->nbr[d][s] >= 0 && c->comm->nbr[d][s] != c->comm->rank; }
+
+// all-gather equal-sized blocks (count doubles per rank): send -> recv[nranks*count]
+void comm_allgather(vdn_ctx *c, const double *send, double *recv, size_t count)
+{
+    VDN_NCCL(ncclAllGather(send, recv, count, ncclDouble, c->comm->nccl, c->stream));
+}
+// coordinates of rank r in the process grid
+void comm_coord_of(const vdn_ctx *c, int r, int *pc)
+{
+    const Comm *cm = c->comm;
+    for (int d = 0; d < 3; ++d) {
+        if (d >= c->dim) { pc[d] = 0; continue; }
+        const int nloc = c->geo.n[d];
+        pc[d] = (cm->rlo[r * 3 + d] - c->dom_lo[d]) / nloc;
+    }
+}
+
+void comm_destroy(Comm *cm)
+{
+    if (!cm) return;
+    if (cm->nccl) ncclCommDestroy(cm->nccl);
+    if (cm->sbuf) cudaFree(cm->sbuf);
+    if (cm->rbuf) cudaFree(cm->rbuf);
+    if (cm->d_scal) cudaFree(cm->d_scal);
+    delete cm;
+}
+
+void ctx_rebuild_bc(vdn_ctx *c);      // vdn_ctx.cu
 
 extern "C" int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *region_lo, const int *region_hi, const void *nccl_unique_id)
 {
-    (void)region_lo; (void)region_hi; (void)nccl_unique_id; (void)rank;
     if (!ctx) return 1;
-    if (nranks == 1) return 0;
-    ctx->err = "multi-rank contexts are not built in this library version";
-    return 1;
+    try {
+        VDN_CUDA(cudaSetDevice(ctx->device));
+        if (nranks == 1) return 0;
+        VDN_REQUIRE(!ctx->comm, "communicator already set");
+        VDN_REQUIRE(!ctx->mg, "vdn_ctx_set_comm must be called before the first solve");
+        for (int d = 0; d < ctx->dim; ++d)
+            VDN_REQUIRE(region_lo[rank * 3 + d] == ctx->rlo[d] && region_hi[rank * 3 + d] == ctx->rhi[d], "region of this rank does not match its boxes");
+        Comm *cm = new Comm();
+        cm->rank = rank; cm->nranks = nranks;
+        cm->rlo.assign(region_lo, region_lo + 3 * nranks); cm->rhi.assign(region_hi, region_hi + 3 * nranks);
+        int pbc[6]; for (int d = 0; d < 3; ++d) { pbc[d * 2] = ctx->dom_bc[d][0]; pbc[d * 2 + 1] = ctx->dom_bc[d][1]; }
+        int nb[6];
+        int rc = vdn_comm_plan(ctx->dim, rank, nranks, region_lo, region_hi, ctx->dom_lo, ctx->dom_hi, pbc, nb, cm->pgrid, cm->pcoord);
+        if (rc) { delete cm; throw VdnError("regions are not a tensor-product decomposition of the domain"); }
+        for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) cm->nbr[d][s] = nb[d * 2 + s];
+        for (int r = 0; r < nranks; ++r) for (int d = 0; d < ctx->dim; ++d)
+            if (region_hi[r * 3 + d] - region_lo[r * 3 + d] + 1 != ctx->geo.n[d]) { delete cm; throw VdnError("all ranks must own regions of equal size"); }
+        ncclUniqueId id; memcpy(&id, nccl_unique_id, 128);
+        ctx->comm = cm;
+        VDN_NCCL(ncclCommInitRank(&cm->nccl, nranks, id, rank));
+        VDN_CUDA(cudaMalloc(&cm->d_scal, 64));
+        // region faces with a rank neighbour are INTERIOR; periodic directions spanned by this rank alone keep wrapping
+        for (int d = 0; d < ctx->dim; ++d) {
+            for (int s = 0; s < 2; ++s) {
+                const bool at_dom = s == 0 ? (ctx->rlo[d] == ctx->dom_lo[d]) : (ctx->rhi[d] == ctx->dom_hi[d]);
+                ctx->geo.pbc[d][s] = at_dom ? ctx->dom_bc[d][s] : BC_INTERIOR;
+            }
+            ctx->wrap[d] = ctx->dom_bc[d][0] == BC_PERIODIC && cm->nbr[d][0] == rank;
+        }
+        ctx_rebuild_bc(ctx);
+        return 0;
+    } catch (const std::exception &e) { ctx->err = e.what(); return 1; }
 }

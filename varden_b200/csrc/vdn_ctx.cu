@@ -76,6 +76,8 @@ static void build_bc_tables(vdn_ctx *c)
     }
 }
 
+void ctx_rebuild_bc(vdn_ctx *c) { build_bc_tables(c); }
+
 // sng = storage ghost width (>= ng).  RH and BETA_* are stored in the multigrid's padded layout (sng = 1, extent n+2
 // in every direction, which also holds the n+1 faces) so that MG level 0 can alias them without copies.
 static void alloc_field(vdn_ctx *c, int id, int ng, int nc, int fdir, int sng = -1)

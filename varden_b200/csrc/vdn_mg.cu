@@ -12,6 +12,7 @@
 // Physical BCs are synthesised in the stencil (Neumann: no flux; Dirichlet: 3*phi0 - phi1/3 one-sided), periodic
 // directions owned by one rank wrap by index, so a single GPU needs no ghost-fill launches at all.
 #include "vdn_ctx.h"
+#include "vdn_comm.h"
 
 enum : int { M_GHOST = 0, M_NEU = 1, M_DIR = 2, M_WRAP = 3 };
 
@@ -35,6 +36,12 @@ struct MG {
     double h0[3];
     cudaGraphExec_t coarse_graph = nullptr;     // levels 1..bottom of one V-cycle (latency-bound launches), captured once
     int coarse_graph_launches = 0;
+    bool distributed = false;                   // levels exchange halos with neighbour ranks
+    // agglomeration (multi-rank): local level agg_level is solved on `tail`, a whole-domain hierarchy every rank holds
+    int agg_level = -1;
+    MG *tail = nullptr;
+    double *agg_send = nullptr, *agg_recv = nullptr;
+    int *d_coords = nullptr;                    // [nranks][3] process-grid coordinates
 };
 
 namespace {
@@ -227,27 +234,58 @@ template <class F> void for_dim(int dim, F f) { if (dim == 3) f(std::integral_co
 
 dim3 cgrid(int nx, int ny, int nz) { return dim3(cdiv(nx, BLK.x), cdiv(ny, BLK.y), nz); }
 
-void mg_build(vdn_ctx *c)
+
+// ---- agglomeration kernels: contiguous block <-> padded level array ----
+struct BlkArgs { double *arr; long off, s1, s2; int ex[3]; double *buf; int nranks; const int *coords; int nloc[3]; int mine[3]; };
+__global__ void k_blk_pack(BlkArgs a)           // buf[t] = arr(block of this rank)
 {
-    MG *m = new MG(); c->mg = m;
+    const long tot = (long)a.ex[0] * a.ex[1] * a.ex[2];
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % a.ex[0]), j = (int)((t / a.ex[0]) % a.ex[1]), k = (int)(t / ((long)a.ex[0] * a.ex[1]));
+        a.buf[t] = a.arr[a.off + i + a.s1 * j + a.s2 * k];
+    }
+}
+__global__ void k_blk_unpack(BlkArgs a)         // arr(global) <- buf[r][t] for every rank r (blockIdx.y)
+{
+    const int r = blockIdx.y;
+    const long tot = (long)a.ex[0] * a.ex[1] * a.ex[2];
+    const int ox = a.coords[r * 3] * a.nloc[0], oy = a.coords[r * 3 + 1] * a.nloc[1], oz = a.coords[r * 3 + 2] * a.nloc[2];
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % a.ex[0]), j = (int)((t / a.ex[0]) % a.ex[1]), k = (int)(t / ((long)a.ex[0] * a.ex[1]));
+        a.arr[a.off + (ox + i) + a.s1 * (oy + j) + a.s2 * (oz + k)] = a.buf[(long)r * tot + t];
+    }
+}
+struct ExtArgs { const double *src; long soff, ss1, ss2; double *dst; long doff, ds1, ds2; int ex[3]; int o[3]; };
+__global__ void k_blk_extract(ExtArgs a)        // local phi <- my block of the global phi
+{
+    const long tot = (long)a.ex[0] * a.ex[1] * a.ex[2];
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % a.ex[0]), j = (int)((t / a.ex[0]) % a.ex[1]), k = (int)(t / ((long)a.ex[0] * a.ex[1]));
+        a.dst[a.doff + i + a.ds1 * j + a.ds2 * k] = a.src[a.soff + (a.o[0] + i) + a.ss1 * (a.o[1] + j) + a.ss2 * (a.o[2] + k)];
+    }
+}
+
+// Build a hierarchy for a grid of n cells (spacing h, global index origin glo) with per-face modes.
+// alias0: level 0 uses the context's PHI / RH / BETA_* storage.  max_levels < 0: coarsen as far as possible.
+MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, const int (*mode)[2], bool alias0, int max_levels)
+{
+    MG *m = new MG();
     m->dim = c->dim;
-    const Geo &g = c->geo;
-    // level count: halve while every direction stays even and >= 2 afterwards (F_MG min_width = 2)
-    int nn[3] = { g.n[0], g.n[1], g.n[2] };
+    int nn[3] = { n_in[0], n_in[1], n_in[2] };
     int nlev = 1;
-    for (;;) {
+    for (;;) {          // halve while every direction stays even and >= 2 afterwards (F_MG min_width = 2)
         bool ok = true;
         for (int d = 0; d < c->dim; ++d) if (nn[d] % 2 != 0 || nn[d] / 2 < 2) ok = false;
-        if (!ok) break;
+        if (!ok || (max_levels > 0 && nlev >= max_levels)) break;
         for (int d = 0; d < c->dim; ++d) nn[d] /= 2;
         ++nlev;
     }
     m->nlev = nlev; m->L.resize(nlev);
     m->singular = true;
     for (int d = 0; d < c->dim; ++d) for (int s = 0; s < 2; ++s) if (c->dom_bc[d][s] == BC_OUTLET) m->singular = false;
-    int n[3] = { g.n[0], g.n[1], g.n[2] };
-    double h[3] = { g.h[0], g.h[1], g.h[2] };
-    int glo[3] = { c->rlo[0], c->rlo[1], c->rlo[2] };
+    int n[3] = { n_in[0], n_in[1], n_in[2] };
+    double h[3] = { h_in[0], h_in[1], h_in[2] };
+    int glo[3] = { glo_in[0], glo_in[1], glo_in[2] };
     for (int l = 0; l < nlev; ++l) {
         Lev &L = m->L[l];
         for (int d = 0; d < 3; ++d) { L.n[d] = n[d]; L.h2inv[d] = 1.0 / (h[d] * h[d]); }
@@ -255,13 +293,9 @@ void mg_build(vdn_ctx *c)
         L.ntot = L.s[2] * (c->dim == 3 ? n[2] + 2 : 1);
         L.off = 1 + L.s[1] + (c->dim == 3 ? L.s[2] : 0);
         L.par0 = (glo[0] + glo[1] + (c->dim == 3 ? glo[2] : 0)) & 1;
-        for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) {
-            int e = d < c->dim ? c->ell_bc[d][s] : ELL_NEU;
-            L.mode[d][s] = e == ELL_NEU ? M_NEU : e == ELL_DIR ? M_DIR : (e == ELL_PER && c->wrap[d]) ? M_WRAP : M_GHOST;
-        }
+        for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) { L.mode[d][s] = d < c->dim ? mode[d][s] : M_NEU; if (L.mode[d][s] == M_GHOST) m->distributed = true; }
         auto dalloc = [&](long cnt) { double *p; VDN_CUDA(cudaMalloc(&p, sizeof(double) * cnt)); VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cnt, c->stream)); m->owned.push_back(p); return p; };
-        if (l == 0) {
-            // level 0 aliases the context fields; they were allocated with the same padded layout
+        if (l == 0 && alias0) {
             L.phi = c->f[VDN_PHI].base; L.rhs = c->f[VDN_RH].base;
             for (int d = 0; d < c->dim; ++d) L.b[d] = c->f[VDN_BETA_X + d].base;
             VDN_REQUIRE(c->f[VDN_RH].sy == L.s[1] && c->f[VDN_PHI].sy == L.s[1] && c->f[VDN_BETA_X].sy == L.s[1], "level-0 layout mismatch");
@@ -275,6 +309,82 @@ void mg_build(vdn_ctx *c)
     }
     for (int q = 0; q < 6; ++q) { VDN_CUDA(cudaMalloc(&m->bot[q], sizeof(double) * m->L[nlev - 1].ntot)); VDN_CUDA(cudaMemsetAsync(m->bot[q], 0, sizeof(double) * m->L[nlev - 1].ntot, c->stream)); }
     VDN_CUDA(cudaMalloc(&m->d_norm, 64));
+    return m;
+}
+
+void mg_build(vdn_ctx *c)
+{
+    const Geo &g = c->geo;
+    int mode[3][2];
+    for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) {
+        int e = d < c->dim ? c->ell_bc[d][s] : ELL_NEU;
+        mode[d][s] = e == ELL_NEU ? M_NEU : e == ELL_DIR ? M_DIR : (e == ELL_PER && c->wrap[d]) ? M_WRAP : M_GHOST;
+    }
+    const int nr = comm_nranks(c);
+    if (nr == 1) { c->mg = mg_make(c, g.n, g.h, c->rlo, mode, true, -1); return; }
+    // multi-rank: distributed levels down to a local size of <= 32 cells per direction, then agglomerate
+    int nloc[3] = { g.n[0], g.n[1], g.n[2] };
+    int ndist = 1;
+    for (;;) {
+        int mx = 0; bool ok = true;
+        for (int d = 0; d < c->dim; ++d) { mx = std::max(mx, nloc[d]); if (nloc[d] % 2 != 0 || nloc[d] / 2 < 2) ok = false; }
+        if (mx <= 32 || !ok) break;
+        for (int d = 0; d < c->dim; ++d) nloc[d] /= 2;
+        ++ndist;
+    }
+    MG *m = mg_make(c, g.n, g.h, c->rlo, mode, true, ndist);
+    c->mg = m;
+    m->agg_level = m->nlev - 1;
+    Lev &A = m->L[m->agg_level];
+    const int *pg = comm_pgrid(c);
+    int gn[3], gl[3] = { 0, 0, 0 }, gmode[3][2];
+    double gh[3];
+    for (int d = 0; d < 3; ++d) {
+        gn[d] = d < c->dim ? A.n[d] * pg[d] : 1;
+        gh[d] = d < c->dim ? g.h[d] * (double)(g.n[d] / A.n[d]) : 1.0;
+        gl[d] = d < c->dim ? (c->dom_lo[d] / (g.n[d] / A.n[d])) : 0;
+        for (int s = 0; s < 2; ++s) {
+            int p = d < c->dim ? c->dom_bc[d][s] : BC_SLIP_WALL;
+            gmode[d][s] = p == BC_PERIODIC ? M_WRAP : p == BC_OUTLET ? M_DIR : M_NEU;
+        }
+    }
+    m->tail = mg_make(c, gn, gh, gl, gmode, false, -1);
+    long mxblk = 1;
+    for (int d = 0; d < c->dim; ++d) mxblk *= (A.n[d] + 1);
+    VDN_CUDA(cudaMalloc(&m->agg_send, sizeof(double) * mxblk));
+    VDN_CUDA(cudaMalloc(&m->agg_recv, sizeof(double) * mxblk * nr));
+    std::vector<int> coords(3 * nr);
+    for (int r = 0; r < nr; ++r) comm_coord_of(c, r, &coords[3 * r]);
+    VDN_CUDA(cudaMalloc(&m->d_coords, sizeof(int) * 3 * nr));
+    VDN_CUDA(cudaMemcpy(m->d_coords, coords.data(), sizeof(int) * 3 * nr, cudaMemcpyHostToDevice));
+}
+
+// gather one array of the local agglomeration level (cells, or faces along fdir) into the tail's level 0 on every rank
+void agg_gather(vdn_ctx *c, MG *m, double *local, double *global, int fdir)
+{
+    Lev &A = m->L[m->agg_level]; Lev &T = m->tail->L[0];
+    const int nr = comm_nranks(c);
+    BlkArgs a; a.arr = local; a.off = A.off; a.s1 = A.s[1]; a.s2 = A.s[2];
+    for (int d = 0; d < 3; ++d) { a.ex[d] = A.n[d] + (d == fdir ? 1 : 0); a.nloc[d] = A.n[d]; a.mine[d] = 0; }
+    a.buf = m->agg_send; a.nranks = nr; a.coords = m->d_coords;
+    const long tot = (long)a.ex[0] * a.ex[1] * a.ex[2];
+    const int nb = (int)std::min<long>(592, (tot + 255) / 256);
+    LaunchScope ls(c, "mg_agglomerate", 0.0, 2);
+    k_blk_pack<<<nb, 256, 0, c->stream>>>(a);
+    comm_allgather(c, m->agg_send, m->agg_recv, (size_t)tot);
+    BlkArgs u = a; u.arr = global; u.off = T.off; u.s1 = T.s[1]; u.s2 = T.s[2]; u.buf = m->agg_recv;
+    k_blk_unpack<<<dim3(nb, nr), 256, 0, c->stream>>>(u);
+    VDN_CUDA(cudaGetLastError());
+}
+
+void mg_halo(vdn_ctx *c, MG *m, Lev &L, double *x)
+{
+    if (!m->distributed) return;
+    View v; v.p = x + L.off; v.sy = L.s[1]; v.sz = L.s[2]; v.cs = L.ntot;
+    int dmask = 0;
+    for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
+    LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
+    comm_halo(c, v, L.n, m->dim, 1, 1, -1, dmask, false);
 }
 
 void smooth(vdn_ctx *c, MG *m, int l, int sweeps)
@@ -283,6 +393,7 @@ void smooth(vdn_ctx *c, MG *m, int l, int sweeps)
     const double cells = (double)L.n[0] * L.n[1] * L.n[2];
     for (int s = 0; s < sweeps; ++s)
         for (int color = 0; color < 2; ++color) {
+            mg_halo(c, m, L, L.phi);        // fill_boundary(phi) before each colour, as F_MG does
             // one colour half-sweep = R phi 8 + rhs 4 + beta 24 (3-D), W phi 4 = 40 B/cell
             LaunchScope ls(c, l == 0 ? "mg_gsrb_l0" : "mg_gsrb_coarse", cells * (m->dim == 3 ? 40.0 : 32.0));
             dim3 gr(cdiv((L.n[0] + 1) / 2, BLK.x), cdiv(L.n[1], BLK.y), L.n[2]);
@@ -293,14 +404,35 @@ void residual(vdn_ctx *c, MG *m, int l, double *nrm)
 {
     Lev &L = m->L[l];
     const double cells = (double)L.n[0] * L.n[1] * L.n[2];
+    mg_halo(c, m, L, L.phi);
     LaunchScope ls(c, l == 0 ? "mg_residual_l0" : "mg_residual_coarse", cells * (m->dim == 3 ? 48.0 : 40.0));
     if (nrm) VDN_CUDA(cudaMemsetAsync(nrm, 0, 8, c->stream));
     for_dim(m->dim, [&](auto D) { k_residual<decltype(D)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, nrm); });
 }
 
+void mg_capture_coarse(vdn_ctx *c, MG *m, int from_level);
+
 void vcycle(vdn_ctx *c, MG *m, int l)
 {
     Lev &L = m->L[l];
+    if (m->tail && l == m->agg_level) {
+        // agglomerated coarse solve: every rank gathers the whole coarse right-hand side and finishes the V-cycle locally
+        MG *t = m->tail;
+        agg_gather(c, m, L.rhs, t->L[0].rhs, -1);
+        VDN_CUDA(cudaMemsetAsync(t->L[0].phi, 0, sizeof(double) * t->L[0].ntot, c->stream));
+        if (t->coarse_graph) {
+            LaunchScope ls(c, "mg_coarse_levels_graph", 0.0, t->coarse_graph_launches);
+            VDN_CUDA(cudaGraphLaunch(t->coarse_graph, c->stream));
+        } else vcycle(c, t, 0);
+        ExtArgs e; e.src = t->L[0].phi; e.soff = t->L[0].off; e.ss1 = t->L[0].s[1]; e.ss2 = t->L[0].s[2];
+        e.dst = L.phi; e.doff = L.off; e.ds1 = L.s[1]; e.ds2 = L.s[2];
+        const int *pc = comm_pcoord(c);
+        for (int d = 0; d < 3; ++d) { e.ex[d] = L.n[d]; e.o[d] = pc[d] * L.n[d]; }
+        LaunchScope ls(c, "mg_agglomerate", 0.0);
+        const long tot = (long)L.n[0] * L.n[1] * L.n[2];
+        k_blk_extract<<<(int)std::min<long>(592, (tot + 255) / 256), 256, 0, c->stream>>>(e);
+        return;
+    }
     if (l == m->nlev - 1) {
         LaunchScope ls(c, "mg_bottom", 0.0);
         BotVec w = { m->bot[0], m->bot[1], m->bot[2], m->bot[3], m->bot[4], m->bot[5] };
@@ -328,17 +460,15 @@ void vcycle(vdn_ctx *c, MG *m, int l)
     smooth(c, m, l, c->prm.mg_nu2);
 }
 
-} // namespace
-
-// capture levels 1..bottom of the V-cycle into a CUDA graph: ~70 tiny launches become one
-static void mg_capture_coarse(vdn_ctx *c, MG *m)
+// capture levels from_level..bottom of the V-cycle into a CUDA graph: ~70 tiny launches become one
+void mg_capture_coarse(vdn_ctx *c, MG *m, int from_level)
 {
-    if (m->nlev < 3 || m->coarse_graph) return;
+    if (m->nlev - from_level < 2 || m->coarse_graph || m->distributed) return;
     const bool prof = c->prof_on; c->prof_on = false;
     const long long l0 = c->launches;
     cudaGraph_t g = nullptr;
     VDN_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    try { vcycle(c, m, 1); } catch (...) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); c->prof_on = prof; throw; }
+    try { vcycle(c, m, from_level); } catch (...) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); c->prof_on = prof; throw; }
     VDN_CUDA(cudaStreamEndCapture(c->stream, &g));
     m->coarse_graph_launches = (int)(c->launches - l0);
     c->launches = l0;
@@ -347,27 +477,46 @@ static void mg_capture_coarse(vdn_ctx *c, MG *m)
     cudaGraphDestroy(g);
 }
 
+void coarsen_coefficients(vdn_ctx *c, MG *m)
+{
+    for (int l = 1; l < m->nlev; ++l) {
+        Lev &F = m->L[l - 1], &C = m->L[l];
+        LaunchScope ls(c, "mg_coarsen_beta", 0.0, m->dim);
+        for (int d = 0; d < m->dim; ++d)
+            for_dim(m->dim, [&](auto D) { k_coarsen_beta<decltype(D)::value><<<cgrid(C.n[0] + (d == 0), C.n[1] + (d == 1), C.n[2] + (d == 2 ? 1 : 0)), BLK, 0, c->stream>>>(F, C, d); });
+    }
+}
+
+} // namespace
+
 void mg_destroy(MG *m)
 {
     if (!m) return;
+    if (m->tail) mg_destroy(m->tail);
     if (m->coarse_graph) cudaGraphExecDestroy(m->coarse_graph);
     for (double *p : m->owned) cudaFree(p);
     for (int q = 0; q < 6; ++q) if (m->bot[q]) cudaFree(m->bot[q]);
     if (m->d_norm) cudaFree(m->d_norm);
+    if (m->agg_send) cudaFree(m->agg_send);
+    if (m->agg_recv) cudaFree(m->agg_recv);
+    if (m->d_coords) cudaFree(m->d_coords);
     delete m;
 }
 
 // Solve with RH / BETA_* as right-hand side / coefficients and PHI as initial guess and result.
 int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm)
 {
-    if (!c->mg) { mg_build(c); mg_capture_coarse(c, c->mg); }
+    if (!c->mg) {
+        mg_build(c);
+        if (c->mg->tail) mg_capture_coarse(c, c->mg->tail, 0); else mg_capture_coarse(c, c->mg, 1);
+    }
     MG *m = c->mg;
     // coefficient hierarchy
-    for (int l = 1; l < m->nlev; ++l) {
-        Lev &F = m->L[l - 1], &C = m->L[l];
-        LaunchScope ls(c, "mg_coarsen_beta", 0.0, m->dim);
-        for (int d = 0; d < m->dim; ++d)
-            for_dim(m->dim, [&](auto D) { k_coarsen_beta<decltype(D)::value><<<cgrid(C.n[0] + (d == 0), C.n[1] + (d == 1), C.n[2] + (d == 2 ? 1 : 0)), BLK, 0, c->stream>>>(F, C, d); });
+    coarsen_coefficients(c, m);
+    if (m->tail) {
+        Lev &A = m->L[m->agg_level];
+        for (int d = 0; d < m->dim; ++d) agg_gather(c, m, A.b[d], m->tail->L[0].b[d], d);
+        coarsen_coefficients(c, m->tail);
     }
     VDN_CUDA(cudaGetLastError());
     const double bnorm = st_absmax_valid(c, VDN_RH);
@@ -379,14 +528,15 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
     };
     double rn = res_norm();
     int cyc = 0;
-    if (c->prm.mg_verbose) printf("vdn_mg: levels %d  |rh| = %.6e  initial |r| = %.6e\n", m->nlev, bnorm, rn);
+    const bool talk = c->prm.mg_verbose && comm_rank(c) == 0;
+    if (talk) printf("vdn_mg: levels %d%s  |rh| = %.6e  initial |r| = %.6e\n", m->nlev, m->tail ? " (+ agglomerated tail)" : "", bnorm, rn);
     auto converged = [&](double r) { return r <= rel_eps * bnorm || r <= abs_eps; };
     while (bnorm > 0.0 && !converged(rn) && cyc < c->prm.mg_max_cycles) {
         vcycle(c, m, 0);
         VDN_CUDA(cudaGetLastError());
         rn = res_norm();
         ++cyc;
-        if (c->prm.mg_verbose) printf("vdn_mg: cycle %2d  |r|/|rh| = %.6e\n", cyc, rn / bnorm);
+        if (talk) printf("vdn_mg: cycle %2d  |r|/|rh| = %.6e\n", cyc, rn / bnorm);
     }
     if (ncycles) *ncycles = cyc;
     if (resnorm) *resnorm = bnorm > 0.0 ? rn / bnorm : 0.0;
