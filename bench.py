@@ -144,14 +144,30 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
-        raise SystemExit("bench.py: multi-GPU arm is not wired in this revision")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # weak scaling: one 256^3 reference box (max_grid_size = 256, _parameters:27) per GPU; the process grid fills z, y, x
     n = args.n
-    geom, st, dt = rt_problem(n, dim=3, max_grid_size=args.max_grid_size, ratio=args.ratio)
+    pgrid = {1: [1, 1, 1], 2: [1, 1, 2], 4: [1, 2, 2], 8: [2, 2, 2]}.get(world)
+    if pgrid is None:
+        raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
+    nglob = [n * pgrid[d] for d in range(3)]
+    mgs = min(args.max_grid_size, n)
+    from varden_b200.problems import Geom, PERIODIC, NO_SLIP_WALL
+    from varden_b200 import parallel as PAR
+    gfull = Geom(3, nglob, [[PERIODIC, PERIODIC], [PERIODIC, PERIODIC], [NO_SLIP_WALL, NO_SLIP_WALL]],
+                 prob_hi=[float(p) for p in pgrid], max_grid_size=mgs)
+    ids, rlo, rhi, pg = PAR.partition(gfull, world)
+    geom, st, dt = rt_problem(nglob, dim=3, max_grid_size=mgs, ratio=args.ratio, prob_hi=[float(p) for p in pgrid], box_ids=ids[rank])
+    ncells_global = gfull.ncells
     dim, nscal = 3, 2
     prm = V.default_params()
-    ctx = V.Context(3, geom.boxes, geom.dlo, geom.dhi, geom.phys_bc, geom.dx, params=prm, device=local)
+    ctx = V.Context(3, geom.boxes, gfull.dlo, gfull.dhi, gfull.phys_bc, gfull.dx, params=prm, device=local)
+    if world > 1:
+        PAR.init_comm(ctx, rank, world, rlo, rhi)
 
     # ---- pinned host buffers = what the Fortran driver would hand over (ghosts filled as varden.f90:291-300) ----
     spec_in = [("UOLD", "uold", 3, dim), ("SOLD", "sold", 3, nscal), ("GP", "gp", 1, dim),
@@ -201,38 +217,51 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     xs = torch.cuda.ExternalStream(ctx.stream_ptr())        # the library's launching stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    barrier()
     t0 = time.perf_counter()
     ev0.record(xs)
     for _ in range(args.steps):
         cyc, res = step_resident()
     ev1.record(xs)
-    ctx.sync()
-    torch.cuda.synchronize()
+    barrier()
     wall_host = time.perf_counter() - t0
-    wall = ev0.elapsed_time(ev1) / 1e3                       # device time by CUDA events on the launching stream
+    wall = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)       # device time by CUDA events on the launching stream, max over ranks
     launches = ctx.launch_count() - l0
     prof = ctx.prof_report()
     ctx.prof_enable(False)
     dev_ms = sum(p["ms"] for p in prof.values())
     # one in-order stream; the host only syncs for the per-V-cycle residual norm, so event time ~ host wall time
     ms_per_step = 1e3 * wall / args.steps
-    value = geom.ncells * args.steps / wall / 1e9
+    value = ncells_global * args.steps / wall / 1e9
 
     # ---- e2e timing (host buffers, copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
         for _ in range(2):
             step_e2e()
-        ctx.sync()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(xs)
         for _ in range(args.steps):
             step_e2e()
         e1.record(xs)
-        ctx.sync()
-        t_e = e0.elapsed_time(e1) / 1e3
-        e2e = {"value": geom.ncells * args.steps / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        barrier()
+        t_e = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+        e2e = {"value": ncells_global * args.steps / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                "ms_per_step": 1e3 * t_e / args.steps}
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -255,7 +284,7 @@ def main():
                 "traffic": None, "peak_source": peak_src, "avg_launch_ms": t["ms_total"] / max(t["launches"], 1), "share_of_step": t["share"]}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
         v, t, ccyc = cpu_oracle_rate(args.cpu_n, args.ratio, 1)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -265,14 +294,19 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D %d^3 single-level variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, "
-                                   "MAC rel tol 1e-10, %d box(es)" % (n, args.ratio, geom.nboxes),
+                                   "MAC rel tol 1e-10, %d^3 box per GPU, global %dx%dx%d" % (n, args.ratio, n, nglob[0], nglob[1], nglob[2]),
+                       "parallelism": "1 region per GPU, process grid %s, NCCL halo + allreduce, coarse MG levels agglomerated" % pgrid if world > 1 else "single GPU",
                        "l2_policy": "inputs (%.1f GB of fields) exceed the 126 MB L2; no explicit flush" % (45 * 8 * (n + 6) ** 3 / 1e9),
                        "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
                        "host_wall_ms_per_step": 1e3 * wall_host / args.steps},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "kernels": fam}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
     ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

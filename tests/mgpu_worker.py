@@ -24,7 +24,7 @@ from util import relerr                  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default="rt3d")
-    ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--size", dest="n", type=int, default=64)
     ap.add_argument("--tol", type=float, default=1e-10)
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

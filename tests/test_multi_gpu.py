@@ -22,7 +22,7 @@ def test_multi_gpu_parity(case, n, world):
     if case == "rt2d" and world == 8:
         pytest.skip("2-D: 4 boxes")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--n", str(n)]
+           "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--size", str(n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-3000:])
     assert r.returncode == 0

@@ -328,10 +328,11 @@ void mg_build(vdn_ctx *c)
     for (;;) {
         int mx = 0; bool ok = true;
         for (int d = 0; d < c->dim; ++d) { mx = std::max(mx, nloc[d]); if (nloc[d] % 2 != 0 || nloc[d] / 2 < 2) ok = false; }
-        if (mx <= 32 || !ok) break;
+        if ((mx <= 32 && ndist >= 2) || !ok) break;     // keep at least one distributed level above the agglomerated one
         for (int d = 0; d < c->dim; ++d) nloc[d] /= 2;
         ++ndist;
     }
+    VDN_REQUIRE(ndist >= 2, "multi-rank multigrid needs a local region that can be coarsened at least once (even sizes >= 4)");
     MG *m = mg_make(c, g.n, g.h, c->rlo, mode, true, ndist);
     c->mg = m;
     m->agg_level = m->nlev - 1;

@@ -94,18 +94,22 @@ def _h(x):
     return 0.02 * np.sin(4.0 * np.pi * x) + 0.01 * np.sin(8.0 * np.pi * x)
 
 
-def rt_problem(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, nscal=2, seeded_velocity=True, phys_bc=None):
+def rt_problem(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, nscal=2, seeded_velocity=True, phys_bc=None,
+               prob_hi=(1., 1., 1.), box_ids=None):
     """
     Density-stratified Rayleigh-Taylor-type state: periodic in x(,y), no-slip walls in the last direction
     (exec/test/inputs_RayleighTaylor_3d:32-37).  rho = mid + amp*tanh((z - 1/2 - h(x) - h(y))/0.01); ratio 2 reproduces
     initdata.f90:270 exactly (1.5 + 0.5 tanh).  VALID cells only are initialised; ghost cells are the caller's job
-    (varden.f90:291-300: fill_boundary + multifab_physbc).  Returns (geom, state dict, dt).
+    (varden.f90:291-300: fill_boundary + multifab_physbc).  Returns (geom, state dict, dt); with box_ids the returned
+    geom holds only those boxes (same domain).
     """
     if np.isscalar(n):
         n = [n] * dim
     if phys_bc is None:
         phys_bc = [[PERIODIC, PERIODIC]] * (dim - 1) + [[NO_SLIP_WALL, NO_SLIP_WALL]]
-    geom = Geom(dim, n, phys_bc, max_grid_size=max_grid_size)
+    geom = Geom(dim, n, phys_bc, prob_hi=prob_hi, max_grid_size=max_grid_size)
+    if box_ids is not None:          # one rank's share: only these boxes are materialised
+        geom = geom.subset(box_ids)
     mid, amp = 0.5 * (float(ratio) + 1.0), 0.5 * (float(ratio) - 1.0)
     st = dict(uold=mf_alloc(geom, 3, dim), sold=mf_alloc(geom, 3, nscal), gp=mf_alloc(geom, 1, dim),
               ext_vel_force=mf_alloc(geom, 1, dim), ext_scal_force=mf_alloc(geom, 1, nscal))
