@@ -302,3 +302,57 @@ def stagewise(geom, params, st, dt, mac_rel_eps=-1.0):
     o["unew"] = mf_alloc(geom, 3, dim)
     update(geom, params, st["uold"], dim, o["umac"], o["uedge"], uflux, o["vel_force_2"], o["unew"], dt, True, [0] * dim)
     return o
+
+
+# ---------------------------------------------------------------------------------------------
+# macproject glue, stage by stage (macproject.f90:137-225, :280-336, :403-505) -- used by the reference-pin tests
+# ---------------------------------------------------------------------------------------------
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ia(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def _box_bc(geom, ib):
+    g = geom.to_c()
+    pb, ell = (C.c_int * 6)(), (C.c_int * 6)()
+    lib().orc_box_phys_bc(C.byref(g), C.c_int(ib), pb)
+    lib().orc_ell_bc_press(pb, C.c_int(geom.dim), ell)
+    return pb, ell
+
+
+def divumac(geom, umac, mac_rhs, rh):
+    """rh = mac_rhs - div(umac)"""
+    dim = geom.dim
+    dx = (C.c_double * 3)(*geom.dx)
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        lib().orc_divumac(_dp(umac[0][ib]), _dp(umac[1][ib]), _dp(umac[2][ib]) if dim == 3 else None, C.c_int(1),
+                          _dp(mac_rhs[ib]), C.c_int(1), _dp(rh[ib]), C.c_int(0), dx, _ia(lo), _ia(hi), C.c_int(dim))
+
+
+def mk_mac_coeffs(geom, rho, ng_r, beta):
+    dim = geom.dim
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        lib().orc_mk_mac_coeffs(_dp(beta[0][ib]), _dp(beta[1][ib]), _dp(beta[2][ib]) if dim == 3 else None, C.c_int(0),
+                                _dp(rho[ib]), C.c_int(ng_r), _ia(lo), _ia(hi), C.c_int(dim))
+
+
+def project_with_phi(geom, params, umac_pred, rho, ncomp_s, phi):
+    """mk_mac_coeffs + mkumac + fill_boundary(umac) for a GIVEN phi (whose ghost cells get filled here); returns umac."""
+    dim = geom.dim
+    beta = [mf_alloc(geom, 0, 1, d) for d in range(dim)]
+    mk_mac_coeffs(geom, rho, 3, beta)
+    ph = [a.copy(order='F') for a in phi]
+    fill_boundary(geom, ph, 1, 1)
+    um = [[a.copy(order='F') for a in umac_pred[d]] for d in range(dim)]
+    dx = (C.c_double * 3)(*geom.dx)
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        _, ell = _box_bc(geom, ib)
+        lib().orc_mkumac(_dp(um[0][ib]), _dp(um[1][ib]), _dp(um[2][ib]) if dim == 3 else None, C.c_int(1), _dp(ph[ib]), C.c_int(1),
+                         _dp(beta[0][ib]), _dp(beta[1][ib]), _dp(beta[2][ib]) if dim == 3 else None, C.c_int(0),
+                         _ia(lo), _ia(hi), C.c_int(dim), dx, ell)
+    for d in range(dim):
+        fill_boundary(geom, um[d], 1, 1, face_dir=d)
+    return um

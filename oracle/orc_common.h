@@ -5,15 +5,13 @@
  * bench.py's cpu_baseline / --impl reference legs may call it.  The product
  * (varden_b200/libvdn.so) never links or loads anything from oracle/.
  *
- * Parity status: the reference ships no golden vectors for this path and
- * cannot be built here (no Fortran compiler, FBoxLib absent).  The Godunov /
- * update / physbc / macproject-glue arithmetic is pinned against the reference
- * by oracle/f2c (a mechanical Fortran->C transpile of the reference's own
- * per-box routines, built into oracle/_ref/ when /root/reference is present)
- * and by the golden fixtures under tests/golden/ generated from it.
- * The multigrid (FBoxLib F_MG, third party, absent, version unpinned) is
- * "parity unpinned": the oracle restates the published algorithm and is
- * checked against a direct sparse solve of the same discrete operator.
+ * Parity status: PINNED for the Godunov / update / physbc / force / macproject-glue arithmetic -- oracle/f2c.py
+ * transpiles the reference's own per-box Fortran routines to C (oracle/_ref/, built where /root/reference is
+ * mounted) and tests/test_ref_pin.py demands bit-identical results stage by stage; tests/golden/*.npz carry the
+ * same reference outputs to machines without the reference tree (tests/test_golden.py).
+ * The multigrid (FBoxLib F_MG, third party, absent, version unpinned) and multifab_fill_boundary (FBoxLib) are
+ * "parity unpinned": restated from the published algorithm / documented semantics; the MG is checked against a
+ * direct sparse solve of the same discrete operator.
  *
  * Array convention everywhere: Fortran column-major boxes with ghost cells,
  *   a(lo1-ng:hi1+ng, lo2-ng:hi2+ng, lo3-ng:hi3+ng, ncomp), i fastest,
