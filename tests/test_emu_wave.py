@@ -1,0 +1,135 @@
+"""
+CPU execution of the REAL k_wave kernel source (varden_b200/csrc/vdn_mg_wave.cuh) under tests/emu/cuda_emu.h
+(one OS thread per CUDA thread, std::barrier for __syncthreads), checked against a plain numpy red-black
+Gauss-Seidel / residual / restriction / prolongation of the same operator (mac_multigrid.f90:53-62 selects these).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+M_NEU, M_DIR, M_WRAP = 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU, "libemu_wave.so")
+    src = [os.path.join(EMU, "emu_wave.cpp"), os.path.join(EMU, "cuda_emu.h"),
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_wave.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
+                               src[0], "-o", so])
+    return C.CDLL(so)
+
+
+def pad(n):
+    return (n[2] + 2, n[1] + 2, n[0] + 2)
+
+
+def fill_wrap(p, n, mode):
+    for d, ax in ((0, 2), (1, 1), (2, 0)):
+        if mode[d][0] == M_WRAP:
+            sl_lo = [slice(None)] * 3; sl_hi = [slice(None)] * 3; src_lo = [slice(None)] * 3; src_hi = [slice(None)] * 3
+            sl_lo[ax] = 0; src_lo[ax] = n[d]
+            sl_hi[ax] = n[d] + 1; src_hi[ax] = 1
+            p[tuple(sl_lo)] = p[tuple(src_lo)]
+            p[tuple(sl_hi)] = p[tuple(src_hi)]
+
+
+def apply_A(phi, b, h2, mode, n):
+    """A*phi and diag on valid cells; b[d][idx] = coefficient on the LOW d-face of cell idx (padded arrays, z,y,x order)."""
+    p = phi.copy()
+    fill_wrap(p, n, mode)
+    V = (slice(1, n[2] + 1), slice(1, n[1] + 1), slice(1, n[0] + 1))
+    p0 = p[V]
+    ax = np.zeros_like(p0); dg = np.zeros_like(p0)
+    for d, axis in ((0, 2), (1, 1), (2, 0)):
+        def sh(a, o):
+            s = list(V); s[axis] = slice(1 + o, n[d] + 1 + o); return a[tuple(s)]
+        blo, bhi = sh(b[d], 0), sh(b[d], 1)
+        pm, pp = sh(p, -1), sh(p, 1)
+        idx = np.arange(n[d]).reshape([-1 if a == axis else 1 for a in range(3)])
+        atlo, athi = idx == 0, idx == n[d] - 1
+        lo_reg = blo * (p0 - pm) * h2[d]; hi_reg = bhi * (p0 - pp) * h2[d]
+        lo_dir = blo * (3.0 * p0 - pp / 3.0) * h2[d]; hi_dir = bhi * (3.0 * p0 - pm / 3.0) * h2[d]
+        mlo, mhi = mode[d]
+        lo = np.where(atlo & (mlo == M_NEU), 0.0, np.where(atlo & (mlo == M_DIR), lo_dir, lo_reg))
+        hi = np.where(athi & (mhi == M_NEU), 0.0, np.where(athi & (mhi == M_DIR), hi_dir, hi_reg))
+        glo = np.where(atlo & (mlo == M_NEU), 0.0, np.where(atlo & (mlo == M_DIR), 3.0, 1.0)) * blo * h2[d]
+        ghi = np.where(athi & (mhi == M_NEU), 0.0, np.where(athi & (mhi == M_DIR), 3.0, 1.0)) * bhi * h2[d]
+        ax += lo + hi; dg += glo + ghi
+    return ax, dg
+
+
+def gsrb(phi, rhs, b, h2, mode, n, par0, sweeps):
+    V = (slice(1, n[2] + 1), slice(1, n[1] + 1), slice(1, n[0] + 1))
+    k, j, i = np.meshgrid(np.arange(n[2]), np.arange(n[1]), np.arange(n[0]), indexing="ij")
+    par = (i + j + k + par0) & 1
+    phi = phi.copy()
+    for _ in range(sweeps):
+        for color in (0, 1):
+            ax, dg = apply_A(phi, b, h2, mode, n)
+            upd = phi[V] + (rhs[V] - ax) / dg
+            phi[V] = np.where(par == color, upd, phi[V])
+    return phi
+
+
+CASES = [
+    # n, cfg, zchunk, mode, par0
+    ((64, 32, 16), 1, 8, ((M_WRAP, M_WRAP), (M_WRAP, M_WRAP), (M_NEU, M_NEU)), 0),
+    ((64, 32, 16), 1, 16, ((M_NEU, M_DIR), (M_DIR, M_NEU), (M_NEU, M_NEU)), 1),
+    ((128, 32, 8), 0, 4, ((M_WRAP, M_WRAP), (M_NEU, M_NEU), (M_WRAP, M_WRAP)), 0),
+    ((40, 24, 12), 1, 6, ((M_NEU, M_NEU), (M_WRAP, M_WRAP), (M_DIR, M_DIR)), 0),     # ragged tiles
+]
+
+
+@pytest.mark.parametrize("n,cfg,zchunk,mode,par0", CASES)
+@pytest.mark.parametrize("nsw,pre,post", [(2, 0, 2), (2, 1, 3), (1, 0, 0), (1, 1, 0), (1, 0, 2), (2, 1, 0), (1, 0, 3)])
+def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, nsw, pre, post):
+    rng = np.random.default_rng(1234 + n[0] + 7 * nsw + pre + 3 * post)
+    shp = pad(n)
+    cn = tuple(x // 2 for x in n)
+    h2 = np.array([1.0 / 0.01 ** 2, 1.0 / 0.012 ** 2, 1.0 / 0.009 ** 2])
+    b = [np.ascontiguousarray(0.5 + rng.random(shp)) for _ in range(3)]
+    # periodic: the face at index n equals the face at index 0
+    for d, axis in ((0, 2), (1, 1), (2, 0)):
+        if mode[d][0] == M_WRAP:
+            s_hi = [slice(None)] * 3; s_lo = [slice(None)] * 3
+            s_hi[axis] = n[d] + 1; s_lo[axis] = 1
+            b[d][tuple(s_hi)] = b[d][tuple(s_lo)]
+    rhs = np.ascontiguousarray(rng.standard_normal(shp))
+    phi = np.ascontiguousarray(rng.standard_normal(shp))
+    cphi = np.ascontiguousarray(rng.standard_normal(pad(cn)))
+    V = (slice(1, n[2] + 1), slice(1, n[1] + 1), slice(1, n[0] + 1))
+    CV = (slice(1, cn[2] + 1), slice(1, cn[1] + 1), slice(1, cn[0] + 1))
+    _, dg = apply_A(phi, b, h2, mode, n)
+    dgi = np.zeros(shp); dgi[V] = 1.0 / dg
+    out = np.full(shp, np.nan)
+    crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan)
+    nrm = np.zeros(1)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu.emu_wave(nsw, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), par0, P(h2),
+                      P(rhs), P(dgi), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk)
+    assert rc == 0
+    # reference
+    start = phi.copy()
+    if pre:
+        start[V] += np.repeat(np.repeat(np.repeat(cphi[CV], 2, axis=0), 2, axis=1), 2, axis=2)
+    ref = gsrb(start, rhs, b, h2, mode, n, par0, nsw)
+    scale = np.abs(ref[V]).max()
+    assert np.all(np.isfinite(out[V]))
+    assert np.abs(out[V] - ref[V]).max() <= 1e-12 * scale
+    if post:
+        ax, _ = apply_A(ref, b, h2, mode, n)
+        res = rhs[V] - ax
+        rs = np.abs(res).max()
+        if post == 3:
+            assert abs(nrm[0] - rs) <= 1e-10 * rs
+        else:
+            cr = res.reshape(cn[2], 2, cn[1], 2, cn[0], 2).mean(axis=(1, 3, 5))
+            assert np.abs(crhs[CV] - cr).max() <= 1e-10 * rs
+            assert np.all(czero[CV] == 0.0)

@@ -150,3 +150,39 @@ def test_mg_high_density_ratio():
         assert e <= TOL_MAC, (d, e)
     ctx.close()
     print("ratio 1000: vcycles", ncyc, "res", res, "oracle cycles", ref["mac_cycles"])
+
+
+@pytest.mark.parametrize("case", ["rt64", "mixed"])
+@pytest.mark.parametrize("fuse,tile", [(2, -1), (1, -1), (2, 0), (2, 1)])
+def test_mg_fused_wavefront(case, fuse, tile, monkeypatch):
+    """the fused wavefront smoother (k_wave: GSRB sweeps + residual + restriction / prolongation in one launch) against the
+    plain per-colour kernels and the oracle: same V-cycle, so phi and the projected velocity agree to the solver tolerance"""
+    if case == "rt64":
+        geom, P, st, dt = O.rt_state(64, dim=3, max_grid_size=64)
+    else:
+        geom, P, st, dt = O.random_state([48, 32, 64], dim=3, max_grid_size=64, phys_bc=[[IN, OUT], [NS, W], [PER, PER]], seed=11)
+    ref = O.stagewise(geom, P, st, dt, mac_rel_eps=1e-13)
+    out = {}
+    for mode in ("plain", "fused"):
+        monkeypatch.setenv("VDN_MG_FUSE", "0" if mode == "plain" else str(fuse))
+        monkeypatch.setenv("VDN_MG_FUSE_MIN", "16")
+        monkeypatch.setenv("VDN_MG_TILE", str(tile))
+        ctx = make_ctx(geom, P)
+        upload_state(ctx, geom, P, st)
+        ctx.mkvelforce("SOLD", 1.0)
+        ctx.velpred(dt)
+        ncyc, res = ctx.macproject(rel_eps=1e-11)
+        assert res <= 1e-11
+        um = [download_like(ctx, geom, "UMAC_" + "XYZ"[d], ref["umac"][d], 1, 1) for d in range(3)]
+        out[mode] = (ncyc, res, um, ctx.launch_count())
+        ctx.close()
+    scale = max(np.abs(O.valid(geom, ref["umac"][d][0], 0, 1, d)).max() for d in range(3))
+    for d in range(3):
+        a = O.valid(geom, out["fused"][2][d][0], 0, 1, d); b = O.valid(geom, out["plain"][2][d][0], 0, 1, d)
+        r = O.valid(geom, ref["umac"][d][0], 0, 1, d)
+        assert np.abs(a - b).max() / scale <= TOL_MAC, (d, np.abs(a - b).max() / scale)
+        assert np.abs(a - r).max() / scale <= TOL_MAC
+    # same algorithm => same cycle count (+-1 for round-off at the stopping test); far fewer launches
+    assert abs(out["fused"][0] - out["plain"][0]) <= 1, (out["fused"][0], out["plain"][0])
+    assert out["fused"][3] < out["plain"][3]
+    print(case, fuse, tile, "cycles fused/plain", out["fused"][0], out["plain"][0], "launches", out["fused"][3], out["plain"][3])

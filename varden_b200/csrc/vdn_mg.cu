@@ -13,8 +13,9 @@
 // directions owned by one rank wrap by index, so a single GPU needs no ghost-fill launches at all.
 #include "vdn_ctx.h"
 #include "vdn_comm.h"
+#include "vdn_mg_wave.cuh"
+#include <algorithm>
 
-enum : int { M_GHOST = 0, M_NEU = 1, M_DIR = 2, M_WRAP = 3 };
 
 struct Lev {
     int n[3];
@@ -24,6 +25,7 @@ struct Lev {
     int mode[3][2];
     int par0;               // parity of the global index of local cell (0,0,0)
     double *phi, *rhs, *res, *b[3];
+    double *dgi;            // 1/diagonal (fused wavefront levels only, else nullptr)
 };
 
 struct MG {
@@ -36,12 +38,18 @@ struct MG {
     double h0[3];
     cudaGraphExec_t coarse_graph = nullptr;     // levels 1..bottom of one V-cycle (latency-bound launches), captured once
     int coarse_graph_launches = 0;
+    int graph_level = 1;                        // first level executed by the captured graph
     bool distributed = false;                   // levels exchange halos with neighbour ranks
     // agglomeration (multi-rank): local level agg_level is solved on `tail`, a whole-domain hierarchy every rank holds
     int agg_level = -1;
     MG *tail = nullptr;
     double *agg_send = nullptr, *agg_recv = nullptr;
     int *d_coords = nullptr;                    // [nranks][3] process-grid coordinates
+    // fused wavefront smoother (k_wave): levels 0..nfused-1 of a rank-local 3-D hierarchy
+    int nfused = 0;                             // number of leading levels that run the fused kernels
+    int fuse_nsw = 2;                           // GSRB sweeps fused per launch (1 or 2)
+    int tile_force = -1, zchunk_force = 0;      // tuning overrides (VDN_MG_TILE, VDN_MG_ZCHUNK)
+    int sm_count = 148;
 };
 
 namespace {
@@ -152,6 +160,20 @@ __global__ void k_coarsen_beta(Lev F, Lev C, int d)
         s = 0.25 * (F.b[d][cf] + F.b[d][cf + ta] + F.b[d][cf + tb] + F.b[d][cf + ta + tb]);
     }
     C.b[d][C.off + i + C.s[1] * j + C.s[2] * k] = s;
+}
+
+// 1/diagonal of the operator (the same face rules as cell_op)
+template <int DIM>
+__global__ void k_dginv(Lev L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.n[0] || j >= L.n[1]) return;
+    const long c = L.off + i + L.s[1] * j + L.s[2] * k;
+    const int ix[3] = { i, j, k };
+    double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+    L.dgi[c] = dg != 0.0 ? 1.0 / dg : 0.0;
 }
 
 // ---- bottom solver: BiCGStab in ONE CTA (the coarsest level is a handful of cells); dot products use
@@ -305,6 +327,7 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         }
         for (int d = c->dim; d < 3; ++d) L.b[d] = nullptr;
         L.res = dalloc(L.ntot);
+        L.dgi = nullptr;
         for (int d = 0; d < c->dim; ++d) { n[d] /= 2; h[d] *= 2.0; glo[d] /= 2; }
     }
     for (int q = 0; q < 6; ++q) { VDN_CUDA(cudaMalloc(&m->bot[q], sizeof(double) * m->L[nlev - 1].ntot)); VDN_CUDA(cudaMemsetAsync(m->bot[q], 0, sizeof(double) * m->L[nlev - 1].ntot, c->stream)); }
@@ -321,7 +344,29 @@ void mg_build(vdn_ctx *c)
         mode[d][s] = e == ELL_NEU ? M_NEU : e == ELL_DIR ? M_DIR : (e == ELL_PER && c->wrap[d]) ? M_WRAP : M_GHOST;
     }
     const int nr = comm_nranks(c);
-    if (nr == 1) { c->mg = mg_make(c, g.n, g.h, c->rlo, mode, true, -1); return; }
+    if (nr == 1) {
+        MG *m = mg_make(c, g.n, g.h, c->rlo, mode, true, -1);
+        c->mg = m;
+        // fused wavefront smoother on the leading (large) levels of a rank-local 3-D hierarchy
+        auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
+        const int fuse = envi("VDN_MG_FUSE", 2), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
+        m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
+        cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
+        if (fuse > 0 && c->dim == 3 && !m->distributed && c->prm.mg_nu1 >= 1 && c->prm.mg_nu2 >= 1) {
+            m->fuse_nsw = fuse >= 2 ? 2 : 1;
+            while (m->nfused < m->nlev - 1) {
+                const Lev &L = m->L[m->nfused];
+                if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
+                ++m->nfused;
+            }
+            for (int l = 0; l < m->nfused; ++l) {
+                double *p; VDN_CUDA(cudaMalloc(&p, sizeof(double) * m->L[l].ntot));
+                VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * m->L[l].ntot, c->stream));
+                m->owned.push_back(p); m->L[l].dgi = p;
+            }
+        }
+        return;
+    }
     // multi-rank: distributed levels down to a local size of <= 32 cells per direction, then agglomerate
     int nloc[3] = { g.n[0], g.n[1], g.n[2] };
     int ndist = 1;
@@ -411,6 +456,96 @@ void residual(vdn_ctx *c, MG *m, int l, double *nrm)
     for_dim(m->dim, [&](auto D) { k_residual<decltype(D)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, nrm); });
 }
 
+
+// ---- fused wavefront launcher ----
+struct WaveVariant { const void *fn = nullptr; size_t smem = 0; int occ = 0; int H = 0, W = 0, HH = 0, TX = 0, TY = 0, NT = 0; };
+template <int NSW, int PRE, int POST, int TX, int TY, int NT>
+WaveVariant wave_variant()
+{
+    constexpr int S = 2 * NSW, E = POST ? 1 : 0, H = S + E, NP = S + 4;
+    WaveVariant v;
+    v.fn = (const void *)k_wave<NSW, PRE, POST, TX, TY, NT>;
+    v.smem = sizeof(double) * NP * (TX + 2 * H) * (TY + 2 * H);
+    v.H = H; v.W = TX + 2 * H; v.HH = TY + 2 * H; v.TX = TX; v.TY = TY; v.NT = NT;
+    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, NT, v.smem));
+    VDN_REQUIRE(v.occ >= 1, "k_wave variant does not fit on an SM");
+    return v;
+}
+// [tile cfg][nsw-1][pre][post: 0 -> 0, 1 -> 2 (restrict), 2 -> 3 (norm)]
+WaveVariant &wave_get(int cfg, int nsw, int pre, int post)
+{
+    static WaveVariant tab[2][2][2][3];
+    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
+    WaveVariant &v = tab[cfg][nsw - 1][pre][pi];
+    if (v.fn) return v;
+#define WV(C, TX, TY, NT) \
+    if (cfg == C) { \
+        if (nsw == 1 && pre == 0 && post == 0) v = wave_variant<1, 0, 0, TX, TY, NT>(); \
+        if (nsw == 1 && pre == 0 && post == 2) v = wave_variant<1, 0, 2, TX, TY, NT>(); \
+        if (nsw == 1 && pre == 0 && post == 3) v = wave_variant<1, 0, 3, TX, TY, NT>(); \
+        if (nsw == 1 && pre == 1 && post == 0) v = wave_variant<1, 1, 0, TX, TY, NT>(); \
+        if (nsw == 1 && pre == 1 && post == 2) v = wave_variant<1, 1, 2, TX, TY, NT>(); \
+        if (nsw == 1 && pre == 1 && post == 3) v = wave_variant<1, 1, 3, TX, TY, NT>(); \
+        if (nsw == 2 && pre == 0 && post == 0) v = wave_variant<2, 0, 0, TX, TY, NT>(); \
+        if (nsw == 2 && pre == 0 && post == 2) v = wave_variant<2, 0, 2, TX, TY, NT>(); \
+        if (nsw == 2 && pre == 0 && post == 3) v = wave_variant<2, 0, 3, TX, TY, NT>(); \
+        if (nsw == 2 && pre == 1 && post == 0) v = wave_variant<2, 1, 0, TX, TY, NT>(); \
+        if (nsw == 2 && pre == 1 && post == 2) v = wave_variant<2, 1, 2, TX, TY, NT>(); \
+        if (nsw == 2 && pre == 1 && post == 3) v = wave_variant<2, 1, 3, TX, TY, NT>(); \
+    }
+    WV(0, 64, 16, 512)
+    WV(1, 32, 16, 256)
+#undef WV
+    VDN_REQUIRE(v.fn != nullptr, "no such k_wave variant");
+    return v;
+}
+
+// one fused launch on level l: nsw sweeps reading L.phi, writing L.res; then the two buffers swap roles
+void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
+{
+    Lev &L = m->L[l];
+    // pick tile shape and z-chunking: cost ~ waves * CTAs sharing an SM * iterations * plane cells
+    int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
+    for (int cfg = 0; cfg < 2; ++cfg) {
+        if (m->tile_force >= 0 && cfg != m->tile_force) continue;
+        const WaveVariant &v = wave_get(cfg, nsw, pre, post);
+        const long ntiles = (long)cdiv(L.n[0], v.TX) * cdiv(L.n[1], v.TY);
+        const long slots = (long)m->sm_count * v.occ;
+        for (int nz = 1; nz <= std::max(1, L.n[2] / 8); ++nz) {
+            int ch = (cdiv(L.n[2], nz) + 1) & ~1;
+            if (m->zchunk_force > 0) ch = m->zchunk_force & ~1;
+            const long ctas = ntiles * cdiv(L.n[2], ch);
+            const long waves = (ctas + slots - 1) / slots;
+            const long per_sm = std::min<long>(v.occ, (ctas + m->sm_count - 1) / m->sm_count);
+            const double cost = (double)waves * per_sm * (ch + 2 * v.H + 3) * v.W * v.HH;
+            if (cost < best * (1.0 - 1e-9)) { best = cost; best_cfg = cfg; best_ch = ch; }
+        }
+    }
+    const WaveVariant &v = wave_get(best_cfg, nsw, pre, post);
+    WaveArgs a;
+    for (int d = 0; d < 3; ++d) { a.n[d] = L.n[d]; a.h2[d] = L.h2inv[d]; a.mode[d][0] = L.mode[d][0]; a.mode[d][1] = L.mode[d][1]; }
+    a.s1 = L.s[1]; a.s2 = L.s[2]; a.off = L.off; a.par0 = L.par0;
+    a.rhs = L.rhs; a.dgi = L.dgi; a.b0 = L.b[0]; a.b1 = L.b[1]; a.b2 = L.b[2];
+    a.in = L.phi; a.out = L.res;
+    a.cphi = nullptr; a.crhs = nullptr; a.czero = nullptr; a.cs1 = a.cs2 = a.coff = 0;
+    if (pre || post == 2) {
+        Lev &C = m->L[l + 1];
+        a.cphi = C.phi; a.crhs = C.rhs; a.czero = C.phi; a.cs1 = C.s[1]; a.cs2 = C.s[2]; a.coff = C.off;
+    }
+    a.nrm = m->d_norm; a.zchunk = best_ch;
+    if (post == 3) VDN_CUDA(cudaMemsetAsync(m->d_norm, 0, 8, c->stream));
+    const double cells = (double)L.n[0] * L.n[1] * L.n[2];
+    // SURVEY 8(a) a8 per stage: colour half-sweep 40, residual 48, restriction 9, prolongation 17 B/cell
+    const double alg = cells * (nsw * 2 * 40.0 + (pre ? 17.0 : 0.0) + (post == 2 ? 48.0 + 9.0 : post == 3 ? 48.0 : 0.0));
+    const char *name = l == 0 ? (post == 2 ? "mg_wave_down_l0" : post == 3 ? "mg_wave_up_l0" : pre ? "mg_wave_pro_l0" : "mg_wave_smooth_l0") : "mg_wave_coarse";
+    LaunchScope ls(c, name, alg);
+    dim3 grid(cdiv(L.n[0], v.TX), cdiv(L.n[1], v.TY), cdiv(L.n[2], best_ch));
+    void *args[] = { (void *)&a };
+    VDN_CUDA(cudaLaunchKernel(v.fn, grid, dim3(v.NT), args, v.smem, c->stream));
+    std::swap(L.phi, L.res);
+}
+
 void mg_capture_coarse(vdn_ctx *c, MG *m, int from_level);
 
 void vcycle(vdn_ctx *c, MG *m, int l)
@@ -443,13 +578,29 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         return;
     }
     Lev &C = m->L[l + 1];
+    if (l < m->nfused) {
+        // fused wavefront path: [sweeps ... + residual + restriction] -> coarse -> [prolongation + sweeps ... (+ norm)]
+        auto coarse = [&]() {
+            if (m->coarse_graph && l + 1 == m->graph_level) {
+                LaunchScope ls(c, "mg_coarse_levels_graph", 0.0, m->coarse_graph_launches);
+                VDN_CUDA(cudaGraphLaunch(m->coarse_graph, c->stream));
+            } else vcycle(c, m, l + 1);
+        };
+        int rem = c->prm.mg_nu1;
+        while (rem > 0) { const int nsw = std::min(m->fuse_nsw, rem); rem -= nsw; wave_launch(c, m, l, nsw, 0, rem == 0 ? 2 : 0); }
+        coarse();
+        rem = c->prm.mg_nu2;
+        bool first = true;
+        while (rem > 0) { const int nsw = std::min(m->fuse_nsw, rem); rem -= nsw; wave_launch(c, m, l, nsw, first ? 1 : 0, (rem == 0 && l == 0) ? 3 : 0); first = false; }
+        return;
+    }
     smooth(c, m, l, c->prm.mg_nu1);
     residual(c, m, l, nullptr);
     {
         LaunchScope ls(c, l == 0 ? "mg_restrict_l0" : "mg_restrict_coarse", (double)L.n[0] * L.n[1] * L.n[2] * 9.0);
         for_dim(m->dim, [&](auto D) { k_restrict<decltype(D)::value><<<cgrid(C.n[0], C.n[1], C.n[2]), BLK, 0, c->stream>>>(L, C); });
     }
-    if (l == 0 && m->coarse_graph) {
+    if (m->coarse_graph && l + 1 == m->graph_level) {
         LaunchScope ls(c, "mg_coarse_levels_graph", 0.0, m->coarse_graph_launches);
         VDN_CUDA(cudaGraphLaunch(m->coarse_graph, c->stream));
     } else
@@ -472,6 +623,7 @@ void mg_capture_coarse(vdn_ctx *c, MG *m, int from_level)
     try { vcycle(c, m, from_level); } catch (...) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); c->prof_on = prof; throw; }
     VDN_CUDA(cudaStreamEndCapture(c->stream, &g));
     m->coarse_graph_launches = (int)(c->launches - l0);
+    m->graph_level = from_level;
     c->launches = l0;
     c->prof_on = prof;
     VDN_CUDA(cudaGraphInstantiate(&m->coarse_graph, g, 0));
@@ -509,7 +661,7 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
 {
     if (!c->mg) {
         mg_build(c);
-        if (c->mg->tail) mg_capture_coarse(c, c->mg->tail, 0); else mg_capture_coarse(c, c->mg, 1);
+        if (c->mg->tail) mg_capture_coarse(c, c->mg->tail, 0); else mg_capture_coarse(c, c->mg, std::max(1, c->mg->nfused));
     }
     MG *m = c->mg;
     // coefficient hierarchy
@@ -518,6 +670,11 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
         Lev &A = m->L[m->agg_level];
         for (int d = 0; d < m->dim; ++d) agg_gather(c, m, A.b[d], m->tail->L[0].b[d], d);
         coarsen_coefficients(c, m->tail);
+    }
+    for (int l = 0; l < m->nfused; ++l) {
+        Lev &L = m->L[l];
+        LaunchScope ls(c, "mg_dginv", (double)L.n[0] * L.n[1] * L.n[2] * 32.0);
+        k_dginv<3><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L);
     }
     VDN_CUDA(cudaGetLastError());
     const double bnorm = st_absmax_valid(c, VDN_RH);
@@ -535,9 +692,17 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
     while (bnorm > 0.0 && !converged(rn) && cyc < c->prm.mg_max_cycles) {
         vcycle(c, m, 0);
         VDN_CUDA(cudaGetLastError());
-        rn = res_norm();
+        if (m->nfused > 0) {            // the up-leg kernel of level 0 already reduced |rhs - A phi|_inf
+            VDN_CUDA(cudaMemcpyAsync(c->h_pin, m->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
+            VDN_CUDA(cudaStreamSynchronize(c->stream));
+            rn = comm_allreduce_max(c, c->h_pin[0]);
+        } else rn = res_norm();
         ++cyc;
         if (talk) printf("vdn_mg: cycle %2d  |r|/|rh| = %.6e\n", cyc, rn / bnorm);
+    }
+    if (m->nfused > 0 && m->L[0].phi != c->f[VDN_PHI].base) {       // odd number of ping-pong launches: result sits in the spare buffer
+        VDN_CUDA(cudaMemcpyAsync(c->f[VDN_PHI].base, m->L[0].phi, sizeof(double) * m->L[0].ntot, cudaMemcpyDeviceToDevice, c->stream));
+        std::swap(m->L[0].phi, m->L[0].res);
     }
     if (ncycles) *ncycles = cyc;
     if (resnorm) *resnorm = bnorm > 0.0 ? rn / bnorm : 0.0;
