@@ -30,6 +30,18 @@ using std::min; using std::max;
 // block-wide max then one "atomic" update: under emulation every thread just takes the lock
 inline void block_atomic_max(double v, double *out) { { std::lock_guard<std::mutex> g(emu_mutex); if (v > *out) *out = v; } __syncthreads(); }
 
+// kernels without __syncthreads: the threads of a CTA can simply run one after another on the calling thread
+template <class Kernel, class Args>
+void emu_launch_seq(Kernel k, dim3 grid, dim3 block, const Args &a)
+{
+    blockDim = block; gridDim = grid;
+    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx)
+        for (unsigned tz = 0; tz < block.z; ++tz) for (unsigned ty = 0; ty < block.y; ++ty) for (unsigned tx = 0; tx < block.x; ++tx) {
+            threadIdx = dim3(tx, ty, tz); blockIdx = dim3(bx, by, bz);
+            k(a);
+        }
+}
+
 template <class Kernel, class Args>
 void emu_launch(Kernel k, dim3 grid, int nthreads, const Args &a)
 {

@@ -1,6 +1,8 @@
 // vdn_common.cuh -- shared device/host definitions for the B200 VARDEN hot path (sm_100a, FP64).
 #pragma once
+#ifndef VDN_EMU
 #include <cuda_runtime.h>
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -99,3 +101,13 @@ __device__ __forceinline__ void block_atomic_max(double v, double *out)
 #endif
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+struct Range { int lo[3], hi[3]; };   // inclusive local index range
+static inline dim3 grid3(const Range &r, dim3 b)
+{
+    return dim3(cdiv(r.hi[0] - r.lo[0] + 1, b.x), cdiv(r.hi[1] - r.lo[1] + 1, b.y), cdiv(r.hi[2] - r.lo[2] + 1, b.z));
+}
+static inline Range mk_range(int l0, int h0, int l1, int h1, int l2, int h2)
+{
+    Range r; r.lo[0] = l0; r.hi[0] = h0; r.lo[1] = l1; r.hi[1] = h1; r.lo[2] = l2; r.hi[2] = h2; return r;
+}

@@ -105,6 +105,7 @@ static void ctx_build(vdn_ctx *c, const vdn_params *prm, int dim, int nboxes, co
     VDN_REQUIRE(prm->stencil_order == 2, "only stencil_order = 2 is implemented");
     VDN_REQUIRE(prm->slope_order == 0 || prm->slope_order == 2 || prm->slope_order == 4, "slope_order must be 0, 2 or 4");
     c->prm = *prm; c->dim = dim; c->device = device; c->nboxes = nboxes;
+    if (const char *e = getenv("VDN_GODUNOV_FUSE")) c->godunov_fuse = atoi(e);
     int ndev = 0;
     VDN_CUDA(cudaGetDeviceCount(&ndev));
     VDN_REQUIRE(ndev > 0, "no CUDA device: the hot path has no CPU fallback");

@@ -3,7 +3,6 @@
 #include "vdn_common.cuh"
 #include <array>
 
-struct Range { int lo[3], hi[3]; };   // inclusive local index range
 
 struct ProfEntry { std::string name; long long launches = 0; double ms = 0.0; double bytes = 0.0;
                    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; };
@@ -38,6 +37,7 @@ struct vdn_ctx {
     std::vector<cudaEvent_t> ev_pool;
     MG *mg = nullptr;
     Comm *comm = nullptr;
+    int godunov_fuse = 1;                               // 3-D: all directions of a Godunov stage per launch (VDN_GODUNOV_FUSE)
 
     View S(int q) const { View v; v.sy = s_sy; v.sz = s_sz; v.cs = s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
     long ncells() const { return (long)geo.n[0] * geo.n[1] * geo.n[2]; }
@@ -50,15 +50,6 @@ struct LaunchScope {
     ~LaunchScope();
 };
 void prof_collect(vdn_ctx *c);
-
-static inline dim3 grid3(const Range &r, dim3 b)
-{
-    return dim3(cdiv(r.hi[0] - r.lo[0] + 1, b.x), cdiv(r.hi[1] - r.lo[1] + 1, b.y), cdiv(r.hi[2] - r.lo[2] + 1, b.z));
-}
-static inline Range mk_range(int l0, int h0, int l1, int h1, int l2, int h2)
-{
-    Range r; r.lo[0] = l0; r.hi[0] = h0; r.lo[1] = l1; r.hi[1] = h1; r.lo[2] = l2; r.hi[2] = h2; return r;
-}
 
 // ---- stage implementations (each in its own .cu) ----
 void st_fill_boundary(vdn_ctx *c, int field);

@@ -10,477 +10,9 @@
 // results are bit-comparable with the CPU oracle.  eps is per reference box.
 #include "vdn_ctx.h"
 
+#include "vdn_godunov_kernels.cuh"
+
 namespace {
-
-constexpr double HALF = 0.5, ZERO = 0.0, ONE = 1.0, TWO = 2.0;
-
-// ------------------------------------------------------------------------------------------
-// slopes (slope.f90).  s points at cell m along a direction with stride st; n = region cells along it.
-// bclo/bchi: adv_bc is EXT_DIR or HOEXTRAP on that region face.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void slope_parts(const double *s, long st, double &cen, double &lim, double &flag, double &fromm)
-{
-    const double sm = s[-st], s0 = s[0], sp = s[st];
-    cen = HALF * (sp - sm);
-    const double dmn = TWO * (s0 - sm), dpls = TWO * (sp - s0);
-    lim = fmin(fabs(dmn), fabs(dpls));
-    lim = (dpls * dmn > ZERO) ? lim : ZERO;
-    flag = copysign(ONE, cen);
-    fromm = flag * fmin(lim, fabs(cen));
-}
-// one-sided 4th-order slope at the first interior cell next to a lo face (slope.f90:247-254); s points at that cell
-__device__ __forceinline__ double slope4_lo(const double *s, long st)
-{
-    const double two3rd = 2.0 / 3.0, tenth = 0.1;
-    double del = (-(16.0 / 15.0)) * s[-st] + HALF * s[0] + two3rd * s[st] - tenth * s[2 * st];
-    double dmn = TWO * (s[0] - s[-st]), dpls = TWO * (s[st] - s[0]);
-    double slim = fmin(fabs(dpls), fabs(dmn));
-    slim = (dpls * dmn > ZERO) ? slim : ZERO;
-    return copysign(ONE, del) * fmin(slim, fabs(del));
-}
-__device__ __forceinline__ double slope4_hi(const double *s, long st)   // slope.f90:268-275
-{
-    const double two3rd = 2.0 / 3.0, tenth = 0.1;
-    double del = -((-(16.0 / 15.0)) * s[st] + HALF * s[0] + two3rd * s[-st] - tenth * s[-2 * st]);
-    double dmn = TWO * (s[0] - s[-st]), dpls = TWO * (s[st] - s[0]);
-    double slim = fmin(fabs(dpls), fabs(dmn));
-    slim = (dpls * dmn > ZERO) ? slim : ZERO;
-    return copysign(ONE, del) * fmin(slim, fabs(del));
-}
-__device__ __forceinline__ double slope2_lo(const double *s, long st)   // slope.f90:193-200
-{
-    double del = (s[st] + 3.0 * s[0] - 4.0 * s[-st]) * (1.0 / 3.0);
-    double dpls = TWO * (s[st] - s[0]), dmn = TWO * (s[0] - s[-st]);
-    double slim = fmin(fabs(dpls), fabs(dmn));
-    slim = (dpls * dmn > ZERO) ? slim : ZERO;
-    return copysign(ONE, del) * fmin(slim, fabs(del));
-}
-__device__ __forceinline__ double slope2_hi(const double *s, long st)   // slope.f90:207-214
-{
-    double del = -(s[-st] + 3.0 * s[0] - 4.0 * s[st]) * (1.0 / 3.0);
-    double dpls = TWO * (s[0] - s[-st]), dmn = TWO * (s[st] - s[0]);
-    double slim = fmin(fabs(dpls), fabs(dmn));
-    slim = (dpls * dmn > ZERO) ? slim : ZERO;
-    return copysign(ONE, del) * fmin(slim, fabs(del));
-}
-__device__ double slope_at(const double *s, long st, int m, int n, bool bclo, bool bchi, int order)
-{
-    if (order == 0) return ZERO;
-    if ((bclo && m == -1) || (bchi && m == n)) return ZERO;
-    if (order == 2) {
-        if (bclo && m == 0) return slope2_lo(s, st);
-        if (bchi && m == n - 1) return slope2_hi(s, st);
-        double del = HALF * (s[st] - s[-st]);
-        double dpls = TWO * (s[st] - s[0]), dmn = TWO * (s[0] - s[-st]);
-        double slim = fmin(fabs(dpls), fabs(dmn));
-        slim = (dpls * dmn > ZERO) ? slim : ZERO;
-        return copysign(ONE, del) * fmin(slim, fabs(del));
-    }
-    if (bclo && m == 0) return slope4_lo(s, st);
-    if (bchi && m == n - 1) return slope4_hi(s, st);
-    const double two3rd = 2.0 / 3.0, sixth = 1.0 / 6.0;
-    double cen, lim, flag, fr, c2, l2, f2, frp, frm;
-    slope_parts(s, st, cen, lim, flag, fr);
-    slope_parts(s + st, st, c2, l2, f2, frp);
-    slope_parts(s - st, st, c2, l2, f2, frm);
-    if (bclo && m - 1 == 0) frm = slope4_lo(s - st, st);          // revised fromm(is), slope.f90:257
-    if (bchi && m + 1 == n - 1) frp = slope4_hi(s + st, st);      // revised fromm(ie), slope.f90:278
-    double ds = TWO * two3rd * cen - sixth * (frp + frm);
-    return flag * fmin(fabs(ds), lim);
-}
-
-struct SlopeArgs { Geo g; View s; View out[3]; int ncomp; int order; int bc[3][3][2]; Range r; };
-
-// slopes of up to 3 comps in all directions on cells -1..n
-__global__ void k_slopes(SlopeArgs a)
-{
-    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = a.r.lo[2] + blockIdx.z;
-    if (i > a.r.hi[0] || j > a.r.hi[1]) return;
-    const int ix[3] = { i, j, k };
-    for (int c = 0; c < a.ncomp; ++c) {
-        const double *p = &a.s(i, j, k, c);
-        for (int d = 0; d < a.g.dim; ++d) {
-            const bool bl = a.bc[c][d][0] == BC_EXT_DIR || a.bc[c][d][0] == BC_HOEXTRAP;
-            const bool bh = a.bc[c][d][1] == BC_EXT_DIR || a.bc[c][d][1] == BC_HOEXTRAP;
-            a.out[d](i, j, k, c) = slope_at(p, a.s.st(d), ix[d], a.g.n[d], bl, bh, a.order);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// shared Riemann / upwind / BC helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double riemann_n(double l, double r, double eps)      // velpred.f90:2084-2088
-{
-    double uavg = HALF * (l + r);
-    bool test = ((l <= ZERO && r >= ZERO) || (fabs(l + r) < eps));
-    double v = (uavg > ZERO) ? l : r;
-    return test ? ZERO : v;
-}
-__device__ __forceinline__ double upwind_t(double l, double r, double un, double eps)   // velpred.f90:2091-2093
-{
-    double v = (un > ZERO) ? l : r;
-    double uavg = HALF * (l + r);
-    return (fabs(un) < eps) ? uavg : v;
-}
-__device__ __forceinline__ double upw(double l, double r, double um, double eps)        // mkflux.f90:1520-1522
-{
-    double v = (um > ZERO) ? l : r;
-    double savg = HALF * (l + r);
-    return (fabs(um) > eps) ? v : savg;
-}
-template <int NC>
-__device__ __forceinline__ void bc_normal(double (&ul)[NC], double (&ur)[NC], int d, int side, int bc, const double (&ug)[NC], bool hi_outlet_min)
-{
-    if (bc == BC_INLET) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { ul[c] = ug[c]; ur[c] = ug[c]; }
-    } else if (bc == BC_SLIP_WALL) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            if (c == d) { ul[c] = ZERO; ur[c] = ZERO; }
-            else if (side == 0) ul[c] = ur[c]; else ur[c] = ul[c];
-        }
-    } else if (bc == BC_NO_SLIP_WALL) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { ul[c] = ZERO; ur[c] = ZERO; }
-    } else if (bc == BC_OUTLET) {
-        if (side == 0) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) { if (c == d) ur[c] = fmin(ur[c], ZERO); ul[c] = ur[c]; }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) { if (c == d) ul[c] = hi_outlet_min ? fmin(ul[c], ZERO) : fmax(ul[c], ZERO); ur[c] = ul[c]; }
-        }
-    }
-}
-__device__ __forceinline__ void bc_trans(double &l, double &r, int side, int bc, double ug)     // velpred.f90:2202-2221
-{
-    if (bc == BC_INLET) { l = ug; r = ug; }
-    else if (bc == BC_SLIP_WALL || bc == BC_OUTLET) { if (side == 0) l = r; else r = l; }
-    else if (bc == BC_NO_SLIP_WALL) { l = ZERO; r = ZERO; }
-}
-__device__ __forceinline__ double bc_mac(double v, double ml, double mr, int side, int bc, double ug)  // velpred.f90:2644-2659
-{
-    if (bc == BC_SLIP_WALL || bc == BC_NO_SLIP_WALL) return ZERO;
-    if (bc == BC_INLET) return ug;
-    if (bc == BC_OUTLET) return side == 0 ? fmin(mr, ZERO) : fmax(ml, ZERO);
-    return v;
-}
-__device__ __forceinline__ void bc_pair(double &l, double &r, int d, int side, int bc, int is_vel, int comp, double sg)  // mkflux.f90:1463-1515
-{
-    if (bc == BC_INLET) { l = sg; r = sg; }
-    else if (bc == BC_SLIP_WALL) {
-        if (is_vel && comp == d) { l = ZERO; r = ZERO; }
-        else if (side == 0) l = r; else r = l;
-    } else if (bc == BC_NO_SLIP_WALL) {
-        if (is_vel) { l = ZERO; r = ZERO; }
-        else if (side == 0) l = r; else r = l;
-    } else if (bc == BC_OUTLET) {
-        if (is_vel && comp == d) {
-            if (side == 0) { l = fmin(r, ZERO); r = fmin(r, ZERO); }
-            else           { l = fmax(l, ZERO); r = fmax(l, ZERO); }
-        } else if (side == 0) l = r; else r = l;
-    }
-}
-__device__ __forceinline__ double bc_edge(double v, double el, double er, int d, int side, int bc, int is_vel, int comp, double sg)  // mkflux.f90:2356-2397
-{
-    const double in = (side == 0) ? er : el;
-    if (bc == BC_INLET) return sg;
-    if (bc == BC_SLIP_WALL) return (is_vel && comp == d) ? ZERO : in;
-    if (bc == BC_NO_SLIP_WALL) return is_vel ? ZERO : in;
-    if (bc == BC_OUTLET) {
-        if (is_vel && comp == d) return (side == 0) ? fmin(er, ZERO) : fmax(el, ZERO);
-        return in;
-    }
-    return v;
-}
-
-#define THREAD_IJK(r)                                                            \
-    const int i = (r).lo[0] + blockIdx.x * blockDim.x + threadIdx.x;             \
-    const int j = (r).lo[1] + blockIdx.y * blockDim.y + threadIdx.y;             \
-    const int k = (r).lo[2] + blockIdx.z;                                        \
-    if (i > (r).hi[0] || j > (r).hi[1]) return;                                  \
-    const int ix[3] = { i, j, k }; (void)ix;
-
-// ------------------------------------------------------------------------------------------
-// velpred
-// ------------------------------------------------------------------------------------------
-struct VpArgs {
-    Geo g; Range r;
-    View u, force;
-    View sl;            // slopes along D, DIM comps
-    View ul, ur, uimh;  // this direction, DIM comps each
-    const double *eps;
-    double dt; int use_minion;
-};
-
-// normal predictor + Riemann/upwind: velpred.f90:2019-2099 (x), 2105-2185 (y), 2283-2367 (z); 2-D :258-322, :330-396
-template <int DIM, int D>
-__global__ void k_vp_normal(VpArgs a)
-{
-    THREAD_IJK(a.r)
-    const double dt2 = HALF * a.dt, h = a.g.h[D];
-    const long su = a.u.st(D);
-    const double *uR = &a.u(i, j, k), *uL = uR - su;
-    const long ss = a.sl.st(D);
-    const double *sR = &a.sl(i, j, k), *sL = sR - ss;
-    const double unL = uL[a.u.cs * D], unR = uR[a.u.cs * D];
-    // operation-order quirks: 3-D x,z: dt2*max(0,u)/h ; 3-D y left: dt2*max(0,u/h) ; 2-D: both inside
-    double cl, cr;
-    if (DIM == 2)             { cl = HALF - dt2 * fmax(ZERO, unL / h); cr = HALF + dt2 * fmin(ZERO, unR / h); }
-    else if (D == 1)          { cl = HALF - dt2 * fmax(ZERO, unL / h); cr = HALF + dt2 * fmin(ZERO, unR) / h; }
-    else                      { cl = HALF - dt2 * fmax(ZERO, unL) / h; cr = HALF + dt2 * fmin(ZERO, unR) / h; }
-    double ul[DIM], ur[DIM];
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-        ul[c] = uL[a.u.cs * c] + cl * sL[a.sl.cs * c];
-        ur[c] = uR[a.u.cs * c] - cr * sR[a.sl.cs * c];
-    }
-    if (a.use_minion) {
-        const long sf = a.force.st(D);
-        const double *fR = &a.force(i, j, k), *fL = fR - sf;
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) { ul[c] = ul[c] + dt2 * fL[a.force.cs * c]; ur[c] = ur[c] + dt2 * fR[a.force.cs * c]; }
-    }
-    if (ix[D] == 0) {
-        double ug[DIM];
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) ug[c] = uL[a.u.cs * c];
-        bc_normal<DIM>(ul, ur, D, 0, a.g.pbc[D][0], ug, false);
-    }
-    if (ix[D] == a.g.n[D]) {
-        double ug[DIM];
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) ug[c] = uR[a.u.cs * c];
-        bc_normal<DIM>(ul, ur, D, 1, a.g.pbc[D][1], ug, DIM == 3 && D == 0 /* velpred.f90:2075 */);
-    }
-    const double eps = a.eps[a.g.box(i, j, k)];
-    const double un = riemann_n(ul[D], ur[D], eps);
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-        a.ul(i, j, k, c) = ul[c];
-        a.ur(i, j, k, c) = ur[c];
-        a.uimh(i, j, k, c) = (c == D) ? un : upwind_t(ul[c], ur[c], un, eps);
-    }
-}
-
-struct VpTransArgs {
-    Geo g; Range r;
-    View u;
-    View ulD, urD;      // comp C of the D-direction L/R states
-    View uimhD_n;       // uimh_D(D)
-    View uimhT_n;       // uimh_T(T)
-    View uimhT_c;       // uimh_T(C)
-    View out;
-    const double *eps; double dt;
-};
-// transverse-corrected tangential state of comp C = 3-D-T on D faces, corrected by T (3-D only):
-// wimhxy :2191, wimhyx :2236, vimhzx :2425, uimhzy :2474, vimhxz :2527, uimhyz :2572
-template <int D, int T>
-__global__ void k_vp_trans(VpTransArgs a)
-{
-    THREAD_IJK(a.r)
-    constexpr int C = 3 - D - T;
-    const double dt6 = a.dt / 6.0, hT = a.g.h[T];
-    const long sD = a.uimhT_n.st(D), sT = a.uimhT_n.st(T);
-    // R cell = (i,j,k), L cell = R - e_D; T-faces of a cell: lo = cell index, hi = cell index + e_T
-    const double *nR = &a.uimhT_n(i, j, k), *cR = &a.uimhT_c(i, j, k);
-    const double *nL = nR - sD, *cL = cR - sD;
-    double l = a.ulD(i, j, k) - (dt6 / hT) * (nL[sT] + nL[0]) * (cL[sT] - cL[0]);
-    double r = a.urD(i, j, k) - (dt6 / hT) * (nR[sT] + nR[0]) * (cR[sT] - cR[0]);
-    if (ix[D] == 0)        bc_trans(l, r, 0, a.g.pbc[D][0], (&a.u(i, j, k, C))[-a.u.st(D)]);
-    if (ix[D] == a.g.n[D]) bc_trans(l, r, 1, a.g.pbc[D][1], a.u(i, j, k, C));
-    const double eps = a.eps[a.g.box(i, j, k)];
-    a.out(i, j, k) = upwind_t(l, r, a.uimhD_n(i, j, k), eps);
-}
-
-struct VpFinalArgs {
-    Geo g; Range r;
-    View u, force;
-    View ulD, urD;          // comp D of the D-direction L/R states
-    View n1, x1;            // uimh_T1(T1), X_{T1,T2}  (2-D: uimh_T(T), uimh_T(D))
-    View n2, x2;            // uimh_T2(T2), X_{T2,T1}
-    View out;               // umac_D (field view)
-    const double *eps; double dt; int use_minion;
-};
-// final MAC velocity: umac :2617-2659, vmac :2665-2707, wmac :2373-2419 ; 2-D :402-444, :454-496
-template <int DIM, int D>
-__global__ void k_vp_final(VpFinalArgs a)
-{
-    THREAD_IJK(a.r)
-    constexpr int T1 = (D == 0) ? 1 : 0;
-    constexpr int T2 = (D == 2) ? 1 : 2;
-    const double dt2 = HALF * a.dt, dt4 = a.dt / 4.0;
-    double ml, mr;
-    {
-        const long sD = a.n1.st(D), s1 = a.n1.st(T1);
-        const double *nR = &a.n1(i, j, k), *xR = &a.x1(i, j, k);
-        const double *nL = nR - sD, *xL = xR - sD;
-        ml = a.ulD(i, j, k) - (dt4 / a.g.h[T1]) * (nL[s1] + nL[0]) * (xL[s1] - xL[0]);
-        mr = a.urD(i, j, k) - (dt4 / a.g.h[T1]) * (nR[s1] + nR[0]) * (xR[s1] - xR[0]);
-    }
-    if (DIM == 3) {
-        const long sD = a.n2.st(D), s2 = a.n2.st(T2);
-        const double *nR = &a.n2(i, j, k), *xR = &a.x2(i, j, k);
-        const double *nL = nR - sD, *xL = xR - sD;
-        ml = ml - (dt4 / a.g.h[T2]) * (nL[s2] + nL[0]) * (xL[s2] - xL[0]);
-        mr = mr - (dt4 / a.g.h[T2]) * (nR[s2] + nR[0]) * (xR[s2] - xR[0]);
-    }
-    if (!a.use_minion) {
-        const double *fR = &a.force(i, j, k, D);
-        ml = ml + dt2 * fR[-a.force.st(D)];
-        mr = mr + dt2 * fR[0];
-    }
-    const double eps = a.eps[a.g.box(i, j, k)];
-    double v = riemann_n(ml, mr, eps);
-    if (ix[D] == 0)        v = bc_mac(v, ml, mr, 0, a.g.pbc[D][0], (&a.u(i, j, k, D))[-a.u.st(D)]);
-    if (ix[D] == a.g.n[D]) v = bc_mac(v, ml, mr, 1, a.g.pbc[D][1], a.u(i, j, k, D));
-    a.out(i, j, k) = v;
-}
-
-// ------------------------------------------------------------------------------------------
-// mkflux
-// ------------------------------------------------------------------------------------------
-struct MfArgs {
-    Geo g; Range r;
-    View s;             // comp already selected
-    View sl;            // slope along D of this comp
-    View macD;          // MAC velocity normal to the face
-    View force, mac_rhs;
-    View l, rr, simh;   // outputs
-    const double *eps;
-    double dt; int use_minion, is_vel, comp, cons, use_rhs;
-};
-// 1-D extrapolation + BC + upwind: mkflux.f90:1443-1524 (x), 1530-1611 (y), 1779-1864 (z)
-template <int D>
-__global__ void k_mf_normal(MfArgs a)
-{
-    THREAD_IJK(a.r)
-    const double dt2 = HALF * a.dt, h = a.g.h[D];
-    const double *sR = &a.s(i, j, k), *sL = sR - a.s.st(D);
-    const double *pR = &a.sl(i, j, k), *pL = pR - a.sl.st(D);
-    const double um = a.macD(i, j, k);
-    double l = sL[0] + (HALF - dt2 * um / h) * pL[0];
-    double r = sR[0] - (HALF + dt2 * um / h) * pR[0];
-    if (a.use_minion) {
-        const double *fR = &a.force(i, j, k);
-        l = l + dt2 * fR[-a.force.st(D)]; r = r + dt2 * fR[0];
-        if (a.cons && a.use_rhs) {
-            const double *dR = &a.mac_rhs(i, j, k);
-            l = l - dt2 * sL[0] * dR[-a.mac_rhs.st(D)]; r = r - dt2 * sR[0] * dR[0];
-        }
-    }
-    if (ix[D] == 0)        bc_pair(l, r, D, 0, a.g.pbc[D][0], a.is_vel, a.comp, sL[0]);
-    if (ix[D] == a.g.n[D]) bc_pair(l, r, D, 1, a.g.pbc[D][1], a.is_vel, a.comp, sR[0]);
-    const double eps = a.eps[a.g.box(i, j, k)];
-    a.l(i, j, k) = l; a.rr(i, j, k) = r;
-    a.simh(i, j, k) = upw(l, r, um, eps);
-}
-
-struct MfTransArgs {
-    Geo g; Range r;
-    View s;                 // comp selected
-    View lD, rD;            // L/R states on D faces
-    View simhT, macT;       // upwinded state and MAC velocity on T faces
-    View macD;
-    View out;
-    const double *eps; double dt; int is_vel, comp, cons;
-};
-// transverse-once states: simhxy :1617, simhyx :1697, simhzx :1978, simhzy :2062, simhxz :2150, simhyz :2230
-template <int D, int T>
-__global__ void k_mf_trans(MfTransArgs a)
-{
-    THREAD_IJK(a.r)
-    const double dt3 = a.dt / 3.0, dt6 = a.dt / 6.0, hT = a.g.h[T];
-    const double *qR = &a.simhT(i, j, k), *qL = qR - a.simhT.st(D);
-    const double *mR = &a.macT(i, j, k), *mL = mR - a.macT.st(D);
-    const long sq = a.simhT.st(T), sm = a.macT.st(T);
-    double l, r;
-    if (a.cons) {
-        l = a.lD(i, j, k) - (dt3 / hT) * (qL[sq] * mL[sm] - qL[0] * mL[0]);
-        r = a.rD(i, j, k) - (dt3 / hT) * (qR[sq] * mR[sm] - qR[0] * mR[0]);
-    } else {
-        l = a.lD(i, j, k) - (dt6 / hT) * (mL[sm] + mL[0]) * (qL[sq] - qL[0]);
-        r = a.rD(i, j, k) - (dt6 / hT) * (mR[sm] + mR[0]) * (qR[sq] - qR[0]);
-    }
-    const double *sR = &a.s(i, j, k);
-    if (ix[D] == 0)        bc_pair(l, r, D, 0, a.g.pbc[D][0], a.is_vel, a.comp, sR[-a.s.st(D)]);
-    if (ix[D] == a.g.n[D]) bc_pair(l, r, D, 1, a.g.pbc[D][1], a.is_vel, a.comp, sR[0]);
-    const double eps = a.eps[a.g.box(i, j, k)];
-    a.out(i, j, k) = upw(l, r, a.macD(i, j, k), eps);
-}
-
-struct MfFinalArgs {
-    Geo g; Range r;
-    View s, force, mac_rhs;
-    View lD, rD;
-    View x1, mac1;      // X_{T1,T2} (2-D: simh_T) and MAC velocity on T1 faces
-    View x2, mac2;
-    View macD;
-    View sedge, flux;   // outputs (comp selected)
-    const double *eps; double dt; int use_minion, is_vel, comp, cons, use_rhs;
-};
-// final edge state + flux: sedgex :2310-2408, sedgey :2414-2512, sedgez :1870-1972 ; 2-D :470-566, :572-666
-template <int DIM, int D>
-__global__ void k_mf_final(MfFinalArgs a)
-{
-    THREAD_IJK(a.r)
-    constexpr int T1 = (D == 0) ? 1 : 0;
-    constexpr int T2 = (D == 2) ? 1 : 2;
-    const double dt2 = HALF * a.dt, dt4 = a.dt / 4.0;
-    const double h1 = a.g.h[T1], h2 = a.g.h[T2];
-    const double *sR = &a.s(i, j, k), *sL = sR - a.s.st(D);
-    const double *x1R = &a.x1(i, j, k), *x1L = x1R - a.x1.st(D);
-    const double *m1R = &a.mac1(i, j, k), *m1L = m1R - a.mac1.st(D);
-    const long sx1 = a.x1.st(T1), sm1 = a.mac1.st(T1);
-    double el = a.lD(i, j, k), er = a.rD(i, j, k);
-    if (DIM == 3) {
-        const double *x2R = &a.x2(i, j, k), *x2L = x2R - a.x2.st(D);
-        const double *m2R = &a.mac2(i, j, k), *m2L = m2R - a.mac2.st(D);
-        const long sx2 = a.x2.st(T2), sm2 = a.mac2.st(T2);
-        if (a.cons) {
-            el = el - (dt2 / h1) * (x1L[sx1] * m1L[sm1] - x1L[0] * m1L[0])
-                    - (dt2 / h2) * (x2L[sx2] * m2L[sm2] - x2L[0] * m2L[0])
-                    + (dt2 / h1) * sL[0] * (m1L[sm1] - m1L[0])
-                    + (dt2 / h2) * sL[0] * (m2L[sm2] - m2L[0]);
-            er = er - (dt2 / h1) * (x1R[sx1] * m1R[sm1] - x1R[0] * m1R[0])
-                    - (dt2 / h2) * (x2R[sx2] * m2R[sm2] - x2R[0] * m2R[0])
-                    + (dt2 / h1) * sR[0] * (m1R[sm1] - m1R[0])
-                    + (dt2 / h2) * sR[0] * (m2R[sm2] - m2R[0]);
-        } else {
-            el = el - (dt4 / h1) * (m1L[sm1] + m1L[0]) * (x1L[sx1] - x1L[0])
-                    - (dt4 / h2) * (m2L[sm2] + m2L[0]) * (x2L[sx2] - x2L[0]);
-            er = er - (dt4 / h1) * (m1R[sm1] + m1R[0]) * (x1R[sx1] - x1R[0])
-                    - (dt4 / h2) * (m2R[sm2] + m2R[0]) * (x2R[sx2] - x2R[0]);
-        }
-    } else {
-        if (a.cons) {
-            el = el - (dt2 / h1) * (x1L[sx1] * m1L[sm1] - x1L[0] * m1L[0]) + (dt2 / h1) * sL[0] * (m1L[sm1] - m1L[0]);
-            er = er - (dt2 / h1) * (x1R[sx1] * m1R[sm1] - x1R[0] * m1R[0]) + (dt2 / h1) * sR[0] * (m1R[sm1] - m1R[0]);
-        } else {
-            el = el - (dt4 / h1) * (m1L[sm1] + m1L[0]) * (x1L[sx1] - x1L[0]);
-            er = er - (dt4 / h1) * (m1R[sm1] + m1R[0]) * (x1R[sx1] - x1R[0]);
-        }
-    }
-    if (!a.use_minion) {
-        const double *fR = &a.force(i, j, k);
-        el = el + dt2 * fR[-a.force.st(D)]; er = er + dt2 * fR[0];
-        if (a.cons && a.use_rhs) {
-            const double *dR = &a.mac_rhs(i, j, k);
-            el = el - dt2 * sL[0] * dR[-a.mac_rhs.st(D)]; er = er - dt2 * sR[0] * dR[0];
-        }
-    }
-    const double um = a.macD(i, j, k);
-    const double eps = a.eps[a.g.box(i, j, k)];
-    double v = upw(el, er, um, eps);
-    if (ix[D] == 0)        v = bc_edge(v, el, er, D, 0, a.g.pbc[D][0], a.is_vel, a.comp, sL[0]);
-    if (ix[D] == a.g.n[D]) v = bc_edge(v, el, er, D, 1, a.g.pbc[D][1], a.is_vel, a.comp, sR[0]);
-    a.sedge(i, j, k) = v;
-    if (a.cons) a.flux(i, j, k) = v * um;
-}
 
 // ------------------------------------------------------------------------------------------
 // per-box eps: 1e-8 * max|.| over the box's valid cells (velpred) / valid faces (mkflux)
@@ -554,172 +86,67 @@ void compute_eps(vdn_ctx *c, bool from_umac)
     VDN_CUDA(cudaGetLastError());
 }
 
+
 // S-layout scratch slots
 enum { SL0 = 0 /* slopes: 9 */, UL0 = 9, UR0 = 18, UI0 = 27, NSCR_NEEDED = 36 };
+// mkflux scratch slots: per component
+enum { MSL0 = 0 /* 3 slopes */, ML0 = 3, MR0 = 6, MI0 = 9, MX0 = 12 /* 9 slots, X[d][t] at d*3+t */, MF_NSCR = 21 };
+
+// launcher handed to the stage orchestration in vdn_godunov_kernels.cuh: CUDA launch on the context's stream,
+// profiling brackets from the context's CUDA-event profiler
+struct CudaLauncher {
+    vdn_ctx *c;
+    LaunchScope scope(const char *name, double alg_bytes, int nlaunch) { return LaunchScope(c, name, alg_bytes, nlaunch); }
+    template <class A> void operator()(void (*k)(A), const Range &r, const A &a) { k<<<grid3(r, BLK), BLK, 0, c->stream>>>(a); }
+};
 
 template <int DIM>
 void velpred_impl(vdn_ctx *c, double dt)
 {
-    const Geo &g = c->geo;
-    const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
-    const int zl = DIM == 3 ? -1 : 0, zh = DIM == 3 ? n2 : 0;       // grown z range
-    const double cells = (double)c->ncells();
     compute_eps(c, false);
-    // slopes on cells -1..n (velpred.f90:1848-1852)
-    {
-        LaunchScope ls(c, "vp_slopes", cells * 8.0 * (DIM + DIM * DIM));
-        SlopeArgs a; a.g = g; a.s = c->f[VDN_UOLD].view(); a.ncomp = DIM; a.order = c->prm.slope_order;
-        for (int d = 0; d < DIM; ++d) a.out[d] = c->S(SL0 + 3 * d);
-        for (int cc = 0; cc < DIM; ++cc) for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) a.bc[cc][d][s] = c->adv_bc[cc][d][s];
-        a.r = mk_range(-1, n0, -1, n1, zl, zh);
-        k_slopes<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+    VpArgs a; a.g = c->geo; a.u = c->f[VDN_UOLD].view(); a.force = c->f[VDN_VEL_FORCE].view();
+    a.eps = c->d_eps; a.dt = dt; a.use_minion = c->prm.use_minion; a.order = c->prm.slope_order;
+    for (int cc = 0; cc < 3; ++cc) for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) a.sbc[cc][d][s] = c->adv_bc[cc][d][s];
+    for (int d = 0; d < 3; ++d) {
+        const int q = d < DIM ? d : 0;
+        a.sl[d] = c->S(SL0 + 3 * q); a.ul[d] = c->S(UL0 + 3 * q); a.ur[d] = c->S(UR0 + 3 * q); a.uimh[d] = c->S(UI0 + 3 * q);
+        a.out[d] = c->f[VDN_UMAC_X + q].view();
+        for (int t = 0; t < 3; ++t) a.X[d][t] = c->S(SL0 + d * 3 + t);     // transverse states reuse the slope slots
     }
-    // normal predictors
-    {
-        LaunchScope ls(c, "vp_normal", cells * 8.0 * DIM * (2 * DIM + 3 * DIM), DIM);
-        VpArgs a; a.g = g; a.u = c->f[VDN_UOLD].view(); a.force = c->f[VDN_VEL_FORCE].view();
-        a.eps = c->d_eps; a.dt = dt; a.use_minion = c->prm.use_minion;
-        for (int d = 0; d < DIM; ++d) {
-            a.sl = c->S(SL0 + 3 * d); a.ul = c->S(UL0 + 3 * d); a.ur = c->S(UR0 + 3 * d); a.uimh = c->S(UI0 + 3 * d);
-            if (d == 0)      { a.r = mk_range(0, n0, -1, n1, zl, zh); k_vp_normal<DIM, 0><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a); }
-            else if (d == 1) { a.r = mk_range(-1, n0, 0, n1, zl, zh); k_vp_normal<DIM, 1><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a); }
-            else             { a.r = mk_range(-1, n0, -1, n1, 0, n2); k_vp_normal<DIM, 2><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a); }
-        }
-    }
-    // transverse states (3-D): stored over the slope slots that are no longer needed
-    // X[d][t] at slot SL0 + (d*3+t)
-    auto X = [&](int d, int t) { return c->S(SL0 + d * 3 + t); };
-    if (DIM == 3) {
-        LaunchScope ls(c, "vp_trans", cells * 8.0 * 6 * 6, 6);
-        VpTransArgs a; a.g = g; a.u = c->f[VDN_UOLD].view(); a.eps = c->d_eps; a.dt = dt;
-        auto go = [&](int d, int t, Range r) {
-            const int cc = 3 - d - t;
-            a.r = r;
-            a.ulD = c->S(UL0 + 3 * d).comp(cc); a.urD = c->S(UR0 + 3 * d).comp(cc);
-            a.uimhD_n = c->S(UI0 + 3 * d).comp(d);
-            a.uimhT_n = c->S(UI0 + 3 * t).comp(t); a.uimhT_c = c->S(UI0 + 3 * t).comp(cc);
-            a.out = X(d, t);
-            dim3 gr = grid3(r, BLK);
-            if (d == 0 && t == 1) k_vp_trans<0, 1><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 0 && t == 2) k_vp_trans<0, 2><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 1 && t == 0) k_vp_trans<1, 0><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 1 && t == 2) k_vp_trans<1, 2><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 2 && t == 0) k_vp_trans<2, 0><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 2 && t == 1) k_vp_trans<2, 1><<<gr, BLK, 0, c->stream>>>(a);
-        };
-        // ranges from the reference pseudo-code velpred.f90:1986-2004
-        go(0, 1, mk_range(0, n0, 0, n1 - 1, -1, n2));          // wimhxy (is:ie+1, js:je, ks-1:ke+1)
-        go(1, 0, mk_range(0, n0 - 1, 0, n1, -1, n2));          // wimhyx (is:ie, js:je+1, ks-1:ke+1)
-        go(2, 0, mk_range(0, n0 - 1, -1, n1, 0, n2));          // vimhzx (is:ie, js-1:je+1, ks:ke+1)
-        go(2, 1, mk_range(-1, n0, 0, n1 - 1, 0, n2));          // uimhzy (is-1:ie+1, js:je, ks:ke+1)
-        go(0, 2, mk_range(0, n0, -1, n1, 0, n2 - 1));          // vimhxz (is:ie+1, js-1:je+1, ks:ke)
-        go(1, 2, mk_range(-1, n0, 0, n1, 0, n2 - 1));          // uimhyz (is-1:ie+1, js:je+1, ks:ke)
-    }
-    // final MAC velocities on the valid faces
-    {
-        LaunchScope ls(c, "vp_final", cells * 8.0 * DIM * (DIM == 3 ? 8 : 6), DIM);
-        VpFinalArgs a; a.g = g; a.u = c->f[VDN_UOLD].view(); a.force = c->f[VDN_VEL_FORCE].view();
-        a.eps = c->d_eps; a.dt = dt; a.use_minion = c->prm.use_minion;
-        for (int d = 0; d < DIM; ++d) {
-            const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
-            a.ulD = c->S(UL0 + 3 * d).comp(d); a.urD = c->S(UR0 + 3 * d).comp(d);
-            a.n1 = c->S(UI0 + 3 * t1).comp(t1);
-            if (DIM == 3) { a.x1 = X(t1, t2); a.n2 = c->S(UI0 + 3 * t2).comp(t2); a.x2 = X(t2, t1); }
-            else          { a.x1 = c->S(UI0 + 3 * t1).comp(d); a.n2 = a.n1; a.x2 = a.x1; }
-            a.out = c->f[VDN_UMAC_X + d].view();
-            a.r = mk_range(0, n0 - 1 + (d == 0), 0, n1 - 1 + (d == 1), 0, n2 - 1 + (d == 2));
-            dim3 gr = grid3(a.r, BLK);
-            if (d == 0) k_vp_final<DIM, 0><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 1) k_vp_final<DIM, 1><<<gr, BLK, 0, c->stream>>>(a);
-            if (d == 2) k_vp_final<DIM, 2><<<gr, BLK, 0, c->stream>>>(a);
-        }
-    }
+    CudaLauncher L{c};
+    velpred_stages<DIM>(L, a, c->godunov_fuse != 0);
     VDN_CUDA(cudaGetLastError());
 }
-
-// mkflux scratch slots: per component
-enum { MSL0 = 0 /* 3 slopes */, ML0 = 3, MR0 = 6, MI0 = 9, MX0 = 12 /* 9 slots, X[d][t] at d*3+t */, MF_NSCR = 21 };
 
 template <int DIM>
 void mkflux_impl(vdn_ctx *c, int is_vel, double dt)
 {
-    const Geo &g = c->geo;
-    const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
-    const int zl = DIM == 3 ? -1 : 0, zh = DIM == 3 ? n2 : 0;
-    const double cells = (double)c->ncells();
     const int ncomp = is_vel ? DIM : c->prm.nscal;
     const int bccomp = is_vel ? 0 : DIM;
     const DField &sfld = c->f[is_vel ? VDN_UOLD : VDN_SOLD];
     const DField &ffld = c->f[is_vel ? VDN_VEL_FORCE : VDN_SCAL_FORCE];
     compute_eps(c, true);
-    View mac[3]; for (int d = 0; d < DIM; ++d) mac[d] = c->f[VDN_UMAC_X + d].view();
     // scalar_advance passes divu == 0 as mac_rhs (scalar_advance.f90:102) => the s*div(u) term is skipped (use_rhs = 0,
     // x - dt2*s*0 == x exactly); velocity_advance passes mac_rhs (:76) but no velocity comp is conservative.
-    View mrhs = c->f[VDN_MAC_RHS].view();
-
+    MfArgs a; a.g = c->geo; a.mac_rhs = c->f[VDN_MAC_RHS].view(); a.eps = c->d_eps; a.dt = dt;
+    a.use_minion = c->prm.use_minion; a.is_vel = is_vel; a.use_rhs = is_vel; a.order = c->prm.slope_order;
+    for (int d = 0; d < 3; ++d) {
+        const int q = d < DIM ? d : 0;
+        a.mac[d] = c->f[VDN_UMAC_X + q].view();
+        a.sl[d] = c->S(MSL0 + q); a.l[d] = c->S(ML0 + q); a.rr[d] = c->S(MR0 + q); a.simh[d] = c->S(MI0 + q);
+        for (int t = 0; t < 3; ++t) a.X[d][t] = c->S(MX0 + d * 3 + t);
+    }
+    CudaLauncher L{c};
     for (int comp = 0; comp < ncomp; ++comp) {
-        const int cons = (!is_vel && comp == 0) ? 1 : 0;     // scalar_advance.f90:54-57, velocity_advance.f90:51
-        View s = sfld.view().comp(comp), force = ffld.view().comp(comp);
-        {
-            LaunchScope ls(c, "mf_slopes", cells * 8.0 * (1 + DIM));
-            SlopeArgs a; a.g = g; a.s = s; a.ncomp = 1; a.order = c->prm.slope_order;
-            for (int d = 0; d < DIM; ++d) a.out[d] = c->S(MSL0 + d);
-            for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) a.bc[0][d][sd] = c->adv_bc[bccomp + comp][d][sd];
-            a.r = mk_range(-1, n0, -1, n1, zl, zh);
-            k_slopes<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        a.cons = (!is_vel && comp == 0) ? 1 : 0;     // scalar_advance.f90:54-57, velocity_advance.f90:51
+        a.s = sfld.view().comp(comp); a.force = ffld.view().comp(comp); a.comp = comp;
+        for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) a.sbc[d][sd] = c->adv_bc[bccomp + comp][d][sd];
+        for (int d = 0; d < 3; ++d) {
+            const int q = d < DIM ? d : 0;
+            a.sedge[d] = c->f[(is_vel ? VDN_UEDGE_X : VDN_SEDGE_X) + q].view().comp(comp);
+            a.flux[d] = is_vel ? a.sedge[d] : c->f[VDN_SFLUX_X + q].view().comp(comp);
         }
-        {
-            LaunchScope ls(c, "mf_normal", cells * 8.0 * DIM * 6, DIM);
-            MfArgs a; a.g = g; a.s = s; a.force = force; a.mac_rhs = mrhs; a.eps = c->d_eps; a.dt = dt;
-            a.use_minion = c->prm.use_minion; a.is_vel = is_vel; a.comp = comp; a.cons = cons; a.use_rhs = is_vel;
-            for (int d = 0; d < DIM; ++d) {
-                a.sl = c->S(MSL0 + d); a.macD = mac[d]; a.l = c->S(ML0 + d); a.rr = c->S(MR0 + d); a.simh = c->S(MI0 + d);
-                if (d == 0)      { a.r = mk_range(0, n0, -1, n1, zl, zh); k_mf_normal<0><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a); }
-                else if (d == 1) { a.r = mk_range(-1, n0, 0, n1, zl, zh); k_mf_normal<1><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a); }
-                else             { a.r = mk_range(-1, n0, -1, n1, 0, n2); k_mf_normal<2><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a); }
-            }
-        }
-        auto X = [&](int d, int t) { return c->S(MX0 + d * 3 + t); };
-        if (DIM == 3) {
-            LaunchScope ls(c, "mf_trans", cells * 8.0 * 6 * 7, 6);
-            MfTransArgs a; a.g = g; a.s = s; a.eps = c->d_eps; a.dt = dt; a.is_vel = is_vel; a.comp = comp; a.cons = cons;
-            auto go = [&](int d, int t, Range r) {
-                a.r = r; a.lD = c->S(ML0 + d); a.rD = c->S(MR0 + d); a.simhT = c->S(MI0 + t); a.macT = mac[t]; a.macD = mac[d];
-                a.out = X(d, t);
-                dim3 gr = grid3(r, BLK);
-                if (d == 0 && t == 1) k_mf_trans<0, 1><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 0 && t == 2) k_mf_trans<0, 2><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 1 && t == 0) k_mf_trans<1, 0><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 1 && t == 2) k_mf_trans<1, 2><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 2 && t == 0) k_mf_trans<2, 0><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 2 && t == 1) k_mf_trans<2, 1><<<gr, BLK, 0, c->stream>>>(a);
-            };
-            go(0, 1, mk_range(0, n0, 0, n1 - 1, -1, n2));      // simhxy
-            go(1, 0, mk_range(0, n0 - 1, 0, n1, -1, n2));      // simhyx
-            go(2, 0, mk_range(0, n0 - 1, -1, n1, 0, n2));      // simhzx
-            go(2, 1, mk_range(-1, n0, 0, n1 - 1, 0, n2));      // simhzy
-            go(0, 2, mk_range(0, n0, -1, n1, 0, n2 - 1));      // simhxz
-            go(1, 2, mk_range(-1, n0, 0, n1, 0, n2 - 1));      // simhyz
-        }
-        {
-            LaunchScope ls(c, "mf_final", cells * 8.0 * DIM * (DIM == 3 ? 11 : 8), DIM);
-            MfFinalArgs a; a.g = g; a.s = s; a.force = force; a.mac_rhs = mrhs; a.eps = c->d_eps; a.dt = dt;
-            a.use_minion = c->prm.use_minion; a.is_vel = is_vel; a.comp = comp; a.cons = cons; a.use_rhs = is_vel;
-            for (int d = 0; d < DIM; ++d) {
-                const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;
-                a.lD = c->S(ML0 + d); a.rD = c->S(MR0 + d); a.macD = mac[d];
-                a.mac1 = mac[t1];
-                if (DIM == 3) { a.x1 = X(t1, t2); a.x2 = X(t2, t1); a.mac2 = mac[t2]; }
-                else          { a.x1 = c->S(MI0 + t1); a.x2 = a.x1; a.mac2 = a.mac1; }
-                a.sedge = c->f[(is_vel ? VDN_UEDGE_X : VDN_SEDGE_X) + d].view().comp(comp);
-                a.flux = is_vel ? a.sedge : c->f[VDN_SFLUX_X + d].view().comp(comp);
-                a.r = mk_range(0, n0 - 1 + (d == 0), 0, n1 - 1 + (d == 1), 0, n2 - 1 + (d == 2));
-                dim3 gr = grid3(a.r, BLK);
-                if (d == 0) k_mf_final<DIM, 0><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 1) k_mf_final<DIM, 1><<<gr, BLK, 0, c->stream>>>(a);
-                if (d == 2) k_mf_final<DIM, 2><<<gr, BLK, 0, c->stream>>>(a);
-            }
-        }
+        mkflux_stages<DIM>(L, a, c->godunov_fuse != 0);
     }
     VDN_CUDA(cudaGetLastError());
 }
