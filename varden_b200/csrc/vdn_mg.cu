@@ -25,7 +25,6 @@ struct Lev {
     int mode[3][2];
     int par0;               // parity of the global index of local cell (0,0,0)
     double *phi, *rhs, *res, *b[3];
-    double *dgi;            // 1/diagonal (fused wavefront levels only, else nullptr)
 };
 
 struct MG {
@@ -47,7 +46,7 @@ struct MG {
     int *d_coords = nullptr;                    // [nranks][3] process-grid coordinates
     // fused wavefront smoother (k_wave): levels 0..nfused-1 of a rank-local 3-D hierarchy
     int nfused = 0;                             // number of leading levels that run the fused kernels
-    int fuse_nsw = 2;                           // GSRB sweeps fused per launch (1 or 2)
+    int fuse_nsw = 1;                           // GSRB sweeps fused per launch
     int tile_force = -1, zchunk_force = 0;      // tuning overrides (VDN_MG_TILE, VDN_MG_ZCHUNK)
     int sm_count = 148;
 };
@@ -160,20 +159,6 @@ __global__ void k_coarsen_beta(Lev F, Lev C, int d)
         s = 0.25 * (F.b[d][cf] + F.b[d][cf + ta] + F.b[d][cf + tb] + F.b[d][cf + ta + tb]);
     }
     C.b[d][C.off + i + C.s[1] * j + C.s[2] * k] = s;
-}
-
-// 1/diagonal of the operator (the same face rules as cell_op)
-template <int DIM>
-__global__ void k_dginv(Lev L)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = blockIdx.z;
-    if (i >= L.n[0] || j >= L.n[1]) return;
-    const long c = L.off + i + L.s[1] * j + L.s[2] * k;
-    const int ix[3] = { i, j, k };
-    double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
-    L.dgi[c] = dg != 0.0 ? 1.0 / dg : 0.0;
 }
 
 // ---- bottom solver: BiCGStab in ONE CTA (the coarsest level is a handful of cells); dot products use
@@ -327,7 +312,6 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         }
         for (int d = c->dim; d < 3; ++d) L.b[d] = nullptr;
         L.res = dalloc(L.ntot);
-        L.dgi = nullptr;
         for (int d = 0; d < c->dim; ++d) { n[d] /= 2; h[d] *= 2.0; glo[d] /= 2; }
     }
     for (int q = 0; q < 6; ++q) { VDN_CUDA(cudaMalloc(&m->bot[q], sizeof(double) * m->L[nlev - 1].ntot)); VDN_CUDA(cudaMemsetAsync(m->bot[q], 0, sizeof(double) * m->L[nlev - 1].ntot, c->stream)); }
@@ -349,20 +333,15 @@ void mg_build(vdn_ctx *c)
         c->mg = m;
         // fused wavefront smoother on the leading (large) levels of a rank-local 3-D hierarchy
         auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
-        const int fuse = envi("VDN_MG_FUSE", 2), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
+        const int fuse = envi("VDN_MG_FUSE", 1), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
         m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
         cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
         if (fuse > 0 && c->dim == 3 && !m->distributed && c->prm.mg_nu1 >= 1 && c->prm.mg_nu2 >= 1) {
-            m->fuse_nsw = fuse >= 2 ? 2 : 1;
+            m->fuse_nsw = 1;
             while (m->nfused < m->nlev - 1) {
                 const Lev &L = m->L[m->nfused];
                 if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
                 ++m->nfused;
-            }
-            for (int l = 0; l < m->nfused; ++l) {
-                double *p; VDN_CUDA(cudaMalloc(&p, sizeof(double) * m->L[l].ntot));
-                VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * m->L[l].ntot, c->stream));
-                m->owned.push_back(p); m->L[l].dgi = p;
             }
         }
         return;
@@ -459,43 +438,39 @@ void residual(vdn_ctx *c, MG *m, int l, double *nrm)
 
 // ---- fused wavefront launcher ----
 struct WaveVariant { const void *fn = nullptr; size_t smem = 0; int occ = 0; int H = 0, W = 0, HH = 0, TX = 0, TY = 0, NT = 0; };
-template <int NSW, int PRE, int POST, int TX, int TY, int NT>
+template <int NSW, int PRE, int POST, int TX, int TY, int NT, int PF>
 WaveVariant wave_variant()
 {
-    constexpr int S = 2 * NSW, E = POST ? 1 : 0, H = S + E, NP = S + 4;
+    using C = WaveCfg<NSW, PRE, POST, TX, TY, NT, PF>;
     WaveVariant v;
-    v.fn = (const void *)k_wave<NSW, PRE, POST, TX, TY, NT>;
-    v.smem = sizeof(double) * NP * (TX + 2 * H) * (TY + 2 * H);
-    v.H = H; v.W = TX + 2 * H; v.HH = TY + 2 * H; v.TX = TX; v.TY = TY; v.NT = NT;
+    v.fn = (const void *)k_wave<NSW, PRE, POST, TX, TY, NT, PF>;
+    v.smem = C::SMEM;
+    v.H = C::H; v.W = C::W; v.HH = C::HH; v.TX = TX; v.TY = TY; v.NT = NT;
     VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, NT, v.smem));
     VDN_REQUIRE(v.occ >= 1, "k_wave variant does not fit on an SM");
     return v;
 }
-// [tile cfg][nsw-1][pre][post: 0 -> 0, 1 -> 2 (restrict), 2 -> 3 (norm)]
+// [tile cfg][pre][post: 0 -> 0, 1 -> 2 (restrict), 2 -> 3 (norm)]; one GSRB sweep per launch (the operator rings of two
+// sweeps do not fit in 227 KB of shared memory at a useful tile size)
 WaveVariant &wave_get(int cfg, int nsw, int pre, int post)
 {
-    static WaveVariant tab[2][2][2][3];
+    static WaveVariant tab[2][2][3];
+    VDN_REQUIRE(nsw == 1, "k_wave is instantiated for one sweep per launch");
     const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
-    WaveVariant &v = tab[cfg][nsw - 1][pre][pi];
+    WaveVariant &v = tab[cfg][pre][pi];
     if (v.fn) return v;
-#define WV(C, TX, TY, NT) \
+#define WV(C, TX, TY, NT, PF) \
     if (cfg == C) { \
-        if (nsw == 1 && pre == 0 && post == 0) v = wave_variant<1, 0, 0, TX, TY, NT>(); \
-        if (nsw == 1 && pre == 0 && post == 2) v = wave_variant<1, 0, 2, TX, TY, NT>(); \
-        if (nsw == 1 && pre == 0 && post == 3) v = wave_variant<1, 0, 3, TX, TY, NT>(); \
-        if (nsw == 1 && pre == 1 && post == 0) v = wave_variant<1, 1, 0, TX, TY, NT>(); \
-        if (nsw == 1 && pre == 1 && post == 2) v = wave_variant<1, 1, 2, TX, TY, NT>(); \
-        if (nsw == 1 && pre == 1 && post == 3) v = wave_variant<1, 1, 3, TX, TY, NT>(); \
-        if (nsw == 2 && pre == 0 && post == 0) v = wave_variant<2, 0, 0, TX, TY, NT>(); \
-        if (nsw == 2 && pre == 0 && post == 2) v = wave_variant<2, 0, 2, TX, TY, NT>(); \
-        if (nsw == 2 && pre == 0 && post == 3) v = wave_variant<2, 0, 3, TX, TY, NT>(); \
-        if (nsw == 2 && pre == 1 && post == 0) v = wave_variant<2, 1, 0, TX, TY, NT>(); \
-        if (nsw == 2 && pre == 1 && post == 2) v = wave_variant<2, 1, 2, TX, TY, NT>(); \
-        if (nsw == 2 && pre == 1 && post == 3) v = wave_variant<2, 1, 3, TX, TY, NT>(); \
+        if (pre == 0 && post == 0) v = wave_variant<1, 0, 0, TX, TY, NT, PF>(); \
+        if (pre == 0 && post == 2) v = wave_variant<1, 0, 2, TX, TY, NT, PF>(); \
+        if (pre == 0 && post == 3) v = wave_variant<1, 0, 3, TX, TY, NT, PF>(); \
+        if (pre == 1 && post == 0) v = wave_variant<1, 1, 0, TX, TY, NT, PF>(); \
+        if (pre == 1 && post == 2) v = wave_variant<1, 1, 2, TX, TY, NT, PF>(); \
+        if (pre == 1 && post == 3) v = wave_variant<1, 1, 3, TX, TY, NT, PF>(); \
     }
-    WV(0, 64, 16, 512)
-    WV(1, 32, 16, 256)
+    WV(0, 32, 16, 512, 2)
+    WV(1, 32, 8, 256, 2)
 #undef WV
     VDN_REQUIRE(v.fn != nullptr, "no such k_wave variant");
     return v;
@@ -526,7 +501,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
     WaveArgs a;
     for (int d = 0; d < 3; ++d) { a.n[d] = L.n[d]; a.h2[d] = L.h2inv[d]; a.mode[d][0] = L.mode[d][0]; a.mode[d][1] = L.mode[d][1]; }
     a.s1 = L.s[1]; a.s2 = L.s[2]; a.off = L.off; a.par0 = L.par0;
-    a.rhs = L.rhs; a.dgi = L.dgi; a.b0 = L.b[0]; a.b1 = L.b[1]; a.b2 = L.b[2];
+    a.rhs = L.rhs; a.b0 = L.b[0]; a.b1 = L.b[1]; a.b2 = L.b[2];
     a.in = L.phi; a.out = L.res;
     a.cphi = nullptr; a.crhs = nullptr; a.czero = nullptr; a.cs1 = a.cs2 = a.coff = 0;
     if (pre || post == 2) {
@@ -670,11 +645,6 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
         Lev &A = m->L[m->agg_level];
         for (int d = 0; d < m->dim; ++d) agg_gather(c, m, A.b[d], m->tail->L[0].b[d], d);
         coarsen_coefficients(c, m->tail);
-    }
-    for (int l = 0; l < m->nfused; ++l) {
-        Lev &L = m->L[l];
-        LaunchScope ls(c, "mg_dginv", (double)L.n[0] * L.n[1] * L.n[2] * 32.0);
-        k_dginv<3><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L);
     }
     VDN_CUDA(cudaGetLastError());
     const double bnorm = st_absmax_valid(c, VDN_RH);
