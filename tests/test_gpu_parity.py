@@ -171,8 +171,11 @@ def test_mg_fused_wavefront(case, fuse, tile, monkeypatch):
         upload_state(ctx, geom, P, st)
         ctx.mkvelforce("SOLD", 1.0)
         ctx.velpred(dt)
-        ncyc, res = ctx.macproject(rel_eps=1e-11)
-        assert res <= 1e-11
+        try:
+            ncyc, res = ctx.macproject(rel_eps=1e-10)
+        except Exception as e:
+            raise AssertionError("macproject failed in mode %s: %s" % (mode, e))
+        assert res <= 1e-10, (mode, res)
         um = [download_like(ctx, geom, "UMAC_" + "XYZ"[d], ref["umac"][d], 1, 1) for d in range(3)]
         out[mode] = (ncyc, res, um, ctx.launch_count())
         ctx.close()

@@ -229,6 +229,7 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
     DField &f = c->f[field];
     VDN_REQUIRE(f.base != nullptr, "field not allocated for this dimension");
     VDN_REQUIRE(ng == f.ng && ncomp == f.nc, "host (ng, ncomp) does not match the field's fixed layout");
+    if (upload && field >= VDN_UMAC_X && field <= VDN_UMAC_Z) ++c->umac_epoch;
     VDN_CUDA(cudaSetDevice(c->device));
     int hext[3], clo[3], chi[3], hlo[3];
     for (int d = 0; d < 3; ++d) {

@@ -37,6 +37,7 @@ struct vdn_ctx {
     std::vector<cudaEvent_t> ev_pool;
     MG *mg = nullptr;
     Comm *comm = nullptr;
+    long long umac_epoch = 0, eps_epoch = -1;          // UMAC_* write counter / counter value the per-box umac eps was computed at
     int godunov_fuse = 1;                               // 3-D: all directions of a Godunov stage per launch (VDN_GODUNOV_FUSE)
 
     View S(int q) const { View v; v.sy = s_sy; v.sz = s_sz; v.cs = s_n; v.p = scratch + (long)q * s_n + s_off; return v; }

@@ -63,6 +63,9 @@ int box_slot(const vdn_ctx *c, int ib)
 
 void compute_eps(vdn_ctx *c, bool from_umac)
 {
+    // the scalar and the velocity mkflux of one step see the same projected umac: reduce it once
+    if (from_umac && c->eps_epoch == c->umac_epoch) return;
+    c->eps_epoch = from_umac ? c->umac_epoch : -1;
     LaunchScope ls(c, from_umac ? "eps_umac" : "eps_u", (double)c->ncells() * 8.0 * c->dim, c->nboxes + 2);
     VDN_CUDA(cudaMemsetAsync(c->d_eps, 0, sizeof(double) * c->nboxes, c->stream));
     for (int ib = 0; ib < c->nboxes; ++ib) {
@@ -157,6 +160,7 @@ void st_velpred(vdn_ctx *c, double dt)
 {
     VDN_REQUIRE(c->nscr >= NSCR_NEEDED, "scratch arena too small for velpred");
     if (c->dim == 3) velpred_impl<3>(c, dt); else velpred_impl<2>(c, dt);
+    ++c->umac_epoch;
     for (int d = 0; d < c->dim; ++d) st_fill_boundary(c, VDN_UMAC_X + d);      // velpred.f90:107-112
 }
 

@@ -134,6 +134,20 @@ __global__ void k_wrap(WrapArgs a)     // range covers the transverse extents an
         else          { p[-(long)g * st] = p[(long)(a.n - g) * st]; p[(long)(a.n + g) * st] = p[(long)g * st]; }
     }
 }
+// the same wrap along x: ghost columns are strided in memory, so threads run along j (one row each) and ghost layer g
+__global__ void k_wrap_x(WrapArgs a)    // blockDim (64, 4): x -> j, y -> g-1 (ng <= 4); grid (rows/64, planes)
+{
+    const int j = a.r.lo[1] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = 1 + threadIdx.y;
+    const int k = a.r.lo[2] + blockIdx.y;
+    if (j > a.r.hi[1] || g > a.ng) return;
+    double *p0 = &a.v(0, j, k);
+    for (int c = 0; c < a.ncomp; ++c) {
+        double *p = p0 + a.v.cs * c;
+        if (!a.nodal) { p[-g] = p[a.n - g]; p[a.n - 1 + g] = p[g - 1]; }
+        else          { p[-g] = p[a.n - g]; p[a.n + g] = p[g]; }
+    }
+}
 // physical BC ghost fill along d (both sides) for one comp; ranges as multifab_physbc.f90
 struct PbcArgs { Range r; int d, n, ng; int bc[2]; int full_lo[3], full_hi[3]; double val[2]; View v; };
 __global__ void k_physbc(PbcArgs a)    // range: transverse extents (full ghosted); index along d unused (lo=hi=0)
@@ -197,6 +211,7 @@ Range valid_range(const vdn_ctx *c, int fdir)
 
 void st_setval(vdn_ctx *c, int field, double val)
 {
+    if (field >= VDN_UMAC_X && field <= VDN_UMAC_Z) ++c->umac_epoch;
     DField &f = c->f[field];
     LaunchScope ls(c, "setval", (double)f.bytes);
     SetArgs a; a.p = f.base; a.n = (long)(f.bytes / 8); a.v = val;
@@ -332,6 +347,7 @@ void st_mkumac(vdn_ctx *c)
         }
         VDN_CUDA(cudaGetLastError());
     }
+    ++c->umac_epoch;
     for (int d = 0; d < c->dim; ++d) st_fill_boundary(c, VDN_UMAC_X + d);       // macproject.f90:491-493
 }
 
@@ -354,7 +370,8 @@ void st_fill_boundary(vdn_ctx *c, int field)
             lo[d] = 1; hi[d] = f.ng;
             a.r = mk_range(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
             LaunchScope ls(c, "fill_boundary", 0.0);
-            k_wrap<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+            if (d == 0 && f.ng <= 4) k_wrap_x<<<dim3(cdiv(hi[1] - lo[1] + 1, 64), hi[2] - lo[2] + 1), BLK, 0, c->stream>>>(a);
+            else k_wrap<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
             VDN_CUDA(cudaGetLastError());
         } else if (c->comm) {
             comm_exchange(c, field, d);
