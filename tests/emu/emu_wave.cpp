@@ -6,14 +6,14 @@ double sm[1 << 17];
 
 extern "C" int emu_wave(int nsw, int pre, int post, int cfg, const int *n, const int *mode, int par0, const double *h2,
                         const double *rhs, const double *b0, const double *b1, const double *b2,
-                        const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk)
+                        const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk, int pad)
 {
     WaveArgs a;
     for (int d = 0; d < 3; ++d) { a.n[d] = n[d]; a.h2[d] = h2[d]; a.mode[d][0] = mode[2 * d]; a.mode[d][1] = mode[2 * d + 1]; }
-    a.s1 = n[0] + 2; a.s2 = (long)(n[0] + 2) * (n[1] + 2); a.off = 1 + a.s1 + a.s2; a.par0 = par0;
+    a.s1 = n[0] + 2 * pad; a.s2 = (long)(n[0] + 2 * pad) * (n[1] + 2 * pad); a.off = pad * (1 + a.s1 + a.s2); a.par0 = par0;
     a.rhs = rhs; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.in = in; a.out = out;
     a.cphi = cphi; a.crhs = crhs; a.czero = czero;
-    a.cs1 = n[0] / 2 + 2; a.cs2 = (long)(n[0] / 2 + 2) * (n[1] / 2 + 2); a.coff = 1 + a.cs1 + a.cs2;
+    a.cs1 = n[0] / 2 + 2 * pad; a.cs2 = (long)(n[0] / 2 + 2 * pad) * (n[1] / 2 + 2 * pad); a.coff = pad * (1 + a.cs1 + a.cs2);
     a.nrm = nrm; a.zchunk = zchunk;
 #define GO(NSW, PRE, POST) if (nsw == NSW && pre == PRE && post == POST) { \
         if (cfg == 0) { emu_launch(k_wave<NSW, PRE, POST, 32, 16, 512, 2>, dim3((n[0] + 31) / 32, (n[1] + 15) / 16, (n[2] + zchunk - 1) / zchunk), 512, a); return 0; } \

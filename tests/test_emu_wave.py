@@ -12,7 +12,8 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
-M_NEU, M_DIR, M_WRAP = 1, 2, 3
+M_GHOST, M_NEU, M_DIR, M_WRAP = 0, 1, 2, 3
+PAD = 3          # MG_PAD in vdn_ctx.h
 
 
 @pytest.fixture(scope="module")
@@ -27,15 +28,15 @@ def emu():
 
 
 def pad(n):
-    return (n[2] + 2, n[1] + 2, n[0] + 2)
+    return (n[2] + 2 * PAD, n[1] + 2 * PAD, n[0] + 2 * PAD)
 
 
 def fill_wrap(p, n, mode):
     for d, ax in ((0, 2), (1, 1), (2, 0)):
         if mode[d][0] == M_WRAP:
             sl_lo = [slice(None)] * 3; sl_hi = [slice(None)] * 3; src_lo = [slice(None)] * 3; src_hi = [slice(None)] * 3
-            sl_lo[ax] = 0; src_lo[ax] = n[d]
-            sl_hi[ax] = n[d] + 1; src_hi[ax] = 1
+            sl_lo[ax] = PAD - 1; src_lo[ax] = PAD - 1 + n[d]
+            sl_hi[ax] = PAD + n[d]; src_hi[ax] = PAD
             p[tuple(sl_lo)] = p[tuple(src_lo)]
             p[tuple(sl_hi)] = p[tuple(src_hi)]
 
@@ -44,12 +45,12 @@ def apply_A(phi, b, h2, mode, n):
     """A*phi and diag on valid cells; b[d][idx] = coefficient on the LOW d-face of cell idx (padded arrays, z,y,x order)."""
     p = phi.copy()
     fill_wrap(p, n, mode)
-    V = (slice(1, n[2] + 1), slice(1, n[1] + 1), slice(1, n[0] + 1))
+    V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
     p0 = p[V]
     ax = np.zeros_like(p0); dg = np.zeros_like(p0)
     for d, axis in ((0, 2), (1, 1), (2, 0)):
         def sh(a, o):
-            s = list(V); s[axis] = slice(1 + o, n[d] + 1 + o); return a[tuple(s)]
+            s = list(V); s[axis] = slice(PAD + o, n[d] + PAD + o); return a[tuple(s)]
         blo, bhi = sh(b[d], 0), sh(b[d], 1)
         pm, pp = sh(p, -1), sh(p, 1)
         idx = np.arange(n[d]).reshape([-1 if a == axis else 1 for a in range(3)])
@@ -66,7 +67,7 @@ def apply_A(phi, b, h2, mode, n):
 
 
 def gsrb(phi, rhs, b, h2, mode, n, par0, sweeps):
-    V = (slice(1, n[2] + 1), slice(1, n[1] + 1), slice(1, n[0] + 1))
+    V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
     k, j, i = np.meshgrid(np.arange(n[2]), np.arange(n[1]), np.arange(n[0]), indexing="ij")
     par = (i + j + k + par0) & 1
     phi = phi.copy()
@@ -100,19 +101,19 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, nsw, pre, post
     for d, axis in ((0, 2), (1, 1), (2, 0)):
         if mode[d][0] == M_WRAP:
             s_hi = [slice(None)] * 3; s_lo = [slice(None)] * 3
-            s_hi[axis] = n[d] + 1; s_lo[axis] = 1
+            s_hi[axis] = n[d] + PAD; s_lo[axis] = PAD
             b[d][tuple(s_hi)] = b[d][tuple(s_lo)]
     rhs = np.ascontiguousarray(rng.standard_normal(shp))
     phi = np.ascontiguousarray(rng.standard_normal(shp))
     cphi = np.ascontiguousarray(rng.standard_normal(pad(cn)))
-    V = (slice(1, n[2] + 1), slice(1, n[1] + 1), slice(1, n[0] + 1))
-    CV = (slice(1, cn[2] + 1), slice(1, cn[1] + 1), slice(1, cn[0] + 1))
+    V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
+    CV = (slice(PAD, cn[2] + PAD), slice(PAD, cn[1] + PAD), slice(PAD, cn[0] + PAD))
     out = np.full(shp, np.nan)
     crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan)
     nrm = np.zeros(1)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = emu.emu_wave(nsw, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), par0, P(h2),
-                      P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk)
+                      P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk, PAD)
     assert rc == 0
     # reference
     start = phi.copy()
@@ -132,3 +133,60 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, nsw, pre, post
             cr = res.reshape(cn[2], 2, cn[1], 2, cn[0], 2).mean(axis=(1, 3, 5))
             assert np.abs(crhs[CV] - cr).max() <= 1e-10 * rs
             assert np.all(czero[CV] == 0.0)
+
+
+@pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
+@pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
+def test_wave_rank_ghost_layers(emu, pre, post, split):
+    """a level split across ranks: the kernel relaxes the neighbour ranks' cells held in its MG_PAD ghost layers (M_GHOST)
+    redundantly; the block of every 'rank' must equal the same block of the whole-domain sweep"""
+    rng = np.random.default_rng(77 + pre + 5 * post + len(split))
+    N = (32, 32, 16)                      # whole periodic domain, halved along the directions in `split`
+    n = tuple(N[d] // 2 if d in split else N[d] for d in range(3))
+    cN = tuple(x // 2 for x in N); cn = tuple(x // 2 for x in n)
+    gmode = ((M_WRAP, M_WRAP),) * 3
+    h2 = np.array([1.0e4, 0.8e4, 1.3e4])
+    shpN = pad(N)
+    b = [np.ascontiguousarray(0.5 + rng.random(shpN)) for _ in range(3)]
+    rhs = np.ascontiguousarray(rng.standard_normal(shpN)); phi = np.ascontiguousarray(rng.standard_normal(shpN))
+    cphi = np.ascontiguousarray(rng.standard_normal(pad(cN)))
+
+    def periodic_fill(a, nn):             # all PAD ghost layers of a whole-domain array
+        for ax, d in ((2, 0), (1, 1), (0, 2)):
+            idx = (np.arange(-PAD, nn[d] + PAD) % nn[d]) + PAD
+            a[...] = np.take(a, idx, axis=ax)
+    for a in b + [rhs, phi]:
+        periodic_fill(a, N)
+    periodic_fill(cphi, cN)
+    VN = (slice(PAD, N[2] + PAD), slice(PAD, N[1] + PAD), slice(PAD, N[0] + PAD))
+    CVN = (slice(PAD, cN[2] + PAD), slice(PAD, cN[1] + PAD), slice(PAD, cN[0] + PAD))
+    start = phi.copy()
+    if pre:
+        start[VN] += np.repeat(np.repeat(np.repeat(cphi[CVN], 2, axis=0), 2, axis=1), 2, axis=2)
+    ref = gsrb(start, rhs, b, h2, gmode, N, 0, 1)
+    ax, _ = apply_A(ref, b, h2, gmode, N)
+    res = rhs[VN] - ax
+    Pp = lambda a: a.ctypes.data_as(C.c_void_p)
+    mode = tuple((M_GHOST, M_GHOST) if d in split else (M_WRAP, M_WRAP) for d in range(3))
+    nrm_all = 0.0
+    for corner in np.ndindex(*[2 if d in split else 1 for d in range(3)]):
+        o = [corner[d] * n[d] for d in range(3)]          # block origin (x, y, z)
+        def cut(a, nn, oo):                                # the block with its ghost layers, as the rank stores it
+            return np.ascontiguousarray(a[oo[2]:oo[2] + nn[2] + 2 * PAD, oo[1]:oo[1] + nn[1] + 2 * PAD, oo[0]:oo[0] + nn[0] + 2 * PAD])
+        lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o); lphi = cut(phi, n, o)
+        lc = cut(cphi, cn, [x // 2 for x in o])
+        out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
+        rc = emu.emu_wave(1, pre, post, 0, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
+                          Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD)
+        assert rc == 0
+        V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
+        want = ref[o[2] + PAD:o[2] + PAD + n[2], o[1] + PAD:o[1] + PAD + n[1], o[0] + PAD:o[0] + PAD + n[0]]
+        assert np.abs(out[V] - want).max() <= 1e-12 * np.abs(want).max(), corner
+        if post == 2:
+            cr = res.reshape(cN[2], 2, cN[1], 2, cN[0], 2).mean(axis=(1, 3, 5))
+            co = [x // 2 for x in o]
+            CV = (slice(PAD, cn[2] + PAD), slice(PAD, cn[1] + PAD), slice(PAD, cn[0] + PAD))
+            assert np.abs(crhs[CV] - cr[co[2]:co[2] + cn[2], co[1]:co[1] + cn[1], co[0]:co[0] + cn[0]]).max() <= 1e-10 * np.abs(res).max()
+        nrm_all = max(nrm_all, nrm[0])
+    if post == 3:
+        assert abs(nrm_all - np.abs(res).max()) <= 1e-10 * np.abs(res).max()

@@ -78,7 +78,7 @@ static void build_bc_tables(vdn_ctx *c)
 
 void ctx_rebuild_bc(vdn_ctx *c) { build_bc_tables(c); }
 
-// sng = storage ghost width (>= ng).  RH and BETA_* are stored in the multigrid's padded layout (sng = 1, extent n+2
+// sng = storage ghost width (>= ng).  PHI, RH and BETA_* are stored in the multigrid's padded layout (sng = MG_PAD, extent n+2*MG_PAD
 // in every direction, which also holds the n+1 faces) so that MG level 0 can alias them without copies.
 static void alloc_field(vdn_ctx *c, int id, int ng, int nc, int fdir, int sng = -1)
 {
@@ -173,8 +173,8 @@ static void ctx_build(vdn_ctx *c, const vdn_params *prm, int dim, int nboxes, co
     for (int d = 0; d < dm; ++d) alloc_field(c, VDN_UMAC_X + d, 1, 1, d);
     alloc_field(c, VDN_MAC_RHS, 1, 1, -1); alloc_field(c, VDN_RHOHALF, 1, 1, -1);
     alloc_field(c, VDN_VEL_FORCE, 1, dm, -1); alloc_field(c, VDN_SCAL_FORCE, 1, ns, -1);
-    alloc_field(c, VDN_RH, 0, 1, -1, 1); alloc_field(c, VDN_PHI, 1, 1, -1);
-    for (int d = 0; d < dm; ++d) alloc_field(c, VDN_BETA_X + d, 0, 1, d, 1);
+    alloc_field(c, VDN_RH, 0, 1, -1, MG_PAD); alloc_field(c, VDN_PHI, 1, 1, -1, MG_PAD);
+    for (int d = 0; d < dm; ++d) alloc_field(c, VDN_BETA_X + d, 0, 1, d, MG_PAD);
     // edge states: the scalar and velocity phases never overlap, so SEDGE aliases the first nscal comps of UEDGE
     const int ne = std::max(dm, ns);
     for (int d = 0; d < dm; ++d) {

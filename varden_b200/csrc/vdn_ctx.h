@@ -7,6 +7,10 @@
 struct ProfEntry { std::string name; long long launches = 0; double ms = 0.0; double bytes = 0.0;
                    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; };
 
+// ghost width of the multigrid level arrays (and of the PHI / RH / BETA_* fields that level 0 aliases): the fused wavefront
+// smoother relaxes 3 layers of neighbour-rank cells redundantly instead of exchanging halos before every colour
+constexpr int MG_PAD = 3;
+
 struct MG;      // vdn_mg.cu
 struct Comm;    // vdn_comm.cu
 

@@ -6,7 +6,7 @@
 // stencil_order = 2 Dirichlet ghost, stop at |r|_inf <= eps*|rh|_inf.  F_MG's source is not available, so results
 // are matched to the solver tolerance (parity bar: 10x eps), not bit-wise.
 //
-// Layout: every level uses one padded layout (n+2 per direction, index (i+1) + sy*(j+1) + sz*(k+1)) shared by
+// Layout: every level uses one padded layout (n+2*MG_PAD per direction, cell (i,j,k) at off + i + sy*j + sz*k) shared by
 // phi, rhs, res and the three face-coefficient arrays (b_d[idx] = beta on the LOW d-face of cell idx), so a
 // stencil needs one index.  Level 0 aliases the context's PHI / RH / BETA_* fields (no copies).
 // Physical BCs are synthesised in the stencil (Neumann: no flux; Dirichlet: 3*phi0 - phi1/3 one-sided), periodic
@@ -296,9 +296,9 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
     for (int l = 0; l < nlev; ++l) {
         Lev &L = m->L[l];
         for (int d = 0; d < 3; ++d) { L.n[d] = n[d]; L.h2inv[d] = 1.0 / (h[d] * h[d]); }
-        L.s[0] = 1; L.s[1] = n[0] + 2; L.s[2] = (long)(n[0] + 2) * (n[1] + 2);
-        L.ntot = L.s[2] * (c->dim == 3 ? n[2] + 2 : 1);
-        L.off = 1 + L.s[1] + (c->dim == 3 ? L.s[2] : 0);
+        L.s[0] = 1; L.s[1] = n[0] + 2 * MG_PAD; L.s[2] = (long)(n[0] + 2 * MG_PAD) * (n[1] + 2 * MG_PAD);
+        L.ntot = L.s[2] * (c->dim == 3 ? n[2] + 2 * MG_PAD : 1);
+        L.off = MG_PAD * (1 + L.s[1] + (c->dim == 3 ? L.s[2] : 0));
         L.par0 = (glo[0] + glo[1] + (c->dim == 3 ? glo[2] : 0)) & 1;
         for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) { L.mode[d][s] = d < c->dim ? mode[d][s] : M_NEU; if (L.mode[d][s] == M_GHOST) m->distributed = true; }
         auto dalloc = [&](long cnt) { double *p; VDN_CUDA(cudaMalloc(&p, sizeof(double) * cnt)); VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cnt, c->stream)); m->owned.push_back(p); return p; };
@@ -319,6 +319,25 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
     return m;
 }
 
+
+// fused wavefront smoother on the leading (large) levels of a 3-D hierarchy.  Rank-local levels wrap by index; levels that
+// are split across ranks relax MG_PAD ghost layers redundantly after ONE deep halo exchange per launch.
+void mg_pick_fused(vdn_ctx *c, MG *m)
+{
+    auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
+    const int fuse = envi("VDN_MG_FUSE", 1), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
+    m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
+    cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
+    if (fuse <= 0 || c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
+    m->fuse_nsw = 1;
+    const int last = m->tail ? m->agg_level : m->nlev - 1;      // the agglomerated / bottom level is never fused
+    while (m->nfused < last) {
+        const Lev &L = m->L[m->nfused];
+        if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
+        ++m->nfused;
+    }
+}
+
 void mg_build(vdn_ctx *c)
 {
     const Geo &g = c->geo;
@@ -331,19 +350,7 @@ void mg_build(vdn_ctx *c)
     if (nr == 1) {
         MG *m = mg_make(c, g.n, g.h, c->rlo, mode, true, -1);
         c->mg = m;
-        // fused wavefront smoother on the leading (large) levels of a rank-local 3-D hierarchy
-        auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
-        const int fuse = envi("VDN_MG_FUSE", 1), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
-        m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
-        cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
-        if (fuse > 0 && c->dim == 3 && !m->distributed && c->prm.mg_nu1 >= 1 && c->prm.mg_nu2 >= 1) {
-            m->fuse_nsw = 1;
-            while (m->nfused < m->nlev - 1) {
-                const Lev &L = m->L[m->nfused];
-                if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
-                ++m->nfused;
-            }
-        }
+        mg_pick_fused(c, m);
         return;
     }
     // multi-rank: distributed levels down to a local size of <= 32 cells per direction, then agglomerate
@@ -382,6 +389,7 @@ void mg_build(vdn_ctx *c)
     for (int r = 0; r < nr; ++r) comm_coord_of(c, r, &coords[3 * r]);
     VDN_CUDA(cudaMalloc(&m->d_coords, sizeof(int) * 3 * nr));
     VDN_CUDA(cudaMemcpy(m->d_coords, coords.data(), sizeof(int) * 3 * nr, cudaMemcpyHostToDevice));
+    mg_pick_fused(c, m);
 }
 
 // gather one array of the local agglomeration level (cells, or faces along fdir) into the tail's level 0 on every rank
@@ -410,6 +418,18 @@ void mg_halo(vdn_ctx *c, MG *m, Lev &L, double *x)
     for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
     LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
     comm_halo(c, v, L.n, m->dim, 1, 1, -1, dmask, false);
+}
+
+// ghost layers of depth ng of one level array, all split directions at once (x, then y over the x-ghosted range, then z: the
+// tiles of the fused smoother also read edge and corner ghosts)
+void mg_halo_deep(vdn_ctx *c, MG *m, Lev &L, double *x, int ng)
+{
+    if (!m->distributed) return;
+    View v; v.p = x + L.off; v.sy = L.s[1]; v.sz = L.s[2]; v.cs = L.ntot;
+    int dmask = 0;
+    for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
+    LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
+    comm_halo(c, v, L.n, m->dim, ng, 1, -1, dmask, true);
 }
 
 void smooth(vdn_ctx *c, MG *m, int l, int sweeps)
@@ -509,6 +529,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
         a.cphi = C.phi; a.crhs = C.rhs; a.czero = C.phi; a.cs1 = C.s[1]; a.cs2 = C.s[2]; a.coff = C.off;
     }
     a.nrm = m->d_norm; a.zchunk = best_ch;
+    mg_halo_deep(c, m, L, L.phi, v.H);          // neighbour-rank cells the tiles relax redundantly
     if (post == 3) VDN_CUDA(cudaMemsetAsync(m->d_norm, 0, 8, c->stream));
     const double cells = (double)L.n[0] * L.n[1] * L.n[2];
     // SURVEY 8(a) a8 per stage: colour half-sweep 40, residual 48, restriction 9, prolongation 17 B/cell
@@ -561,9 +582,11 @@ void vcycle(vdn_ctx *c, MG *m, int l)
                 VDN_CUDA(cudaGraphLaunch(m->coarse_graph, c->stream));
             } else vcycle(c, m, l + 1);
         };
+        if (l > 0) mg_halo_deep(c, m, L, L.rhs, MG_PAD);        // restricted by the level above: valid cells only
         int rem = c->prm.mg_nu1;
         while (rem > 0) { const int nsw = std::min(m->fuse_nsw, rem); rem -= nsw; wave_launch(c, m, l, nsw, 0, rem == 0 ? 2 : 0); }
         coarse();
+        mg_halo_deep(c, m, C, C.phi, 2);                        // the prolongation under 3 fine ghost layers reads 2 coarse ones
         rem = c->prm.mg_nu2;
         bool first = true;
         while (rem > 0) { const int nsw = std::min(m->fuse_nsw, rem); rem -= nsw; wave_launch(c, m, l, nsw, first ? 1 : 0, (rem == 0 && l == 0) ? 3 : 0); first = false; }
@@ -646,6 +669,11 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
         for (int d = 0; d < m->dim; ++d) agg_gather(c, m, A.b[d], m->tail->L[0].b[d], d);
         coarsen_coefficients(c, m->tail);
     }
+    if (m->distributed)
+        for (int l = 0; l < m->nfused; ++l) {
+            for (int d = 0; d < m->dim; ++d) mg_halo_deep(c, m, m->L[l], m->L[l].b[d], MG_PAD);
+            if (l == 0) mg_halo_deep(c, m, m->L[0], m->L[0].rhs, MG_PAD);
+        }
     VDN_CUDA(cudaGetLastError());
     const double bnorm = st_absmax_valid(c, VDN_RH);
     auto res_norm = [&]() {

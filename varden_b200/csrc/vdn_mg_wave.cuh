@@ -45,21 +45,23 @@ __device__ __forceinline__ void wave_commit() { asm volatile("cp.async.commit_gr
 template <int N> __device__ __forceinline__ void wave_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 #endif
 
-// index of a tile cell in the level arrays: cells that take part in the relaxation ...
+// index of a tile cell in the level arrays, or WAVE_NONE.  Cells that take part in the relaxation: the level's own cells,
+// periodic images (M_WRAP, wrap by index) and neighbour-rank cells held in the level's ghost layers (M_GHOST) ...
+constexpr int WAVE_NONE = -(1 << 28);
 template <int H>
-__device__ __forceinline__ int wave_wrap(int g, int n, bool wrap)
+__device__ __forceinline__ int wave_idx(int g, int n, int mlo, int mhi)
 {
-    if (g < 0) return (wrap && g >= -H) ? g + n : -1;
-    if (g >= n) return (wrap && g < n + H) ? g - n : -1;
+    if (g < 0) { if (g < -H) return WAVE_NONE; return mlo == M_WRAP ? g + n : (mlo == M_GHOST ? g : WAVE_NONE); }
+    if (g >= n) { if (g >= n + H) return WAVE_NONE; return mhi == M_WRAP ? g - n : (mhi == M_GHOST ? g : WAVE_NONE); }
     return g;
 }
-// ... and cells whose data is LOADED: additionally index n of a non-periodic direction, which holds the coefficient of the
+// ... and cells whose data is LOADED: additionally index n next to a physical boundary, which holds the coefficient of the
 // high boundary face (the padded level layout stores face n at cell index n)
 template <int H>
-__device__ __forceinline__ int wave_wrap_ld(int g, int n, bool wrap)
+__device__ __forceinline__ int wave_idx_ld(int g, int n, int mlo, int mhi)
 {
-    if (!wrap) return (g >= 0 && g <= n) ? g : -1;
-    return wave_wrap<H>(g, n, true);
+    if (g == n && mhi != M_WRAP && mhi != M_GHOST) return n;
+    return wave_idx<H>(g, n, mlo, mhi);
 }
 
 // A*phi contribution and diagonal of one direction (same face formulas as cell_op in vdn_mg.cu)
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(NT) k_wave(const WaveArgs a)
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int z0 = blockIdx.z * a.zchunk, z1 = min(z0 + a.zchunk, a.n[2]);
     const int gx0 = x0 - H, gy0 = y0 - H;
-    const bool wrx = a.mode[0][0] == M_WRAP, wry = a.mode[1][0] == M_WRAP, wrz = a.mode[2][0] == M_WRAP;
+    const int mx0 = a.mode[0][0], mx1 = a.mode[0][1], my0 = a.mode[1][0], my1 = a.mode[1][1], mz0 = a.mode[2][0], mz1 = a.mode[2][1];
     const int n0 = a.n[0], n1 = a.n[1], n2 = a.n[2];
 
     // per-thread load slots of a plane: global offset of the (x,y) part, or -1
@@ -107,13 +109,15 @@ __global__ void __launch_bounds__(NT) k_wave(const WaveArgs a)
 #pragma unroll
     for (int m = 0; m < NL; ++m) {
         const int q = tid + m * NT;
-        lofs[m] = -1; cofs[m] = -1;
+        lofs[m] = WAVE_NONE; cofs[m] = WAVE_NONE;
         if (q < PLANE) {
             const int ly = q / W, lx = q - ly * W;
-            const int wx = wave_wrap_ld<H>(gx0 + lx, n0, wrx), wy = wave_wrap_ld<H>(gy0 + ly, n1, wry);
-            if (wx >= 0 && wy >= 0) {
+            const int wx = wave_idx_ld<H>(gx0 + lx, n0, mx0, mx1), wy = wave_idx_ld<H>(gy0 + ly, n1, my0, my1);
+            if (wx != WAVE_NONE && wy != WAVE_NONE) {
                 lofs[m] = (int)(wx + a.s1 * wy);
-                if (PRE && wx < n0 && wy < n1) cofs[m] = (int)((wx >> 1) + a.cs1 * (wy >> 1));
+                // coarse cell under a fine cell (ghost cells: floor division, the coarse level carries ghost layers too)
+                if (PRE && wave_idx<H>(gx0 + lx, n0, mx0, mx1) != WAVE_NONE && wave_idx<H>(gy0 + ly, n1, my0, my1) != WAVE_NONE)
+                    cofs[m] = (int)((wx >> 1) + a.cs1 * (wy >> 1));
             }
         }
     }
@@ -121,12 +125,12 @@ __global__ void __launch_bounds__(NT) k_wave(const WaveArgs a)
     auto cslot = [&](int p) { return ((p + 16 * NPC) % NPC) * PLANE; };
     // request plane p (phi + operator data) with cp.async; always commits one group
     auto request = [&](int p) {
-        const int wz = (p >= z0 - H && p <= z1 - 1 + H) ? wave_wrap_ld<H>(p, n2, wrz) : -1;
-        if (wz >= 0) {
+        const int wz = (p >= z0 - H && p <= z1 - 1 + H) ? wave_idx_ld<H>(p, n2, mz0, mz1) : WAVE_NONE;
+        if (wz != WAVE_NONE) {
             const int ps = pslot(p), cs = cslot(p);
 #pragma unroll
             for (int m = 0; m < NL; ++m)
-                if (lofs[m] >= 0) {
+                if (lofs[m] != WAVE_NONE) {
                     const int q = tid + m * NT;
                     const long c = a.off + lofs[m] + a.s2 * wz;
                     wave_cp8(sP + ps + q, a.in + c);
@@ -165,12 +169,12 @@ __global__ void __launch_bounds__(NT) k_wave(const WaveArgs a)
         // ---- plane t has landed (at most PF-1 younger requests may still be in flight) ----
         wave_wait<PF - 1>();
         if (PRE) {
-            const int wz = (t >= z0 - H && t <= z1 - 1 + H) ? wave_wrap<H>(t, n2, wrz) : -1;
-            if (wz >= 0) {
+            const int wz = (t >= z0 - H && t <= z1 - 1 + H) ? wave_idx<H>(t, n2, mz0, mz1) : WAVE_NONE;
+            if (wz != WAVE_NONE) {
                 const int ps = pslot(t);
 #pragma unroll
                 for (int m = 0; m < NL; ++m)
-                    if (cofs[m] >= 0) sP[ps + tid + m * NT] += __ldg(a.cphi + a.coff + cofs[m] + a.cs2 * (wz >> 1));
+                    if (cofs[m] != WAVE_NONE) sP[ps + tid + m * NT] += __ldg(a.cphi + a.coff + cofs[m] + a.cs2 * (wz >> 1));
             }
         }
         __syncthreads();
@@ -180,8 +184,8 @@ __global__ void __launch_bounds__(NT) k_wave(const WaveArgs a)
         for (int s = 0; s < S; ++s) {
             const int RS = E + S - 1 - s;                      // region = core grown by RS
             const int p = t - 1 - s;
-            const int wz = (p >= z0 - RS && p <= z1 - 1 + RS) ? wave_wrap<H>(p, n2, wrz) : -1;
-            if (wz >= 0) {
+            const int wz = (p >= z0 - RS && p <= z1 - 1 + RS) ? wave_idx<H>(p, n2, mz0, mz1) : WAVE_NONE;
+            if (wz != WAVE_NONE) {
                 const int Ws = TX + 2 * RS, Hs = TY + 2 * RS, hw = Ws / 2, ls = H - RS;
                 const int color = s & 1;
                 double *P0 = sP + pslot(p);
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(NT) k_wave(const WaveArgs a)
                     const int ly = ls + yy, gy = gy0 + ly;
                     const int lx = ls + 2 * xh + ((color ^ (gx0 + ls + gy + p + a.par0)) & 1);
                     const int gx = gx0 + lx;
-                    if (wave_wrap<H>(gx, n0, wrx) < 0 || wave_wrap<H>(gy, n1, wry) < 0) continue;
+                    if (wave_idx<H>(gx, n0, mx0, mx1) == WAVE_NONE || wave_idx<H>(gy, n1, my0, my1) == WAVE_NONE) continue;
                     double ax, dg, p0, rhs;
                     apply(p, lx, ly, gx, gy, ax, dg, p0, rhs);
                     if (dg != 0.0) P0[ly * W + lx] = p0 + (rhs - ax) / dg;
