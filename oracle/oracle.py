@@ -162,14 +162,14 @@ def rt_state(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, seeded_velocity=
     return geom, params, st, dt
 
 
-def random_state(n, dim=3, max_grid_size=256, phys_bc=None, seed=0, params=None, umag=1.0):
+def random_state(n, dim=3, max_grid_size=256, phys_bc=None, seed=0, params=None, umag=1.0, prob_hi=None):
     """Randomised but smooth-ish state exercising all selects; any phys_bc combination."""
     rng = np.random.default_rng(seed)
     if np.isscalar(n):
         n = [n] * dim
     if phys_bc is None:
         phys_bc = [[SLIP_WALL, SLIP_WALL]] * dim
-    geom = Geom(dim, n, phys_bc, max_grid_size=max_grid_size)
+    geom = Geom(dim, n, phys_bc, max_grid_size=max_grid_size) if prob_hi is None else Geom(dim, n, phys_bc, prob_hi=prob_hi, max_grid_size=max_grid_size)
     if params is None:
         bcval = np.zeros((5, 3, 2))
         bcval[0:3] = rng.uniform(-0.5, 0.5, size=(3, 3, 2)) * umag     # inflow velocities
