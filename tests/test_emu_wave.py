@@ -13,14 +13,15 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu")
 M_GHOST, M_NEU, M_DIR, M_WRAP = 0, 1, 2, 3
-PAD = 3          # MG_PAD in vdn_ctx.h
+PAD = 4          # MG_PAD in vdn_ctx.h
 
 
 @pytest.fixture(scope="module")
 def emu():
     so = os.path.join(EMU, "libemu_wave.so")
     src = [os.path.join(EMU, "emu_wave.cpp"), os.path.join(EMU, "cuda_emu.h"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_wave.cuh")]
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_wave.cuh"),
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
                                src[0], "-o", so])
@@ -89,9 +90,13 @@ CASES = [
 ]
 
 
+KERNELS = [("wave", 1, 0, 0), ("wave", 1, 1, 0), ("wave", 1, 0, 2), ("wave", 1, 1, 2), ("wave", 1, 0, 3), ("wave", 1, 1, 3)] + \
+          [("sweep", nsw, pre, post) for nsw in (1, 2) for pre in (0, 1) for post in (0, 2, 3)]
+
+
 @pytest.mark.parametrize("n,cfg,zchunk,mode,par0", CASES)
-@pytest.mark.parametrize("nsw,pre,post", [(1, 0, 0), (1, 1, 0), (1, 0, 2), (1, 1, 2), (1, 0, 3), (1, 1, 3)])
-def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, nsw, pre, post):
+@pytest.mark.parametrize("kern,nsw,pre,post", KERNELS)
+def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre, post):
     rng = np.random.default_rng(1234 + n[0] + 7 * nsw + pre + 3 * post)
     shp = pad(n)
     cn = tuple(x // 2 for x in n)
@@ -112,8 +117,9 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, nsw, pre, post
     crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan)
     nrm = np.zeros(1)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = emu.emu_wave(nsw, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), par0, P(h2),
-                      P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk, PAD)
+    fn = emu.emu_wave if kern == "wave" else emu.emu_sweep
+    rc = fn(nsw, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), par0, P(h2),
+            P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk, PAD)
     assert rc == 0
     # reference
     start = phi.copy()
@@ -135,9 +141,10 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, nsw, pre, post
             assert np.all(czero[CV] == 0.0)
 
 
+@pytest.mark.parametrize("kern", ["wave", "sweep"])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
 @pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
-def test_wave_rank_ghost_layers(emu, pre, post, split):
+def test_wave_rank_ghost_layers(emu, pre, post, split, kern):
     """a level split across ranks: the kernel relaxes the neighbour ranks' cells held in its MG_PAD ghost layers (M_GHOST)
     redundantly; the block of every 'rank' must equal the same block of the whole-domain sweep"""
     rng = np.random.default_rng(77 + pre + 5 * post + len(split))
@@ -176,8 +183,9 @@ def test_wave_rank_ghost_layers(emu, pre, post, split):
         lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o); lphi = cut(phi, n, o)
         lc = cut(cphi, cn, [x // 2 for x in o])
         out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
-        rc = emu.emu_wave(1, pre, post, 0, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
-                          Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD)
+        fn = emu.emu_wave if kern == "wave" else emu.emu_sweep
+        rc = fn(1, pre, post, 0, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
+                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD)
         assert rc == 0
         V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
         want = ref[o[2] + PAD:o[2] + PAD + n[2], o[1] + PAD:o[1] + PAD + n[1], o[0] + PAD:o[0] + PAD + n[0]]

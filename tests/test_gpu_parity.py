@@ -153,10 +153,11 @@ def test_mg_high_density_ratio():
 
 
 @pytest.mark.parametrize("case", ["rt64", "mixed"])
-@pytest.mark.parametrize("fuse,tile", [(1, -1), (1, 0), (1, 1)])
-def test_mg_fused_wavefront(case, fuse, tile, monkeypatch):
-    """the fused wavefront smoother (k_wave: GSRB sweeps + residual + restriction / prolongation in one launch) against the
-    plain per-colour kernels and the oracle: same V-cycle, so phi and the projected velocity agree to the solver tolerance"""
+@pytest.mark.parametrize("fuse,tile,nsw", [(1, -1, 1), (1, 0, 1), (1, 1, 1), (2, -1, 1), (2, 0, 1), (2, 1, 1), (2, 2, 1), (2, -1, 2), (2, 0, 2), (2, 1, 2), (2, 2, 2)])
+def test_mg_fused_wavefront(case, fuse, tile, nsw, monkeypatch):
+    """the fused wavefront smoothers (fuse 1: k_wave, fuse 2: k_sweep -- GSRB sweeps + residual + restriction / prolongation in
+    one launch) against the plain per-colour kernels and the oracle: same V-cycle, so phi and the projected velocity agree to
+    the solver tolerance"""
     if case == "rt64":
         geom, P, st, dt = O.rt_state(64, dim=3, max_grid_size=64)
     else:
@@ -169,6 +170,7 @@ def test_mg_fused_wavefront(case, fuse, tile, monkeypatch):
         monkeypatch.setenv("VDN_MG_FUSE", "0" if mode == "plain" else str(fuse))
         monkeypatch.setenv("VDN_MG_FUSE_MIN", "16")
         monkeypatch.setenv("VDN_MG_TILE", str(tile))
+        monkeypatch.setenv("VDN_MG_NSW", str(nsw))
         ctx = make_ctx(geom, P)
         upload_state(ctx, geom, P, st)
         ctx.mkvelforce("SOLD", 1.0)
@@ -190,4 +192,4 @@ def test_mg_fused_wavefront(case, fuse, tile, monkeypatch):
     # same algorithm => same cycle count (+-1 for round-off at the stopping test); far fewer launches
     assert abs(out["fused"][0] - out["plain"][0]) <= 1, (out["fused"][0], out["plain"][0])
     assert out["fused"][3] < out["plain"][3]
-    print(case, fuse, tile, "cycles fused/plain", out["fused"][0], out["plain"][0], "launches", out["fused"][3], out["plain"][3])
+    print(case, fuse, tile, nsw, "cycles fused/plain", out["fused"][0], out["plain"][0], "launches", out["fused"][3], out["plain"][3])

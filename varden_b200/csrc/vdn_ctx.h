@@ -8,8 +8,9 @@ struct ProfEntry { std::string name; long long launches = 0; double ms = 0.0; do
                    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending; };
 
 // ghost width of the multigrid level arrays (and of the PHI / RH / BETA_* fields that level 0 aliases): the fused wavefront
-// smoother relaxes 3 layers of neighbour-rank cells redundantly instead of exchanging halos before every colour
-constexpr int MG_PAD = 3;
+// smoother relaxes up to 3 layers of neighbour-rank cells redundantly instead of exchanging halos before every colour; 4 keeps
+// every row of an even-sized level 32-byte aligned (16-byte pair loads, whole sectors)
+constexpr int MG_PAD = 4;
 
 struct MG;      // vdn_mg.cu
 struct Comm;    // vdn_comm.cu

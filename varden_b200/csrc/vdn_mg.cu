@@ -14,6 +14,7 @@
 #include "vdn_ctx.h"
 #include "vdn_comm.h"
 #include "vdn_mg_wave.cuh"
+#include "vdn_mg_sweep.cuh"
 #include <algorithm>
 
 
@@ -47,6 +48,7 @@ struct MG {
     // fused wavefront smoother (k_wave): levels 0..nfused-1 of a rank-local 3-D hierarchy
     int nfused = 0;                             // number of leading levels that run the fused kernels
     int fuse_nsw = 1;                           // GSRB sweeps fused per launch
+    int fuse_kind = 2;                          // 1: k_wave (operator rings in shared memory), 2: k_sweep (2x2 column blocks)
     int tile_force = -1, zchunk_force = 0;      // tuning overrides (VDN_MG_TILE, VDN_MG_ZCHUNK)
     int sm_count = 148;
 };
@@ -325,11 +327,13 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
 void mg_pick_fused(vdn_ctx *c, MG *m)
 {
     auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
-    const int fuse = envi("VDN_MG_FUSE", 1), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
+    const int fuse = envi("VDN_MG_FUSE", 2), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
     m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
     cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
     if (fuse <= 0 || c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
-    m->fuse_nsw = 1;
+    m->fuse_kind = fuse >= 2 ? 2 : 1;
+    m->fuse_nsw = m->fuse_kind == 2 ? std::max(1, std::min(2, envi("VDN_MG_NSW", 1))) : 1;
+    if (m->distributed) m->fuse_nsw = 1;                        // two sweeps need 5 ghost layers, the level arrays carry MG_PAD
     const int last = m->tail ? m->agg_level : m->nlev - 1;      // the agglomerated / bottom level is never fused
     while (m->nfused < last) {
         const Lev &L = m->L[m->nfused];
@@ -496,15 +500,55 @@ WaveVariant &wave_get(int cfg, int nsw, int pre, int post)
     return v;
 }
 
+// k_sweep variants: [tile cfg][nsw-1][pre][post index]
+template <int NSW, int PRE, int POST, int TX, int TY, int MINB>
+WaveVariant sweep_variant()
+{
+    using C = SweepCfg<NSW, PRE, POST, TX, TY>;
+    WaveVariant v;
+    v.fn = (const void *)k_sweep<NSW, PRE, POST, TX, TY, MINB>;
+    v.smem = C::SMEM;
+    v.H = C::H; v.W = C::X; v.HH = C::Y; v.TX = TX; v.TY = TY; v.NT = C::NT;
+    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, C::NT, v.smem));
+    VDN_REQUIRE(v.occ >= 1, "k_sweep variant does not fit on an SM");
+    return v;
+}
+constexpr int SWEEP_NCFG = 3;
+WaveVariant &sweep_get(int cfg, int nsw, int pre, int post)
+{
+    static WaveVariant tab[SWEEP_NCFG][2][2][3];
+    VDN_REQUIRE(nsw == 1 || nsw == 2, "k_sweep is instantiated for one or two sweeps per launch");
+    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
+    WaveVariant &v = tab[cfg][nsw - 1][pre][pi];
+    if (v.fn) return v;
+#define SV1(C, NSW, TX, TY, MB) \
+    if (cfg == C && nsw == NSW) { \
+        if (pre == 0 && post == 0) v = sweep_variant<NSW, 0, 0, TX, TY, MB>(); \
+        if (pre == 0 && post == 2) v = sweep_variant<NSW, 0, 2, TX, TY, MB>(); \
+        if (pre == 0 && post == 3) v = sweep_variant<NSW, 0, 3, TX, TY, MB>(); \
+        if (pre == 1 && post == 0) v = sweep_variant<NSW, 1, 0, TX, TY, MB>(); \
+        if (pre == 1 && post == 2) v = sweep_variant<NSW, 1, 2, TX, TY, MB>(); \
+        if (pre == 1 && post == 3) v = sweep_variant<NSW, 1, 3, TX, TY, MB>(); \
+    }
+    SV1(0, 1, 64, 32, 1) SV1(1, 1, 64, 16, 2) SV1(2, 1, 32, 16, 3)
+    SV1(0, 2, 64, 16, 1) SV1(1, 2, 32, 16, 2) SV1(2, 2, 32, 8, 2)
+#undef SV1
+    VDN_REQUIRE(v.fn != nullptr, "no such k_sweep variant");
+    return v;
+}
+
 // one fused launch on level l: nsw sweeps reading L.phi, writing L.res; then the two buffers swap roles
 void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
 {
     Lev &L = m->L[l];
     // pick tile shape and z-chunking: cost ~ waves * CTAs sharing an SM * iterations * plane cells
     int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
-    for (int cfg = 0; cfg < 2; ++cfg) {
+    const int kind = m->fuse_kind;
+    auto variant = [&](int cfg) -> const WaveVariant & { return kind == 2 ? sweep_get(cfg, nsw, pre, post) : wave_get(cfg, nsw, pre, post); };
+    for (int cfg = 0; cfg < (kind == 2 ? SWEEP_NCFG : 2); ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
-        const WaveVariant &v = wave_get(cfg, nsw, pre, post);
+        const WaveVariant &v = variant(cfg);
         const long ntiles = (long)cdiv(L.n[0], v.TX) * cdiv(L.n[1], v.TY);
         const long slots = (long)m->sm_count * v.occ;
         for (int nz = 1; nz <= std::max(1, L.n[2] / 8); ++nz) {
@@ -517,7 +561,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
             if (cost < best * (1.0 - 1e-9)) { best = cost; best_cfg = cfg; best_ch = ch; }
         }
     }
-    const WaveVariant &v = wave_get(best_cfg, nsw, pre, post);
+    const WaveVariant &v = variant(best_cfg);
     WaveArgs a;
     for (int d = 0; d < 3; ++d) { a.n[d] = L.n[d]; a.h2[d] = L.h2inv[d]; a.mode[d][0] = L.mode[d][0]; a.mode[d][1] = L.mode[d][1]; }
     a.s1 = L.s[1]; a.s2 = L.s[2]; a.off = L.off; a.par0 = L.par0;
