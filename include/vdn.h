@@ -138,6 +138,19 @@ int vdn_make_at_halftime(vdn_ctx *ctx);
  * advance_premac -> macproject -> scalar_advance -> make_at_halftime -> velocity_advance. */
 int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, double *mac_resnorm);
 
+/* The same pass driven from HOST multifabs, i.e. what the Fortran advance_timestep hands over and takes back
+ * (advance_timestep.f90:26-27 arguments; SURVEY 8(b) "Copies"): every pointer array has one entry per local box
+ * (dataptr(mf,i)), ghost widths / components as in the field table above.  Uploads run on a copy stream in the order
+ * the stages first read them (ext_vel_force, gp, sold | uold | ext_scal_force) and each stage waits only for its own
+ * inputs; snew and rhohalf travel back while velocity_advance is still running, unew last.  Returns when every output
+ * array is complete on the host.  Host arrays should be page-locked (cudaHostRegister once per layout) for the copies to
+ * overlap; pageable memory works but serialises. */
+typedef struct vdn_host_state {
+    const double *const *uold, *const *sold, *const *gp, *const *ext_vel_force, *const *ext_scal_force;   /* in  */
+    double *const *unew, *const *snew, *const *rhohalf;                                                    /* out */
+} vdn_host_state;
+int vdn_advance_host(vdn_ctx *ctx, double dt, double mac_rel_eps, const vdn_host_state *hs, int *mac_cycles, double *mac_resnorm);
+
 /* ---- building blocks exposed for parity tests (macproject.f90 internal procedures) ---- */
 int vdn_divumac(vdn_ctx *ctx, double *rhmax);     /* RH = MAC_RHS - div(UMAC), macproject.f90:137 */
 int vdn_mk_mac_coeffs(vdn_ctx *ctx);              /* BETA_* from SOLD comp 1, macproject.f90:280 */

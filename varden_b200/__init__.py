@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "vdn_nccl_unique_id", "vdn_comm_plan",
     "vdn_field_upload", "vdn_field_download", "vdn_field_setval", "vdn_sync", "vdn_get_stream",
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
-    "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance",
+    "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
     "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count",
 ]
@@ -39,6 +39,12 @@ class VdnParams(C.Structure):
                 ("mg_max_cycles", C.c_int), ("mg_max_bottom_iter", C.c_int),
                 ("mg_bottom_eps", C.c_double), ("visc_coef", C.c_double), ("diff_coef", C.c_double),
                 ("bc_val", C.c_double * 30)]
+
+
+class VdnHostState(C.Structure):
+    """vdn_host_state: one pointer per local box and multifab (include/vdn.h)"""
+    _fields_ = [(k, C.POINTER(C.POINTER(C.c_double))) for k in
+                ("uold", "sold", "gp", "ext_vel_force", "ext_scal_force", "unew", "snew", "rhohalf")]
 
 
 class VdnError(RuntimeError):
@@ -55,6 +61,18 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise VdnError("varden_b200/libvdn.so is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(nvcc, sm_100a). The hot path has no CPU fallback.")
+        # libvdn.so needs libnccl.so.2.  PyTorch ships a newer NCCL under the same SONAME than the system one; whichever is mapped
+        # first serves both, so map PyTorch's first (a superset) -- otherwise a later `import torch` fails to resolve its symbols.
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia")
+            for base in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                    break
+        except Exception:
+            pass
         _lib = C.CDLL(LIB_PATH)
         _lib.vdn_last_error.restype = C.c_char_p
         _lib.vdn_launch_count.restype = C.c_longlong
@@ -201,6 +219,25 @@ class Context:
         """advance_timestep.f90:95-124 on the device; returns (V-cycles, final relative residual)."""
         n, r = C.c_int(0), C.c_double(0.0)
         self._chk(self.lib.vdn_advance(self.h, C.c_double(dt), C.c_double(mac_rel_eps), C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def host_state(self, **mfs):
+        """build a vdn_host_state from lists of per-box numpy arrays (order F, float64; page-locked for overlapping copies)"""
+        hs = VdnHostState()
+        keep = []
+        for k, _ in VdnHostState._fields_:
+            mf = mfs[k]
+            assert len(mf) == len(self.boxes) and all(a.dtype == np.float64 and a.flags.f_contiguous for a in mf)
+            arr = (C.POINTER(C.c_double) * len(mf))(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in mf])
+            keep.append(arr)
+            setattr(hs, k, C.cast(arr, C.POINTER(C.POINTER(C.c_double))))
+        hs._keep = (keep, mfs)
+        return hs
+
+    def advance_host(self, dt, hs, mac_rel_eps=-1.0):
+        """the same pass from / to HOST multifabs (vdn_advance_host): pipelined H2D -> stages -> D2H"""
+        n, r = C.c_int(0), C.c_double(0.0)
+        self._chk(self.lib.vdn_advance_host(self.h, C.c_double(dt), C.c_double(mac_rel_eps), C.byref(hs), C.byref(n), C.byref(r)))
         return n.value, r.value
 
     # ---- measurement ----

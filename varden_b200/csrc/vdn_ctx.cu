@@ -216,14 +216,16 @@ static void ctx_free(vdn_ctx *c)
     if (c->stage) cudaFreeHost(c->stage);
     for (auto &p : c->prof) for (auto &pr : p.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); for (int i = 0; i < VDN_NFIELDS; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_fin[i]); } }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 // copy between a host box array and the region array: valid cells of the box plus the ghost cells that lie
 // outside the region's valid area (ghosts inside it are other boxes' valid cells).
-static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int ncomp, bool upload)
+static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int ncomp, bool upload, cudaStream_t stream = nullptr, bool wait = true)
 {
+    if (!stream) stream = c->stream;
     VDN_REQUIRE(field >= 0 && field < VDN_NFIELDS, "bad field id");
     VDN_REQUIRE(ibox >= 0 && ibox < c->nboxes, "bad box index");
     DField &f = c->f[field];
@@ -240,6 +242,15 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
         clo[d] = lo - (lo == c->rlo[d] ? ng : 0);
         chi[d] = hi + nod + (hi == c->rhi[d] ? ng : 0);
     }
+    // one box covering the region, stored with the host's own ghost width: host and device layouts coincide -> one flat copy
+    bool flat = c->nboxes == 1;
+    for (int d = 0; d < c->dim; ++d) if (f.ngd[d] != ng || f.ext[d] != hext[d]) flat = false;
+    if (flat) {
+        if (upload) VDN_CUDA(cudaMemcpyAsync(f.base, host, f.bytes, cudaMemcpyHostToDevice, stream));
+        else        VDN_CUDA(cudaMemcpyAsync(host, f.base, f.bytes, cudaMemcpyDeviceToHost, stream));
+        if (!upload && wait) VDN_CUDA(cudaStreamSynchronize(stream));
+        return;
+    }
     cudaMemcpy3DParms p; memset(&p, 0, sizeof p);
     const size_t hplane = (size_t)hext[0] * hext[1], dplane = (size_t)f.ext[0] * f.ext[1];
     for (int comp = 0; comp < ncomp; ++comp) {
@@ -252,19 +263,31 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
         p.extent = make_cudaExtent(sizeof(double) * (chi[0] - clo[0] + 1), chi[1] - clo[1] + 1, chi[2] - clo[2] + 1);
         if (upload) { p.srcPtr = hptr; p.srcPos = hpos; p.dstPtr = dptr; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
         else        { p.srcPtr = dptr; p.srcPos = dpos; p.dstPtr = hptr; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
-        VDN_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+        VDN_CUDA(cudaMemcpy3DAsync(&p, stream));
         (void)hplane; (void)dplane;
     }
-    if (!upload) VDN_CUDA(cudaStreamSynchronize(c->stream));
+    if (!upload && wait) VDN_CUDA(cudaStreamSynchronize(stream));
 }
 
 // one pass of the hot path, advance_timestep.f90:95-124
+// vdn_advance_host hooks: a stage waits for the upload of its own inputs; an output starts its way back as soon as it is final
+static void io_need(vdn_ctx *c, int field) { if (c->hio) VDN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[field], 0)); }
+static void io_final(vdn_ctx *c, int field, double *const *host)
+{
+    if (!c->hio) return;
+    VDN_CUDA(cudaEventRecord(c->ev_fin[field], c->stream));
+    VDN_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_fin[field], 0));
+    for (int b = 0; b < c->nboxes; ++b) box_copy(c, field, b, host[b], c->f[field].ng, c->f[field].nc, false, c->s_d2h, false);
+}
+
 static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles, double *resnorm)
 {
     // advance_timestep.f90:76-77 builds umac = 1.d20 every step; here the 1.d20 poison is set once at context creation:
     // the only faces that keep it (ghost faces outside non-periodic boundaries) are never written afterwards.
     // advance_premac (advance_premac.f90:44-51)
+    io_need(c, VDN_EXT_VEL_FORCE); io_need(c, VDN_GP); io_need(c, VDN_SOLD);
     st_mkvelforce(c, VDN_SOLD, 1.0);
+    io_need(c, VDN_UOLD);
     st_velpred(c, dt);
     // macproject (macproject.f90:20-133)
     st_divumac(c, false);
@@ -273,17 +296,21 @@ static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles,
     int rc = st_mac_solve(c, mac_rel_eps > 0 ? mac_rel_eps : 1.0e-10, -1.0, cycles, resnorm);
     st_mkumac(c);
     // scalar_advance (scalar_advance.f90:96-119)
+    io_need(c, VDN_EXT_SCAL_FORCE);
     st_mkscalforce(c, 1.0);
     st_mkflux(c, 0, dt);
     st_mkscalforce(c, 0.0);
     st_update(c, 0, dt);
+    if (c->hio) io_final(c, VDN_SNEW, c->hio->snew);
     // make_at_halftime (advance_timestep.f90:114)
     st_make_at_halftime(c);
+    if (c->hio) io_final(c, VDN_RHOHALF, c->hio->rhohalf);
     // velocity_advance (velocity_advance.f90:70-93)
     st_mkvelforce(c, VDN_SOLD, 1.0);
     st_mkflux(c, 1, dt);
     st_mkvelforce(c, VDN_RHOHALF, 0.0);
     st_update(c, 1, dt);
+    if (c->hio) io_final(c, VDN_UNEW, c->hio->unew);
     if (rc != 0) throw VdnError("MAC multigrid did not converge within mg_max_cycles");
 }
 
@@ -375,6 +402,40 @@ int vdn_macproject(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, d
 
 int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, double *mac_resnorm)
 { VDN_TRY(ctx, advance_impl(ctx, dt, mac_rel_eps, mac_cycles, mac_resnorm)) }
+
+static void advance_host_impl(vdn_ctx *c, double dt, double mac_rel_eps, const vdn_host_state *hs, int *cycles, double *resnorm)
+{
+    VDN_REQUIRE(hs && hs->uold && hs->sold && hs->gp && hs->ext_vel_force && hs->ext_scal_force && hs->unew && hs->snew && hs->rhohalf,
+                "vdn_advance_host: every host pointer array must be given");
+    if (!c->s_h2d) {
+        VDN_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        VDN_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < VDN_NFIELDS; ++i) {
+            VDN_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+            VDN_CUDA(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming));
+        }
+    }
+    // the previous pass (and whatever the caller enqueued on the context's stream) must be done with the input fields
+    VDN_CUDA(cudaEventRecord(c->ev_fin[VDN_UOLD], c->stream));
+    VDN_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_fin[VDN_UOLD], 0));
+    const struct { int field; const double *const *host; } up[5] = {
+        { VDN_EXT_VEL_FORCE, hs->ext_vel_force }, { VDN_GP, hs->gp }, { VDN_SOLD, hs->sold }, { VDN_UOLD, hs->uold },
+        { VDN_EXT_SCAL_FORCE, hs->ext_scal_force } };
+    for (const auto &u : up) {
+        for (int b = 0; b < c->nboxes; ++b)
+            box_copy(c, u.field, b, const_cast<double *>(u.host[b]), c->f[u.field].ng, c->f[u.field].nc, true, c->s_h2d);
+        VDN_CUDA(cudaEventRecord(c->ev_up[u.field], c->s_h2d));
+    }
+    c->hio = hs;
+    try { advance_impl(c, dt, mac_rel_eps, cycles, resnorm); }
+    catch (...) { c->hio = nullptr; cudaStreamSynchronize(c->s_d2h); throw; }
+    c->hio = nullptr;
+    VDN_CUDA(cudaStreamSynchronize(c->s_d2h));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+int vdn_advance_host(vdn_ctx *ctx, double dt, double mac_rel_eps, const vdn_host_state *hs, int *mac_cycles, double *mac_resnorm)
+{ VDN_TRY(ctx, advance_host_impl(ctx, dt, mac_rel_eps, hs, mac_cycles, mac_resnorm)) }
 
 int vdn_prof_enable(vdn_ctx *ctx, int on)
 { VDN_TRY(ctx, { prof_collect(ctx); ctx->prof.clear(); ctx->prof_idx.clear(); ctx->prof_on = on != 0; }) }

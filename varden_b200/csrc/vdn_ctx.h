@@ -43,6 +43,10 @@ struct vdn_ctx {
     MG *mg = nullptr;
     Comm *comm = nullptr;
     long long umac_epoch = 0, eps_epoch = -1;          // UMAC_* write counter / counter value the per-box umac eps was computed at
+    // vdn_advance_host: copy streams + per-field events (uploaded / final on the device)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_up[VDN_NFIELDS] = {}, ev_fin[VDN_NFIELDS] = {};
+    const vdn_host_state *hio = nullptr;
     int godunov_fuse = 1;                               // 3-D: all directions of a Godunov stage per launch (VDN_GODUNOV_FUSE)
 
     View S(int q) const { View v; v.sy = s_sy; v.sz = s_sz; v.cs = s_n; v.p = scratch + (long)q * s_n + s_off; return v; }

@@ -9,6 +9,7 @@
 //   multifab_physbc        multifab_physbc.f90:238-561
 // All of them are pure HBM streaming: one thread per cell, i fastest (coalesced 256 B per warp row).
 #include "vdn_ctx.h"
+#include <type_traits>
 
 namespace {
 
@@ -23,26 +24,39 @@ const dim3 BLK(64, 4, 1);
 
 // ---------------- update ----------------
 struct UpdArgs { Range r; int dim, ncomp, is_vel, cons_mask; View sold, snew, force, mac[3], sedge[3], flux[3]; double dt, dx[3]; };
-template <int DIM>
-__global__ void k_update(UpdArgs a)
+// NC components per thread, every load issued (read-only path) before the first store so the memory system sees them all at once
+template <int DIM, int NC, bool VEL>
+__global__ void __launch_bounds__(256) k_update(UpdArgs a)
 {
     THREAD_IJK(a.r)
-    const double ubar = HALF * (a.mac[0](i, j, k) + a.mac[0](i + 1, j, k));
-    const double vbar = HALF * (a.mac[1](i, j, k) + a.mac[1](i, j + 1, k));
-    double wbar = ZERO;
-    if (DIM == 3) wbar = HALF * (a.mac[2](i, j, k) + a.mac[2](i, j, k + 1));
-    for (int c = 0; c < a.ncomp; ++c) {
+    const long sx = 1, sy = a.mac[1].sy, sz = a.mac[2].sz;
+    const double *m0 = &a.mac[0](i, j, k), *m1 = &a.mac[1](i, j, k), *m2 = &a.mac[DIM == 3 ? 2 : 0](i, j, k);
+    const double u0 = __ldg(m0), u1 = __ldg(m0 + sx), v0 = __ldg(m1), v1 = __ldg(m1 + sy);
+    const double w0 = DIM == 3 ? __ldg(m2) : ZERO, w1 = DIM == 3 ? __ldg(m2 + sz) : ZERO;
+    double xl[NC], xh[NC], yl[NC], yh[NC], zl[NC], zh[NC], so[NC], fo[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const bool cons = !VEL && ((a.cons_mask >> c) & 1);
+        const View &fx = cons ? a.flux[0] : a.sedge[0], &fy = cons ? a.flux[1] : a.sedge[1], &fz = cons ? a.flux[2] : a.sedge[2];
+        const double *px = &fx(i, j, k, c), *py = &fy(i, j, k, c);
+        xl[c] = __ldg(px); xh[c] = __ldg(px + 1); yl[c] = __ldg(py); yh[c] = __ldg(py + fy.sy);
+        if (DIM == 3) { const double *pz = &fz(i, j, k, c); zl[c] = __ldg(pz); zh[c] = __ldg(pz + fz.sz); } else { zl[c] = ZERO; zh[c] = ZERO; }
+        so[c] = __ldg(&a.sold(i, j, k, c)); fo[c] = __ldg(&a.force(i, j, k, c));
+    }
+    const double ubar = HALF * (u0 + u1);
+    const double vbar = HALF * (v0 + v1);
+    const double wbar = DIM == 3 ? HALF * (w0 + w1) : ZERO;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
         double adv;
-        if (!a.is_vel && ((a.cons_mask >> c) & 1)) {
-            adv = (a.flux[0](i + 1, j, k, c) - a.flux[0](i, j, k, c)) / a.dx[0]
-                + (a.flux[1](i, j + 1, k, c) - a.flux[1](i, j, k, c)) / a.dx[1];
-            if (DIM == 3) adv = adv + (a.flux[2](i, j, k + 1, c) - a.flux[2](i, j, k, c)) / a.dx[2];
+        if (!VEL && ((a.cons_mask >> c) & 1)) {
+            adv = (xh[c] - xl[c]) / a.dx[0] + (yh[c] - yl[c]) / a.dx[1];
+            if (DIM == 3) adv = adv + (zh[c] - zl[c]) / a.dx[2];
         } else {
-            adv = ubar * (a.sedge[0](i + 1, j, k, c) - a.sedge[0](i, j, k, c)) / a.dx[0]
-                + vbar * (a.sedge[1](i, j + 1, k, c) - a.sedge[1](i, j, k, c)) / a.dx[1];
-            if (DIM == 3) adv = adv + wbar * (a.sedge[2](i, j, k + 1, c) - a.sedge[2](i, j, k, c)) / a.dx[2];
+            adv = ubar * (xh[c] - xl[c]) / a.dx[0] + vbar * (yh[c] - yl[c]) / a.dx[1];
+            if (DIM == 3) adv = adv + wbar * (zh[c] - zl[c]) / a.dx[2];
         }
-        a.snew(i, j, k, c) = a.sold(i, j, k, c) - a.dt * adv + a.dt * a.force(i, j, k, c);
+        a.snew(i, j, k, c) = so[c] - a.dt * adv + a.dt * fo[c];
     }
 }
 
@@ -251,8 +265,23 @@ void st_update(vdn_ctx *c, int is_vel, double dt)
         // velocity 168 B/cell, scalars 120 B/cell (3-D)
         double bpc = is_vel ? 8.0 * (dim + dim + dim * dim + dim + dim) : 8.0 * (2 + dim + dim + dim + 2 + 2);
         LaunchScope ls(c, is_vel ? "update_vel" : "update_scal", (double)c->ncells() * bpc);
-        if (dim == 3) k_update<3><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
-        else          k_update<2><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        // the flux arrays carry one comp (density): comps >= 1 are never conservative, so their index stays inside sedge
+        auto go = [&](auto D, auto NC, auto VEL) {
+            k_update<decltype(D)::value, decltype(NC)::value, decltype(VEL)::value><<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        };
+        using std::integral_constant;
+        const int nc = a.ncomp;
+        VDN_REQUIRE(nc >= 1 && nc <= 8, "update: component count out of range");
+        auto by_nc = [&](auto D, auto VEL) {
+            switch (nc) {
+            case 1: go(D, integral_constant<int, 1>(), VEL); break; case 2: go(D, integral_constant<int, 2>(), VEL); break;
+            case 3: go(D, integral_constant<int, 3>(), VEL); break; case 4: go(D, integral_constant<int, 4>(), VEL); break;
+            case 5: go(D, integral_constant<int, 5>(), VEL); break; case 6: go(D, integral_constant<int, 6>(), VEL); break;
+            case 7: go(D, integral_constant<int, 7>(), VEL); break; default: go(D, integral_constant<int, 8>(), VEL); break;
+            }
+        };
+        if (dim == 3) { if (is_vel) by_nc(integral_constant<int, 3>(), std::true_type()); else by_nc(integral_constant<int, 3>(), std::false_type()); }
+        else          { if (is_vel) by_nc(integral_constant<int, 2>(), std::true_type()); else by_nc(integral_constant<int, 2>(), std::false_type()); }
         VDN_CUDA(cudaGetLastError());
     }
     // ml_restrict_and_fill (update.f90:103-107)
