@@ -32,13 +32,15 @@ struct VdnError : std::runtime_error { using std::runtime_error::runtime_error; 
 // so ghost cells are reached with negative indices.  Local index = global index - region_lo.
 struct View {
     double *p;
-    long sy, sz, cs;
+    // 32-bit strides and offsets: the stage kernels are issue-bound and 64-bit index arithmetic costs 3-4 instructions per
+    // multiply; alloc_field refuses fields of 2^31 elements (16 GB) or more
+    int sy, sz, cs;
     __host__ __device__ __forceinline__ double &operator()(int i, int j, int k, int c = 0) const {
-        return p[(long)i + sy * (long)j + sz * (long)k + cs * (long)c];
+        return p[i + sy * j + sz * k + cs * c];
     }
-    __host__ __device__ __forceinline__ View comp(int c) const { View v = *this; v.p += cs * (long)c; return v; }
+    __host__ __device__ __forceinline__ View comp(int c) const { View v = *this; v.p += (long)cs * (long)c; return v; }
     // stride along direction d
-    __host__ __device__ __forceinline__ long st(int d) const { return d == 0 ? 1 : (d == 1 ? sy : sz); }
+    __host__ __device__ __forceinline__ int st(int d) const { return d == 0 ? 1 : (d == 1 ? sy : sz); }
 };
 
 constexpr int VDN_MAXCUT = 16;
@@ -73,7 +75,7 @@ struct DField {
     long sy = 0, sz = 0, cs = 0;
     int ngd[3] = {0, 0, 0};     // ghost width per direction (0 in the unused 3rd direction of 2-D)
     View view() const {
-        View v; v.sy = sy; v.sz = sz; v.cs = cs;
+        View v; v.sy = (int)sy; v.sz = (int)sz; v.cs = (int)cs;
         v.p = base + ngd[0] + sy * ngd[1] + sz * ngd[2];
         return v;
     }

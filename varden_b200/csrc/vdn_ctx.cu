@@ -92,6 +92,7 @@ static void alloc_field(vdn_ctx *c, int id, int ng, int nc, int fdir, int sng = 
     }
     f.sy = f.ext[0]; f.sz = (long)f.ext[0] * f.ext[1]; f.cs = f.sz * f.ext[2];
     f.bytes = (size_t)f.cs * nc * sizeof(double);
+    VDN_REQUIRE(f.cs * (long)std::max(nc, 3) < (1L << 31), "field too large for 32-bit element offsets (2^31 elements)");
     VDN_CUDA(cudaMalloc(&f.base, f.bytes));
     VDN_CUDA(cudaMemsetAsync(f.base, 0, f.bytes, c->stream));
 }
@@ -246,8 +247,9 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
     bool flat = c->nboxes == 1;
     for (int d = 0; d < c->dim; ++d) if (f.ngd[d] != ng || f.ext[d] != hext[d]) flat = false;
     if (flat) {
-        if (upload) VDN_CUDA(cudaMemcpyAsync(f.base, host, f.bytes, cudaMemcpyHostToDevice, stream));
-        else        VDN_CUDA(cudaMemcpyAsync(host, f.base, f.bytes, cudaMemcpyDeviceToHost, stream));
+        const size_t nb = sizeof(double) * (size_t)f.cs * ncomp;      // not f.bytes: SEDGE_* alias the (larger) UEDGE_* storage
+        if (upload) VDN_CUDA(cudaMemcpyAsync(f.base, host, nb, cudaMemcpyHostToDevice, stream));
+        else        VDN_CUDA(cudaMemcpyAsync(host, f.base, nb, cudaMemcpyDeviceToHost, stream));
         if (!upload && wait) VDN_CUDA(cudaStreamSynchronize(stream));
         return;
     }

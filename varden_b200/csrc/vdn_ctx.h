@@ -49,7 +49,7 @@ struct vdn_ctx {
     const vdn_host_state *hio = nullptr;
     int godunov_fuse = 1;                               // 3-D: all directions of a Godunov stage per launch (VDN_GODUNOV_FUSE)
 
-    View S(int q) const { View v; v.sy = s_sy; v.sz = s_sz; v.cs = s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
+    View S(int q) const { View v; v.sy = (int)s_sy; v.sz = (int)s_sz; v.cs = (int)s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
     long ncells() const { return (long)geo.n[0] * geo.n[1] * geo.n[2]; }
 };
 

@@ -10,7 +10,7 @@ constexpr double HALF = 0.5, ZERO = 0.0, ONE = 1.0, TWO = 2.0;
 // slopes (slope.f90).  s points at cell m along a direction with stride st; n = region cells along it.
 // bclo/bchi: adv_bc is EXT_DIR or HOEXTRAP on that region face.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void slope_parts(const double *s, long st, double &cen, double &lim, double &flag, double &fromm)
+__device__ __forceinline__ void slope_parts(const double *s, int st, double &cen, double &lim, double &flag, double &fromm)
 {
     const double sm = s[-st], s0 = s[0], sp = s[st];
     cen = HALF * (sp - sm);
@@ -21,7 +21,7 @@ __device__ __forceinline__ void slope_parts(const double *s, long st, double &ce
     fromm = flag * fmin(lim, fabs(cen));
 }
 // one-sided 4th-order slope at the first interior cell next to a lo face (slope.f90:247-254); s points at that cell
-__device__ __forceinline__ double slope4_lo(const double *s, long st)
+__device__ __forceinline__ double slope4_lo(const double *s, int st)
 {
     const double two3rd = 2.0 / 3.0, tenth = 0.1;
     double del = (-(16.0 / 15.0)) * s[-st] + HALF * s[0] + two3rd * s[st] - tenth * s[2 * st];
@@ -30,7 +30,7 @@ __device__ __forceinline__ double slope4_lo(const double *s, long st)
     slim = (dpls * dmn > ZERO) ? slim : ZERO;
     return copysign(ONE, del) * fmin(slim, fabs(del));
 }
-__device__ __forceinline__ double slope4_hi(const double *s, long st)   // slope.f90:268-275
+__device__ __forceinline__ double slope4_hi(const double *s, int st)   // slope.f90:268-275
 {
     const double two3rd = 2.0 / 3.0, tenth = 0.1;
     double del = -((-(16.0 / 15.0)) * s[st] + HALF * s[0] + two3rd * s[-st] - tenth * s[-2 * st]);
@@ -39,7 +39,7 @@ __device__ __forceinline__ double slope4_hi(const double *s, long st)   // slope
     slim = (dpls * dmn > ZERO) ? slim : ZERO;
     return copysign(ONE, del) * fmin(slim, fabs(del));
 }
-__device__ __forceinline__ double slope2_lo(const double *s, long st)   // slope.f90:193-200
+__device__ __forceinline__ double slope2_lo(const double *s, int st)   // slope.f90:193-200
 {
     double del = (s[st] + 3.0 * s[0] - 4.0 * s[-st]) * (1.0 / 3.0);
     double dpls = TWO * (s[st] - s[0]), dmn = TWO * (s[0] - s[-st]);
@@ -47,7 +47,7 @@ __device__ __forceinline__ double slope2_lo(const double *s, long st)   // slope
     slim = (dpls * dmn > ZERO) ? slim : ZERO;
     return copysign(ONE, del) * fmin(slim, fabs(del));
 }
-__device__ __forceinline__ double slope2_hi(const double *s, long st)   // slope.f90:207-214
+__device__ __forceinline__ double slope2_hi(const double *s, int st)   // slope.f90:207-214
 {
     double del = -(s[-st] + 3.0 * s[0] - 4.0 * s[st]) * (1.0 / 3.0);
     double dpls = TWO * (s[0] - s[-st]), dmn = TWO * (s[st] - s[0]);
@@ -55,7 +55,7 @@ __device__ __forceinline__ double slope2_hi(const double *s, long st)   // slope
     slim = (dpls * dmn > ZERO) ? slim : ZERO;
     return copysign(ONE, del) * fmin(slim, fabs(del));
 }
-__device__ double slope_at(const double *s, long st, int m, int n, bool bclo, bool bchi, int order)
+__device__ double slope_at(const double *s, int st, int m, int n, bool bclo, bool bchi, int order)
 {
     if (order == 0) return ZERO;
     if ((bclo && m == -1) || (bchi && m == n)) return ZERO;
@@ -220,7 +220,7 @@ __device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int 
 {
     const int ix[3] = { i, j, k };
     const double dt2 = HALF * a.dt, h = a.g.h[D];
-    const long su = a.u.st(D);
+    const int su = a.u.st(D);
     const double *uR = &a.u(i, j, k), *uL = uR - su;
     double slL[DIM], slR[DIM];
     if (INL) {
@@ -232,7 +232,7 @@ __device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int 
             slR[c] = slope_at(uR + a.u.cs * c, su, ix[D], a.g.n[D], bl, bh, a.order);
         }
     } else {
-        const long ss = a.sl[D].st(D);
+        const int ss = a.sl[D].st(D);
         const double *sR = &a.sl[D](i, j, k), *sL = sR - ss;
 #pragma unroll
         for (int c = 0; c < DIM; ++c) { slL[c] = sL[a.sl[D].cs * c]; slR[c] = sR[a.sl[D].cs * c]; }
@@ -250,7 +250,7 @@ __device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int 
         ur[c] = uR[a.u.cs * c] - cr * slR[c];
     }
     if (a.use_minion) {
-        const long sf = a.force.st(D);
+        const int sf = a.force.st(D);
         const double *fR = &a.force(i, j, k), *fL = fR - sf;
 #pragma unroll
         for (int c = 0; c < DIM; ++c) { ul[c] = ul[c] + dt2 * fL[a.force.cs * c]; ur[c] = ur[c] + dt2 * fR[a.force.cs * c]; }
@@ -301,7 +301,7 @@ __device__ __forceinline__ void vp_trans_pt(const VpArgs &a, int i, int j, int k
     const View ulD = a.ul[D].comp(C), urD = a.ur[D].comp(C);
     const View uimhD_n = a.uimh[D].comp(D), uimhT_n = a.uimh[T].comp(T), uimhT_c = a.uimh[T].comp(C);
     const double dt6 = a.dt / 6.0, hT = a.g.h[T];
-    const long sD = uimhT_n.st(D), sT = uimhT_n.st(T);
+    const int sD = uimhT_n.st(D), sT = uimhT_n.st(T);
     // R cell = (i,j,k), L cell = R - e_D; T-faces of a cell: lo = cell index, hi = cell index + e_T
     const double *nR = &uimhT_n(i, j, k), *cR = &uimhT_c(i, j, k);
     const double *nL = nR - sD, *cL = cR - sD;
@@ -352,14 +352,14 @@ __device__ __forceinline__ void vp_final_pt(const VpArgs &a, int i, int j, int k
     const double dt2 = HALF * a.dt, dt4 = a.dt / 4.0;
     double ml, mr;
     {
-        const long sD = n1.st(D), s1 = n1.st(T1);
+        const int sD = n1.st(D), s1 = n1.st(T1);
         const double *nR = &n1(i, j, k), *xR = &x1(i, j, k);
         const double *nL = nR - sD, *xL = xR - sD;
         ml = ulD(i, j, k) - (dt4 / a.g.h[T1]) * (nL[s1] + nL[0]) * (xL[s1] - xL[0]);
         mr = urD(i, j, k) - (dt4 / a.g.h[T1]) * (nR[s1] + nR[0]) * (xR[s1] - xR[0]);
     }
     if (DIM == 3) {
-        const long sD = n2.st(D), s2 = n2.st(T2);
+        const int sD = n2.st(D), s2 = n2.st(T2);
         const double *nR = &n2(i, j, k), *xR = &x2(i, j, k);
         const double *nL = nR - sD, *xL = xR - sD;
         ml = ml - (dt4 / a.g.h[T2]) * (nL[s2] + nL[0]) * (xL[s2] - xL[0]);
@@ -472,7 +472,7 @@ __device__ __forceinline__ void mf_trans_pt(const MfArgs &a, int i, int j, int k
     const double dt3 = a.dt / 3.0, dt6 = a.dt / 6.0, hT = a.g.h[T];
     const double *qR = &a.simh[T](i, j, k), *qL = qR - a.simh[T].st(D);
     const double *mR = &a.mac[T](i, j, k), *mL = mR - a.mac[T].st(D);
-    const long sq = a.simh[T].st(T), sm = a.mac[T].st(T);
+    const int sq = a.simh[T].st(T), sm = a.mac[T].st(T);
     double l, r;
     if (a.cons) {
         l = a.l[D](i, j, k) - (dt3 / hT) * (qL[sq] * mL[sm] - qL[0] * mL[0]);
@@ -518,13 +518,13 @@ __device__ __forceinline__ void mf_final_pt(const MfArgs &a, int i, int j, int k
     const double *sR = &a.s(i, j, k), *sL = sR - a.s.st(D);
     const double *x1R = &x1(i, j, k), *x1L = x1R - x1.st(D);
     const double *m1R = &mac1(i, j, k), *m1L = m1R - mac1.st(D);
-    const long sx1 = x1.st(T1), sm1 = mac1.st(T1);
+    const int sx1 = x1.st(T1), sm1 = mac1.st(T1);
     double el = a.l[D](i, j, k), er = a.rr[D](i, j, k);
     if (DIM == 3) {
         const View x2 = a.X[T2][T1], mac2 = a.mac[T2];
         const double *x2R = &x2(i, j, k), *x2L = x2R - x2.st(D);
         const double *m2R = &mac2(i, j, k), *m2L = m2R - mac2.st(D);
-        const long sx2 = x2.st(T2), sm2 = mac2.st(T2);
+        const int sx2 = x2.st(T2), sm2 = mac2.st(T2);
         if (a.cons) {
             el = el - (dt2 / h1) * (x1L[sx1] * m1L[sm1] - x1L[0] * m1L[0])
                     - (dt2 / h2) * (x2L[sx2] * m2L[sm2] - x2L[0] * m2L[0])
