@@ -21,7 +21,8 @@ def emu():
     so = os.path.join(EMU, "libemu_wave.so")
     src = [os.path.join(EMU, "emu_wave.cpp"), os.path.join(EMU, "cuda_emu.h"),
            os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_wave.cuh"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep.cuh")]
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep.cuh"),
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep2.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
                                src[0], "-o", so])
@@ -91,7 +92,8 @@ CASES = [
 
 
 KERNELS = [("wave", 1, 0, 0), ("wave", 1, 1, 0), ("wave", 1, 0, 2), ("wave", 1, 1, 2), ("wave", 1, 0, 3), ("wave", 1, 1, 3)] + \
-          [("sweep", nsw, pre, post) for nsw in (1, 2) for pre in (0, 1) for post in (0, 2, 3)]
+          [("sweep", nsw, pre, post) for nsw in (1, 2) for pre in (0, 1) for post in (0, 2, 3)] + \
+          [("sweep2", 1, pre, post) for pre in (0, 1) for post in (0, 2, 3)]
 
 
 @pytest.mark.parametrize("n,cfg,zchunk,mode,par0", CASES)
@@ -117,7 +119,7 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
     crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan)
     nrm = np.zeros(1)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
-    fn = emu.emu_wave if kern == "wave" else emu.emu_sweep
+    fn = getattr(emu, "emu_" + kern)
     rc = fn(nsw, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), par0, P(h2),
             P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk, PAD)
     assert rc == 0
@@ -141,7 +143,7 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
             assert np.all(czero[CV] == 0.0)
 
 
-@pytest.mark.parametrize("kern", ["wave", "sweep"])
+@pytest.mark.parametrize("kern", ["wave", "sweep", "sweep2"])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
 @pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
 def test_wave_rank_ghost_layers(emu, pre, post, split, kern):
@@ -183,7 +185,7 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, kern):
         lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o); lphi = cut(phi, n, o)
         lc = cut(cphi, cn, [x // 2 for x in o])
         out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
-        fn = emu.emu_wave if kern == "wave" else emu.emu_sweep
+        fn = getattr(emu, "emu_" + kern)
         rc = fn(1, pre, post, 0, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
                 Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD)
         assert rc == 0

@@ -15,6 +15,7 @@
 #include "vdn_comm.h"
 #include "vdn_mg_wave.cuh"
 #include "vdn_mg_sweep.cuh"
+#include "vdn_mg_sweep2.cuh"
 #include <algorithm>
 
 
@@ -331,7 +332,7 @@ void mg_pick_fused(vdn_ctx *c, MG *m)
     m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
     cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
     if (fuse <= 0 || c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
-    m->fuse_kind = fuse >= 2 ? 2 : 1;
+    m->fuse_kind = fuse >= 3 ? 3 : fuse >= 2 ? 2 : 1;
     m->fuse_nsw = m->fuse_kind == 2 ? std::max(1, std::min(2, envi("VDN_MG_NSW", 1))) : 1;
     if (m->distributed) m->fuse_nsw = 1;                        // two sweeps need 5 ghost layers, the level arrays carry MG_PAD
     const int last = m->tail ? m->agg_level : m->nlev - 1;      // the agglomerated / bottom level is never fused
@@ -538,6 +539,42 @@ WaveVariant &sweep_get(int cfg, int nsw, int pre, int post)
     return v;
 }
 
+// k_sweep2 variants (operator data staged through shared memory): [tile cfg][pre][post index], one sweep per launch
+template <int PRE, int POST, int TX, int TY>
+WaveVariant sweep2_variant()
+{
+    using C = Sweep2Cfg<PRE, POST, TX, TY>;
+    WaveVariant v;
+    v.fn = (const void *)k_sweep2<PRE, POST, TX, TY>;
+    v.smem = C::SMEM;
+    v.H = C::H; v.W = C::RX; v.HH = C::RY; v.TX = TX; v.TY = TY; v.NT = C::NT;
+    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, C::NT, v.smem));
+    VDN_REQUIRE(v.occ >= 1, "k_sweep2 variant does not fit on an SM");
+    return v;
+}
+WaveVariant &sweep2_get(int cfg, int nsw, int pre, int post)
+{
+    static WaveVariant tab[SWEEP_NCFG][2][3];
+    VDN_REQUIRE(nsw == 1, "k_sweep2 is instantiated for one sweep per launch");
+    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
+    WaveVariant &v = tab[cfg][pre][pi];
+    if (v.fn) return v;
+#define SV2(C, TX, TY) \
+    if (cfg == C) { \
+        if (pre == 0 && post == 0) v = sweep2_variant<0, 0, TX, TY>(); \
+        if (pre == 0 && post == 2) v = sweep2_variant<0, 2, TX, TY>(); \
+        if (pre == 0 && post == 3) v = sweep2_variant<0, 3, TX, TY>(); \
+        if (pre == 1 && post == 0) v = sweep2_variant<1, 0, TX, TY>(); \
+        if (pre == 1 && post == 2) v = sweep2_variant<1, 2, TX, TY>(); \
+        if (pre == 1 && post == 3) v = sweep2_variant<1, 3, TX, TY>(); \
+    }
+    SV2(0, 64, 16) SV2(1, 32, 32) SV2(2, 32, 16)
+#undef SV2
+    VDN_REQUIRE(v.fn != nullptr, "no such k_sweep2 variant");
+    return v;
+}
+
 // one fused launch on level l: nsw sweeps reading L.phi, writing L.res; then the two buffers swap roles
 void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
 {
@@ -545,9 +582,12 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
     // pick tile shape and z-chunking: cost ~ waves * CTAs sharing an SM * iterations * plane cells
     int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
     const int kind = m->fuse_kind;
-    auto variant = [&](int cfg) -> const WaveVariant & { return kind == 2 ? sweep_get(cfg, nsw, pre, post) : wave_get(cfg, nsw, pre, post); };
-    for (int cfg = 0; cfg < (kind == 2 ? SWEEP_NCFG : 2); ++cfg) {
+    auto variant = [&](int cfg) -> const WaveVariant & {
+        return kind == 3 ? sweep2_get(cfg, nsw, pre, post) : kind == 2 ? sweep_get(cfg, nsw, pre, post) : wave_get(cfg, nsw, pre, post);
+    };
+    for (int cfg = 0; cfg < (kind >= 2 ? SWEEP_NCFG : 2); ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
+        if (m->tile_force < 0 && kind >= 2 && cfg != 0) continue;       // measured (profiles/r01_bench_256_v3_*): the largest tile wins on every level
         const WaveVariant &v = variant(cfg);
         const long ntiles = (long)cdiv(L.n[0], v.TX) * cdiv(L.n[1], v.TY);
         const long slots = (long)m->sm_count * v.occ;
