@@ -33,6 +33,16 @@ METRIC = "Gcell-updates/s per step (advect+MAC proj)"
 UNIT = "Gcell-updates/s"
 
 
+def ncu_traffic(kernel_family):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel family from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, written by profiles/summarize_ncu.py traffic ...); None if that family was not captured"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_family, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -261,7 +271,9 @@ def main():
         barrier()
         t_e = max_over_ranks(time.perf_counter() - t_h)
         e2e = {"value": ncells_global * args.steps / t_e / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-               "ms_per_step": 1e3 * t_e / args.steps}
+               "ms_per_step": 1e3 * t_e / args.steps,
+               "how": "vdn_advance_host (C ABI, pinned host multifabs in and out, copies on the library's copy streams overlapped with the stages); "
+                      "host clock around the blocking calls, max over ranks"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -280,7 +292,7 @@ def main():
     if top:
         t = fam[top]
         roof = {"bound": "hbm", "kernel": top, "achieved": t["gbs"], "peak": peak, "unit": "GB/s", "frac": (t["gbs"] / peak) if t["gbs"] else None,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": t["ms_total"] / max(t["launches"], 1), "share_of_step": t["share"]}
+                "traffic": ncu_traffic(top), "alg_bytes_per_launch": t["alg_gb"] * 1e9 / max(t["launches"], 1), "peak_source": peak_src, "avg_launch_ms": t["ms_total"] / max(t["launches"], 1), "share_of_step": t["share"]}
 
     cpu = None
     if not args.no_cpu and world == 1:

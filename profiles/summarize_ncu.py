@@ -54,7 +54,46 @@ def full(path, out):
                 out.write("    %-70s %s %s\n" % (w, r[h.index(w)], u[h.index(w)]))
 
 
+def family(kname, grid):
+    """bench.py kernel-family name of a captured launch (level-0 launches of the 256^3 bench are the ones with the large grid)"""
+    import re
+    m = re.search(r"k_(sweep2|sweep|wave)<([^>]*)>", kname)
+    if m:
+        a = [x.strip() for x in m.group(2).split(",")]
+        pre, post = (int(a[0]), int(a[1])) if m.group(1) == "sweep2" else (int(a[1]), int(a[2]))
+        return {2: "mg_wave_down_l0", 3: "mg_wave_up_l0"}.get(post, "mg_wave_pro_l0" if pre else "mg_wave_smooth_l0")
+    for k, f in (("k_gsrb", "mg_gsrb_l0"), ("k_residual", "mg_residual_l0"), ("k_mf_normal3", "mf_normal3"), ("k_mf_trans6", "mf_trans6"),
+                 ("k_mf_final3", "mf_final3"), ("k_vp_normal3", "vp_normal3"), ("k_vp_trans6", "vp_trans6"), ("k_vp_final3", "vp_final3"),
+                 ("k_mkvelforce", "mkvelforce")):
+        if k in kname:
+            return f
+    if "k_update" in kname:
+        return "update_vel" if ", 3, 1>" in kname.replace("(bool)1", "1") or "3, 3, true" in kname else "update_scal"
+    return None
+
+
+def traffic(path, out):
+    """{family: {dram_bytes_per_launch, duration_us, kernel}} from a --set full raw CSV: the LARGEST launch of every family"""
+    import json
+    rows = list(csv.reader(open(path)))
+    h, u = rows[0], rows[1]
+    ik, ir, iw, it, ig = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum"), h.index("Grid Size")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tsc = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
+    res = {}
+    for r in rows[2:]:
+        f = family(r[ik], r[ig])
+        if not f:
+            continue
+        b = float(r[ir].replace(",", "")) * scale[u[ir]] + float(r[iw].replace(",", "")) * scale[u[iw]]
+        t = float(r[it].replace(",", "")) * tsc[u[it]]
+        if f not in res or b > res[f]["dram_bytes_per_launch"]:
+            res[f] = {"dram_bytes_per_launch": b, "duration_us": t, "kernel": r[ik], "grid": r[ig], "source": path}
+    json.dump(res, out, indent=1, sort_keys=True)
+    out.write("\n")
+
+
 if __name__ == "__main__":
     mode, src = sys.argv[1], sys.argv[2]
     dst = open(sys.argv[3], "w") if len(sys.argv) > 3 else sys.stdout
-    (launches if mode == "launches" else full)(src, dst)
+    {"launches": launches, "full": full, "traffic": traffic}[mode](src, dst)

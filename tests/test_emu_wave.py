@@ -22,7 +22,8 @@ def emu():
     src = [os.path.join(EMU, "emu_wave.cpp"), os.path.join(EMU, "cuda_emu.h"),
            os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_wave.cuh"),
            os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep.cuh"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep2.cuh")]
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep2.cuh"),
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep3.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
                                src[0], "-o", so])
@@ -93,7 +94,7 @@ CASES = [
 
 KERNELS = [("wave", 1, 0, 0), ("wave", 1, 1, 0), ("wave", 1, 0, 2), ("wave", 1, 1, 2), ("wave", 1, 0, 3), ("wave", 1, 1, 3)] + \
           [("sweep", nsw, pre, post) for nsw in (1, 2) for pre in (0, 1) for post in (0, 2, 3)] + \
-          [("sweep2", 1, pre, post) for pre in (0, 1) for post in (0, 2, 3)]
+          [(kk, 1, pre, post) for kk in ("sweep2", "sweep3") for pre in (0, 1) for post in (0, 2, 3)]
 
 
 @pytest.mark.parametrize("n,cfg,zchunk,mode,par0", CASES)
@@ -143,7 +144,7 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
             assert np.all(czero[CV] == 0.0)
 
 
-@pytest.mark.parametrize("kern", ["wave", "sweep", "sweep2"])
+@pytest.mark.parametrize("kern", ["wave", "sweep", "sweep2", "sweep3"])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
 @pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
 def test_wave_rank_ghost_layers(emu, pre, post, split, kern):

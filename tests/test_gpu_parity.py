@@ -176,9 +176,9 @@ def test_mg_high_density_ratio():
 
 @pytest.mark.parametrize("case", ["rt64", "mixed"])
 @pytest.mark.parametrize("fuse,tile,nsw", [(1, -1, 1), (1, 0, 1), (1, 1, 1), (2, -1, 1), (2, 0, 1), (2, 1, 1), (2, 2, 1), (2, -1, 2), (2, 0, 2), (2, 1, 2), (2, 2, 2),
-                                           (3, -1, 1), (3, 0, 1), (3, 1, 1), (3, 2, 1)])
+                                           (3, -1, 1), (3, 0, 1), (3, 1, 1), (3, 2, 1), (4, -1, 1), (4, 0, 1), (4, 1, 1), (4, 2, 1)])
 def test_mg_fused_wavefront(case, fuse, tile, nsw, monkeypatch):
-    """the fused wavefront smoothers (fuse 1: k_wave, fuse 2: k_sweep, fuse 3: k_sweep2 -- GSRB sweeps + residual + restriction / prolongation in
+    """the fused wavefront smoothers (fuse 1: k_wave, fuse 2: k_sweep, fuse 3: k_sweep2, fuse 4: k_sweep3 -- GSRB sweeps + residual + restriction / prolongation in
     one launch) against the plain per-colour kernels and the oracle: same V-cycle, so phi and the projected velocity agree to
     the solver tolerance"""
     if case == "rt64":

@@ -16,6 +16,7 @@
 #include "vdn_mg_wave.cuh"
 #include "vdn_mg_sweep.cuh"
 #include "vdn_mg_sweep2.cuh"
+#include "vdn_mg_sweep3.cuh"
 #include <algorithm>
 
 
@@ -332,7 +333,7 @@ void mg_pick_fused(vdn_ctx *c, MG *m)
     m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
     cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
     if (fuse <= 0 || c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
-    m->fuse_kind = fuse >= 3 ? 3 : fuse >= 2 ? 2 : 1;
+    m->fuse_kind = fuse >= 4 ? 4 : fuse >= 3 ? 3 : fuse >= 2 ? 2 : 1;
     m->fuse_nsw = m->fuse_kind == 2 ? std::max(1, std::min(2, envi("VDN_MG_NSW", 1))) : 1;
     if (m->distributed) m->fuse_nsw = 1;                        // two sweeps need 5 ghost layers, the level arrays carry MG_PAD
     const int last = m->tail ? m->agg_level : m->nlev - 1;      // the agglomerated / bottom level is never fused
@@ -575,6 +576,42 @@ WaveVariant &sweep2_get(int cfg, int nsw, int pre, int post)
     return v;
 }
 
+// k_sweep3 variants (one column of cell pairs per thread, register-pipelined operator data): [tile cfg][pre][post index]
+template <int PRE, int POST, int TX, int TY>
+WaveVariant sweep3_variant()
+{
+    using C = Sweep3Cfg<PRE, POST, TX, TY>;
+    WaveVariant v;
+    v.fn = (const void *)k_sweep3<PRE, POST, TX, TY>;
+    v.smem = C::SMEM;
+    v.H = C::H; v.W = C::X; v.HH = C::Y; v.TX = TX; v.TY = TY; v.NT = C::NT;
+    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, C::NT, v.smem));
+    VDN_REQUIRE(v.occ >= 1, "k_sweep3 variant does not fit on an SM");
+    return v;
+}
+WaveVariant &sweep3_get(int cfg, int nsw, int pre, int post)
+{
+    static WaveVariant tab[SWEEP_NCFG][2][3];
+    VDN_REQUIRE(nsw == 1, "k_sweep3 is instantiated for one sweep per launch");
+    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
+    WaveVariant &v = tab[cfg][pre][pi];
+    if (v.fn) return v;
+#define SV3(C, TX, TY) \
+    if (cfg == C) { \
+        if (pre == 0 && post == 0) v = sweep3_variant<0, 0, TX, TY>(); \
+        if (pre == 0 && post == 2) v = sweep3_variant<0, 2, TX, TY>(); \
+        if (pre == 0 && post == 3) v = sweep3_variant<0, 3, TX, TY>(); \
+        if (pre == 1 && post == 0) v = sweep3_variant<1, 0, TX, TY>(); \
+        if (pre == 1 && post == 2) v = sweep3_variant<1, 2, TX, TY>(); \
+        if (pre == 1 && post == 3) v = sweep3_variant<1, 3, TX, TY>(); \
+    }
+    SV3(0, 32, 32) SV3(1, 64, 16) SV3(2, 32, 16)
+#undef SV3
+    VDN_REQUIRE(v.fn != nullptr, "no such k_sweep3 variant");
+    return v;
+}
+
 // one fused launch on level l: nsw sweeps reading L.phi, writing L.res; then the two buffers swap roles
 void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
 {
@@ -583,7 +620,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
     int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
     const int kind = m->fuse_kind;
     auto variant = [&](int cfg) -> const WaveVariant & {
-        return kind == 3 ? sweep2_get(cfg, nsw, pre, post) : kind == 2 ? sweep_get(cfg, nsw, pre, post) : wave_get(cfg, nsw, pre, post);
+        return kind == 4 ? sweep3_get(cfg, nsw, pre, post) : kind == 3 ? sweep2_get(cfg, nsw, pre, post) : kind == 2 ? sweep_get(cfg, nsw, pre, post) : wave_get(cfg, nsw, pre, post);
     };
     for (int cfg = 0; cfg < (kind >= 2 ? SWEEP_NCFG : 2); ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;

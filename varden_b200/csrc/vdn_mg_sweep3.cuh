@@ -1,0 +1,220 @@
+// vdn_mg_sweep3.cuh -- k_sweep3: the fused red-black smoother with ONE column of cell pairs per thread and the operator data
+// of the leading stage software-pipelined through registers.
+//
+// Lessons of the two earlier kernels (profiles/r01_ncu_full_ksweep_v3.txt, r01_ncu_full_ksweep2_v4.txt):
+//   k_sweep  (2x2 columns per thread, operator data loaded where used): 20 warps/SM, 4.6 of 11 stall cycles per issue are
+//            long-scoreboard waits -- both colour stages of a step wait for their global loads --, half of the shared-memory
+//            wavefronts are 2-way bank conflicts of the strided pair layout;
+//   k_sweep2 (operator data staged in shared memory by cp.async): the global latency is gone but 185-222 KB of shared memory
+//            leave 11 warps/SM, which cannot cover shared-memory and FP64 dependency latencies (31 % issue utilisation).
+// Here a thread owns the two cells (x, 2j) and (x, 2j+1) of a column pair: one is red, one is black, so every thread has
+// exactly ONE active cell per step and runs all colour stages on it (stage s on plane t-s; z-neighbours in program order,
+// x/y-neighbours written one step earlier -> one barrier per plane, as in k_sweep).  Consecutive lanes are consecutive x:
+// global accesses are coalesced 8-byte words, shared-memory rows are read conflict-free (the two interleaved rows of a warp
+// fall into disjoint banks).  A 32x32 core tile needs 648 threads and 41 KB: 21 warps per SM.  The operator data of stage 0
+// of step t+1 (new lines, HBM latency) is loaded into registers at the top of step t; stage 1 (and the residual stage) read
+// lines that were streamed one (two) steps earlier and are L1/L2-resident; both are issued before the phi traffic of the step.
+#pragma once
+#include "vdn_mg_sweep.cuh"
+
+#ifdef VDN_EMU
+inline double emu_shfl_buf[2048];
+inline double __shfl_xor_sync(unsigned, double v, int m)
+{
+    emu_shfl_buf[threadIdx.x] = v;
+    __syncthreads();
+    const double r = emu_shfl_buf[threadIdx.x ^ m];
+    __syncthreads();
+    return r;
+}
+#endif
+
+template <int PRE, int POST, int TX, int TY>
+struct Sweep3Cfg {
+    static constexpr int S = 2, E = POST ? 1 : 0, H = S + E, HE = (H + 1) & ~1;
+    static constexpr int X = TX + 2 * HE, Y = TY + 2 * HE;      // shared-memory tile; row pairs / lane pairs aligned to even global indices
+    static constexpr int BY = Y / 2, PLANE = X * Y;
+    static constexpr int NPL = S + 2 + E;                        // phi ring: planes t-S-E .. t+1
+    static constexpr size_t SMEM = sizeof(double) * PLANE * NPL;
+    static constexpr int NT = ((X * BY + 31) / 32) * 32;
+    static_assert(TX % 2 == 0 && TY % 2 == 0, "even tiles");
+};
+
+template <int PRE, int POST, int TX, int TY>
+__global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(const WaveArgs a)
+{
+    using C = Sweep3Cfg<PRE, POST, TX, TY>;
+    constexpr int S = C::S, E = C::E, H = C::H, HE = C::HE, X = C::X, PLANE = C::PLANE, NPL = C::NPL;
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int z0 = blockIdx.z * a.zchunk, z1 = min(z0 + a.zchunk, a.n[2]);
+    const int n0 = a.n[0], n1 = a.n[1], n2 = a.n[2];
+    const int mx0 = a.mode[0][0], mx1 = a.mode[0][1], my0 = a.mode[1][0], my1 = a.mode[1][1], mz0 = a.mode[2][0], mz1 = a.mode[2][1];
+    const bool have = tid < X * C::BY;
+    const int ty = have ? tid / X : 0, lx = have ? tid - ty * X : 0, ly0 = 2 * ty;
+    const int gx = x0 - HE + lx, gy0 = y0 - HE + ly0;           // unwrapped global coordinates (gy0 even)
+    const int sid = ly0 * X + lx;                               // shared-memory index of the pair's row-0 cell
+
+    // per cell (row r): number of stages it may run (0: not loaded).  Stage s needs s+1 cells to the edge of the H-grown region.
+    const int ux = lx - (HE - H);
+    const int wx = wave_idx<H>(gx, n0, mx0, mx1);
+    const bool okx = have && wx != WAVE_NONE && ux >= 0 && ux < TX + 2 * H;
+    int depth[2], wy[2];
+    bool ld[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int uy = ly0 + r - (HE - H);
+        wy[r] = wave_idx<H>(gy0 + r, n1, my0, my1);
+        ld[r] = okx && wy[r] != WAVE_NONE && uy >= 0 && uy < TY + 2 * H;
+        const int d = min(min(ux, TX + 2 * H - 1 - ux), min(uy, TY + 2 * H - 1 - uy));
+        depth[r] = ld[r] ? min(max(d, 0), H) : 0;
+    }
+    const int wyb = ld[0] ? wy[0] : wy[1] - 1;                  // rows of a pair exist together except on the masked outer ring
+    const long gofs = a.off + (okx ? wx : 0) + a.s1 * (long)wyb;  // + s1 * row + s2 * plane
+    const long cofs = PRE ? a.coff + ((okx ? wx : 0) >> 1) + a.cs1 * (long)(wyb >> 1) : 0;
+    const bool anyld = ld[0] || ld[1];
+    const bool bndx = (gx == 0 && (mx0 == M_NEU || mx0 == M_DIR)) || (gx == n0 - 1 && (mx1 == M_NEU || mx1 == M_DIR));
+    bool bndy[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+        bndy[r] = (gy0 + r == 0 && (my0 == M_NEU || my0 == M_DIR)) || (gy0 + r == n1 - 1 && (my1 == M_NEU || my1 == M_DIR));
+    const bool core = have && lx >= HE && lx < HE + TX && ly0 >= HE && ly0 < HE + TY && gx < n0 && gy0 < n1;
+
+    auto zidx = [&](int p) { return (p >= z0 - H && p <= z1 - 1 + H) ? wave_idx<H>(p, n2, mz0, mz1) : WAVE_NONE; };
+    auto ring = [](int p) { return ((p + 64 * NPL) % NPL) * PLANE; };
+
+    // ---- phi prefetch registers: the pair's two cells of one plane (+ the coarse correction under them) ----
+    double pf[2] = { 0.0, 0.0 }, pc = 0.0;
+    auto fetch = [&](int wz) {
+        pf[0] = 0.0; pf[1] = 0.0; pc = 0.0;
+        if (wz != WAVE_NONE && anyld) {
+            const double *src = a.in + gofs + a.s2 * (long)wz;
+            if (ld[0]) pf[0] = src[0];
+            if (ld[1]) pf[1] = src[a.s1];
+            if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wz >> 1));
+        }
+    };
+    auto stash = [&](int o) {
+        if (!have) return;
+        sm[o + sid] = pf[0] + ((PRE && ld[0]) ? pc : 0.0);
+        sm[o + sid + X] = pf[1] + ((PRE && ld[1]) ? pc : 0.0);
+    };
+
+    // A*phi and the diagonal at tile cell `id` of the plane at ring offset o0 (o0m / o0p: the planes below / above)
+    auto apply = [&](int p, int o0, int o0m, int o0p, int id, int gy, bool general, const SweepCoef &c, double &ax, double &dg, double &p0) {
+        const double *P0 = sm + o0 + id;
+        p0 = P0[0];
+        const double xm = P0[-1], xp = P0[1], ym = P0[-X], yp = P0[X], zm = sm[o0m + id], zp = sm[o0p + id];
+        if (!general) {
+            ax = (c.xl * (p0 - xm) + c.xh * (p0 - xp)) * a.h2[0] + (c.yl * (p0 - ym) + c.yh * (p0 - yp)) * a.h2[1]
+               + (c.zl * (p0 - zm) + c.zh * (p0 - zp)) * a.h2[2];
+            dg = (c.xl + c.xh) * a.h2[0] + (c.yl + c.yh) * a.h2[1] + (c.zl + c.zh) * a.h2[2];
+        } else {
+            ax = 0.0; dg = 0.0;
+            wave_dir(c.xl, c.xh, a.h2[0], p0, xm, xp, gx == 0, gx == n0 - 1, mx0, mx1, ax, dg);
+            wave_dir(c.yl, c.yh, a.h2[1], p0, ym, yp, gy == 0, gy == n1 - 1, my0, my1, ax, dg);
+            wave_dir(c.zl, c.zh, a.h2[2], p0, zm, zp, p == 0, p == n2 - 1, mz0, mz1, ax, dg);
+        }
+    };
+    // may stage s run on row r of plane p?
+    auto runs = [&](int s, int p, int r, bool exists) {
+        const int RS = E + S - 1 - s;
+        return exists && p >= z0 - RS && p <= z1 - 1 + RS && (r ? depth[1] : depth[0]) > s;
+    };
+
+    double nmax = 0.0, acc = 0.0;
+    const int tfirst = z0 - H, tlast = z1 + S - 2 + E;
+    // ring offsets as rotating registers: at step t, oP[k] = offset of plane t+1-k; wzq[k] = array plane index of plane t+2-k
+    int oP[NPL], wzq[S + 3 + E];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) oP[k] = ring(tfirst - k);             // state "step tfirst-1", rotated at the top of the loop
+#pragma unroll
+    for (int k = 0; k < S + 3 + E; ++k) wzq[k] = zidx(tfirst + 1 - k);
+    fetch(wzq[1]); stash(oP[0]); fetch(wzq[0]);                        // planes tfirst (into the ring) and tfirst+1 (registers)
+    // operator data of stage 0 of the first step
+    SweepCoef c0n;
+    bool run0n;
+    {
+        const int ra = (gx + tfirst + a.par0) & 1;
+        run0n = runs(0, tfirst, ra, wzq[1] != WAVE_NONE);
+        if (run0n) sweep_load(c0n, a, gofs + a.s1 * ra + a.s2 * (long)wzq[1]);
+    }
+    __syncthreads();
+
+    for (int t = tfirst; t <= tlast; ++t) {
+        const int ra = (gx + t + a.par0) & 1;                    // active row of this column in this step
+        { const int x = oP[NPL - 1];
+#pragma unroll
+          for (int k = NPL - 1; k > 0; --k) oP[k] = oP[k - 1];
+          oP[0] = x; }
+#pragma unroll
+        for (int k = S + 2 + E; k > 0; --k) wzq[k] = wzq[k - 1];
+        wzq[0] = zidx(t + 2);
+        // ---- operator data of stage 1: lines that stage 0 streamed one step ago (L1/L2-resident), issued before the phi traffic ----
+        SweepCoef c1;
+        const bool run1 = runs(1, t - 1, ra, wzq[3] != WAVE_NONE);
+        if (run1) sweep_load(c1, a, gofs + a.s1 * ra + a.s2 * (long)wzq[3]);
+        const int r0 = t - S;
+        const bool run2 = POST && core && r0 >= z0 && r0 < z1;
+        // ---- plane t+1 into the ring, plane t+2 on its way ----
+        stash(oP[0]);
+        fetch(wzq[0]);
+        const int id = sid + (ra ? X : 0), gy = gy0 + ra;
+        const bool bxy = bndx || (ra ? bndy[1] : bndy[0]);
+        // ---- stage 0 on plane t: its operator data was requested in the middle of the previous step ----
+        if (run0n) {
+            const int p = t;
+            const bool zb = (p == 0 && (mz0 == M_NEU || mz0 == M_DIR)) || (p == n2 - 1 && (mz1 == M_NEU || mz1 == M_DIR));
+            double ax, dg, p0;
+            apply(p, oP[1], oP[2], oP[0], id, gy, bxy || zb, c0n, ax, dg, p0);
+            if (dg != 0.0) sm[oP[1] + id] = p0 + (c0n.rhs - ax) / dg;
+        }
+        // ---- request the operator data of stage 0 of the NEXT step (new lines: HBM latency, half a step + the barrier to arrive) ----
+        run0n = runs(0, t + 1, ra ^ 1, wzq[1] != WAVE_NONE);
+        if (run0n) sweep_load(c0n, a, gofs + a.s1 * (ra ^ 1) + a.s2 * (long)wzq[1]);
+        // ---- stage 1 on plane t-1 ----
+        if (run1) {
+            const int p = t - 1;
+            const bool zb = (p == 0 && (mz0 == M_NEU || mz0 == M_DIR)) || (p == n2 - 1 && (mz1 == M_NEU || mz1 == M_DIR));
+            double ax, dg, p0;
+            apply(p, oP[2], oP[3], oP[1], id, gy, bxy || zb, c1, ax, dg, p0);
+            if (dg != 0.0) sm[oP[2] + id] = p0 + (c1.rhs - ax) / dg;
+        }
+        // ---- plane t-S+1 has passed every stage: write it out ----
+        {
+            const int r1 = t - S + 1;
+            if (core && r1 >= z0 && r1 < z1) {
+                double *dst = a.out + gofs + a.s2 * (long)r1;
+                dst[0] = sm[oP[S] + sid];
+                dst[a.s1] = sm[oP[S] + sid + X];
+            }
+        }
+        // ---- residual of plane t-S: red cells only (the black ones were just relaxed) ----
+        if (POST) {
+            double res = 0.0;
+            if (run2) {
+                SweepCoef c2; sweep_load(c2, a, gofs + a.s1 * ra + a.s2 * (long)r0);        // streamed two steps ago
+                const bool zb = (r0 == 0 && (mz0 == M_NEU || mz0 == M_DIR)) || (r0 == n2 - 1 && (mz1 == M_NEU || mz1 == M_DIR));
+                double ax, dg, p0;
+                apply(r0, oP[S + 1], oP[(S + 2) % NPL], oP[S], id, gy, bxy || zb, c2, ax, dg, p0);
+                res = c2.rhs - ax;
+                if (POST == 3) nmax = fmax(nmax, fabs(res));
+            }
+            if (POST == 2) {
+                // the 2x2 block of a coarse cell: this column and its lane partner (x ^ 1) hold one red cell each
+                const double s2 = res + __shfl_xor_sync(0xffffffffu, res, 1);
+                if (run2) {
+                    if ((r0 & 1) == 0) acc = s2;
+                    else if ((gx & 1) == 0) {
+                        const long cc = a.coff + (gx >> 1) + a.cs1 * (long)(gy0 >> 1) + a.cs2 * (long)(r0 >> 1);
+                        a.crhs[cc] = (acc + s2) * 0.125;
+                        a.czero[cc] = 0.0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (POST == 3) block_atomic_max(nmax, a.nrm);
+}
