@@ -329,7 +329,7 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
 void mg_pick_fused(vdn_ctx *c, MG *m)
 {
     auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
-    const int fuse = envi("VDN_MG_FUSE", 2), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
+    const int fuse = envi("VDN_MG_FUSE", 4), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
     m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
     cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
     if (fuse <= 0 || c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
@@ -624,7 +624,11 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
     };
     for (int cfg = 0; cfg < (kind >= 2 ? SWEEP_NCFG : 2); ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
-        if (m->tile_force < 0 && kind >= 2 && cfg != 0) continue;       // measured (profiles/r01_bench_256_v3_*): the largest tile wins on every level
+        // measured defaults (profiles/r01_bench_256_v3_* / _v5_*): k_sweep / k_sweep2: the largest tile on every level; k_sweep3: 64x16 for
+        // the plain and prolongating sweeps, 32x16 for the variants with the residual stage (their 864-thread 64x16 CTA is capped at 72
+        // registers and spills)
+        if (m->tile_force < 0 && (kind == 2 || kind == 3) && cfg != 0) continue;
+        if (m->tile_force < 0 && kind == 4 && cfg != (post ? 2 : 1)) continue;
         const WaveVariant &v = variant(cfg);
         const long ntiles = (long)cdiv(L.n[0], v.TX) * cdiv(L.n[1], v.TY);
         const long slots = (long)m->sm_count * v.occ;
