@@ -28,6 +28,12 @@ module vdn_iso_c
      real(c_double) :: bc_val(2,3,5)     ! C bc_val[5][3][2]: (side, dir, {u,v,w,rho,trac})
   end type vdn_params
 
+  ! struct vdn_host_state (include/vdn.h): arrays of nboxes pointers, one per local fab (c_loc(dataptr(mf,i)))
+  type, bind(c) :: vdn_host_state
+     type(c_ptr) :: uold, sold, gp, ext_vel_force, ext_scal_force      ! in
+     type(c_ptr) :: unew, snew, rhohalf                                ! out
+  end type vdn_host_state
+
   interface
      subroutine vdn_params_default(p) bind(c, name='vdn_params_default')
        import :: vdn_params
@@ -73,6 +79,16 @@ module vdn_iso_c
        integer(c_int), intent(out) :: mac_cycles
        real(c_double), intent(out) :: mac_resnorm
      end function vdn_advance
+
+     ! the same pass from / to HOST multifabs, copies overlapped with the stages (include/vdn.h: vdn_advance_host)
+     integer(c_int) function vdn_advance_host(ctx, dt, mac_rel_eps, hs, mac_cycles, mac_resnorm) bind(c, name='vdn_advance_host')
+       import :: c_ptr, c_int, c_double, vdn_host_state
+       type(c_ptr), value :: ctx
+       real(c_double), value :: dt, mac_rel_eps
+       type(vdn_host_state), intent(in) :: hs
+       integer(c_int), intent(out) :: mac_cycles
+       real(c_double), intent(out) :: mac_resnorm
+     end function vdn_advance_host
 
      ! stage-wise entry points (same names as the reference procedures)
      integer(c_int) function vdn_mkvelforce(ctx, rho_field, visc_fac) bind(c, name='vdn_mkvelforce')
@@ -125,6 +141,7 @@ module vdn_path_module
   public :: vdn_advance_path, vdn_path_finalize
 
   type(c_ptr), save :: ctx = c_null_ptr      ! one context per MPI rank; rebuilt after regrid (call vdn_path_finalize)
+  type(c_ptr), allocatable, target, save :: fab_tab(:,:)   ! (local fab, multifab slot): host pointers handed to vdn_advance_host
 
 contains
 
@@ -176,6 +193,7 @@ contains
   subroutine vdn_path_finalize()
     if (c_associated(ctx)) call vdn_ctx_destroy(ctx)
     ctx = c_null_ptr
+    if (allocated(fab_tab)) deallocate(fab_tab)
   end subroutine vdn_path_finalize
 
   subroutine put(field, mf)
@@ -203,6 +221,21 @@ contains
     end do
   end subroutine get
 
+  ! c_ptr array of the local fabs of mf (slot = which of the eight multifabs of a step; storage lives in the module)
+  function fabptrs(mf, slot) result(p)
+    type(multifab), intent(in) :: mf
+    integer, intent(in) :: slot
+    type(c_ptr) :: p
+    real(dp_t), pointer :: q(:,:,:,:)
+    integer :: i
+    if (.not. allocated(fab_tab)) allocate(fab_tab(nfabs(mf), 8))
+    do i = 1, nfabs(mf)
+       q => dataptr(mf, i)
+       fab_tab(i, slot) = c_loc(q(lbound(q,1),lbound(q,2),lbound(q,3),1))
+    end do
+    p = c_loc(fab_tab(1, slot))
+  end function fabptrs
+
   ! Replaces advance_timestep.f90:95-124 for nlevs == 1 and visc_coef == diff_coef == 0.
   subroutine vdn_advance_path(mla,sold,uold,snew,unew,gp,ext_vel_force,ext_scal_force,rhohalf,umac,the_bc_tower,dt,dx)
     type(ml_layout), intent(in   ) :: mla
@@ -212,16 +245,19 @@ contains
     real(dp_t)     , intent(in   ) :: dt, dx(:,:)
     integer(c_int) :: ncyc
     real(c_double) :: res
+    type(vdn_host_state) :: hs
     integer :: d
 
     if (mla%nlevel /= 1) call bl_error('vdn_advance_path: single-level only')
     if (.not. c_associated(ctx)) call vdn_path_init(mla, sold, the_bc_tower, dx)
-    ! copies only at the path boundary (BASELINE.json north_star)
-    call put(VDN_UOLD, uold(1)); call put(VDN_SOLD, sold(1)); call put(VDN_GP, gp(1))
-    call put(VDN_EXT_VEL_FORCE, ext_vel_force(1)); call put(VDN_EXT_SCAL_FORCE, ext_scal_force(1))
-    call vdn_check(vdn_advance(ctx, real(dt,c_double), -1.0_c_double, ncyc, res))
-    call get(VDN_UNEW, unew(1), mla%dim); call get(VDN_SNEW, snew(1), ncomp(snew(1)))
-    call get(VDN_RHOHALF, rhohalf(1), 1)            ! only comp 1 is meaningful (advance_timestep.f90:70,114)
+    ! copies only at the path boundary (BASELINE.json north_star).  Sequential form:
+    !   put(uold, sold, gp, ext_vel_force, ext_scal_force); vdn_advance; get(unew, snew, rhohalf)
+    ! Pipelined form (default): one call that overlaps the copies with the stages.  fabptrs(mf) returns a
+    ! c_ptr array with c_loc(dataptr(mf,i)) for the local fabs (kept in module storage until the call returns).
+    hs%uold = fabptrs(uold(1), 1); hs%sold = fabptrs(sold(1), 2); hs%gp = fabptrs(gp(1), 3)
+    hs%ext_vel_force = fabptrs(ext_vel_force(1), 4); hs%ext_scal_force = fabptrs(ext_scal_force(1), 5)
+    hs%unew = fabptrs(unew(1), 6); hs%snew = fabptrs(snew(1), 7); hs%rhohalf = fabptrs(rhohalf(1), 8)
+    call vdn_check(vdn_advance_host(ctx, real(dt,c_double), -1.0_c_double, hs, ncyc, res))
     do d = 1, mla%dim
        call get(VDN_UMAC_X + int(d-1,c_int), umac(1,d), 1)     ! diagnostics only
     end do

@@ -57,10 +57,10 @@ def full(path, out):
 def family(kname, grid):
     """bench.py kernel-family name of a captured launch (level-0 launches of the 256^3 bench are the ones with the large grid)"""
     import re
-    m = re.search(r"k_(sweep2|sweep|wave)<([^>]*)>", kname)
+    m = re.search(r"k_(sweep3|sweep2|sweep|wave)<([^>]*)>", kname)
     if m:
         a = [x.strip() for x in m.group(2).split(",")]
-        pre, post = (int(a[0]), int(a[1])) if m.group(1) == "sweep2" else (int(a[1]), int(a[2]))
+        pre, post = (int(a[0]), int(a[1])) if m.group(1) in ("sweep2", "sweep3") else (int(a[1]), int(a[2]))
         return {2: "mg_wave_down_l0", 3: "mg_wave_up_l0"}.get(post, "mg_wave_pro_l0" if pre else "mg_wave_smooth_l0")
     for k, f in (("k_gsrb", "mg_gsrb_l0"), ("k_residual", "mg_residual_l0"), ("k_mf_normal3", "mf_normal3"), ("k_mf_trans6", "mf_trans6"),
                  ("k_mf_final3", "mf_final3"), ("k_vp_normal3", "vp_normal3"), ("k_vp_trans6", "vp_trans6"), ("k_vp_final3", "vp_final3"),

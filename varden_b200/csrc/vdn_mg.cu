@@ -516,7 +516,7 @@ WaveVariant sweep_variant()
     VDN_REQUIRE(v.occ >= 1, "k_sweep variant does not fit on an SM");
     return v;
 }
-constexpr int SWEEP_NCFG = 3;
+constexpr int SWEEP_NCFG = 5;
 WaveVariant &sweep_get(int cfg, int nsw, int pre, int post)
 {
     static WaveVariant tab[SWEEP_NCFG][2][2][3];
@@ -606,7 +606,7 @@ WaveVariant &sweep3_get(int cfg, int nsw, int pre, int post)
         if (pre == 1 && post == 2) v = sweep3_variant<1, 2, TX, TY>(); \
         if (pre == 1 && post == 3) v = sweep3_variant<1, 3, TX, TY>(); \
     }
-    SV3(0, 32, 32) SV3(1, 64, 16) SV3(2, 32, 16)
+    SV3(0, 32, 32) SV3(1, 64, 16) SV3(2, 32, 16) SV3(3, 64, 14) SV3(4, 32, 24)     // 3, 4: 640-thread CTAs (20 warps: 96 registers, no spills)
 #undef SV3
     VDN_REQUIRE(v.fn != nullptr, "no such k_sweep3 variant");
     return v;
