@@ -121,6 +121,12 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fd
 {
     Comm *cm = c->comm;
     if (!cm || ng == 0) return;
+    // the x -> y -> z cascade: the slab sent along d carries the ghost cells of the directions before it, so those directions must be
+    // complete (received AND unpacked) before the slab is packed -- one phase per direction, not one pack for all of them
+    if (grow_prev && (dmask & (dmask - 1)) != 0) {
+        for (int d = 0; d < dim; ++d) if ((dmask >> d) & 1) comm_halo(c, v, n, dim, ng, nc, fdir, 1 << d, true);
+        return;
+    }
     PackArgs ps; ps.v = v; ps.nc = nc; ps.nseg = 0; ps.unpack = 0;
     PackArgs pu = ps; pu.unpack = 1;
     struct Msg { int peer; long off, cnt; };

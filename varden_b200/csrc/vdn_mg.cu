@@ -624,11 +624,11 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
     };
     for (int cfg = 0; cfg < (kind >= 2 ? SWEEP_NCFG : 2); ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
-        // measured defaults (profiles/r01_bench_256_v3_* / _v5_*): k_sweep / k_sweep2: the largest tile on every level; k_sweep3: 64x16 for
-        // the plain and prolongating sweeps, 32x16 for the variants with the residual stage (their 864-thread 64x16 CTA is capped at 72
-        // registers and spills)
+        // measured defaults (profiles/r01_bench_256_v3_* / _v5_*): k_sweep / k_sweep2: the largest tile on every level; k_sweep3: 32x24 (640 threads,
+        // 96 registers) for the plain / prolongating sweeps of the finest level and for sweep + norm, 64x16 for the plain sweeps of smaller
+        // levels, 32x16 for sweep + residual + restriction (an 864-thread 64x16 CTA is capped at 72 registers and spills)
         if (m->tile_force < 0 && (kind == 2 || kind == 3) && cfg != 0) continue;
-        if (m->tile_force < 0 && kind == 4 && cfg != (post ? 2 : 1)) continue;
+        if (m->tile_force < 0 && kind == 4 && cfg != (post == 2 ? 2 : (post == 3 || L.n[0] >= 256) ? 4 : 1)) continue;
         const WaveVariant &v = variant(cfg);
         const long ntiles = (long)cdiv(L.n[0], v.TX) * cdiv(L.n[1], v.TY);
         const long slots = (long)m->sm_count * v.occ;
