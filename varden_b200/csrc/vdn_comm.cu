@@ -22,6 +22,7 @@ struct Comm {
     int nbr[3][2];                 // neighbour rank per (dir, side); -1 = none (physical boundary); == rank = periodic self
     int pgrid[3] = {1, 1, 1}, pcoord[3] = {0, 0, 0};
     std::vector<int> rlo, rhi;     // all regions [nranks][3]
+    std::vector<int> coord2rank;   // process-grid coordinates (x fastest) -> rank
     double *sbuf = nullptr, *rbuf = nullptr; size_t buf_doubles = 0;
     double *d_scal = nullptr;
 };
@@ -80,7 +81,7 @@ extern "C" int vdn_nccl_unique_id(void *out128)
 
 // ---- pack / unpack of up to 6 rectangular segments in one launch ----
 struct Seg { int lo[3], n[3]; long off; };
-struct PackArgs { View v; int nc; int nseg; Seg seg[6]; double *buf; int unpack; };
+struct PackArgs { View v; int nc; int nseg; Seg seg[26]; double *buf; int unpack; };
 __global__ void k_pack(PackArgs a)
 {
     const Seg &s = a.seg[blockIdx.y];
@@ -117,14 +118,15 @@ static void ensure_buf(vdn_ctx *c, size_t doubles)
 
 // Exchange along the directions in `dirs` (bit mask) of an array described by (v, n, ng, nc, fdir).
 // grow_prev: transverse range includes ghosts in directions < d (the x->y->z cascade that fills corners).
-void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fdir, int dmask, bool grow_prev)
+void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fdir, int dmask, bool grow_prev, bool incl_n, int dmask_all)
 {
+    if (dmask_all < 0) dmask_all = dmask;
     Comm *cm = c->comm;
     if (!cm || ng == 0) return;
     // the x -> y -> z cascade: the slab sent along d carries the ghost cells of the directions before it, so those directions must be
     // complete (received AND unpacked) before the slab is packed -- one phase per direction, not one pack for all of them
     if (grow_prev && (dmask & (dmask - 1)) != 0) {
-        for (int d = 0; d < dim; ++d) if ((dmask >> d) & 1) comm_halo(c, v, n, dim, ng, nc, fdir, 1 << d, true);
+        for (int d = 0; d < dim; ++d) if ((dmask >> d) & 1) comm_halo(c, v, n, dim, ng, nc, fdir, 1 << d, true, incl_n, dmask_all);
         return;
     }
     PackArgs ps; ps.v = v; ps.nc = nc; ps.nseg = 0; ps.unpack = 0;
@@ -139,7 +141,8 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fd
         for (int t = 0; t < 3; ++t) {
             if (t >= dim) { tlo[t] = 0; tn[t] = 1; continue; }
             const int ext = n[t] + (fdir == t ? 1 : 0);
-            if (grow_prev && t < d) { tlo[t] = -ng; tn[t] = ext + 2 * ng; } else { tlo[t] = 0; tn[t] = ext; }
+            if (grow_prev && t < d) { tlo[t] = -ng; tn[t] = ext + 2 * ng; }
+            else { tlo[t] = 0; tn[t] = ext + ((incl_n && t != d && !(((dmask_all >> t) & 1) && cm->pgrid[t] > 1)) ? 1 : 0); }
         }
         Msg rcv_of_side[2]; bool has[2] = { false, false };
         for (int s = 0; s < 2; ++s) {
@@ -162,6 +165,71 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fd
         if (has[1]) recvs.push_back(rcv_of_side[1]);
         if (has[0]) recvs.push_back(rcv_of_side[0]);
     }
+    if (ps.nseg == 0) return;
+    ensure_buf(c, (size_t)std::max(soff, roff));
+    ps.buf = cm->sbuf; pu.buf = cm->rbuf;
+    launch_pack(c, ps);
+    VDN_NCCL(ncclGroupStart());
+    for (const Msg &m : sends) VDN_NCCL(ncclSend(cm->sbuf + m.off, (size_t)m.cnt, ncclDouble, m.peer, cm->nccl, c->stream));
+    for (const Msg &m : recvs) VDN_NCCL(ncclRecv(cm->rbuf + m.off, (size_t)m.cnt, ncclDouble, m.peer, cm->nccl, c->stream));
+    VDN_NCCL(ncclGroupEnd());
+    launch_pack(c, pu);
+}
+
+// Ghost layers of depth ng of a cell-centred array in ONE phase: faces, edges and corners travel as separate messages to the
+// (up to 26) neighbour ranks of the process grid inside one NCCL group, bracketed by one pack and one unpack launch.  The
+// direction-by-direction cascade above needs one pack / group / unpack per split direction; the fused multigrid smoother
+// calls this once per launch, so the latency of a phase is what limits multi-GPU scaling.
+// Message matching: NCCL pairs the sends and receives of two ranks in issue order.  Every rank issues its sends in
+// lexicographic order of the offset vector o (neighbour = my coordinates + o) and its receives in the reverse order -- the
+// message a peer sent for its offset o' is the one I receive for my offset -o', and negation reverses the order -- so the
+// pairing also holds when one peer is my neighbour for several offsets (two ranks along a periodic direction).
+void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask)
+{
+    Comm *cm = c->comm;
+    if (!cm || ng == 0) return;
+    PackArgs ps; ps.v = v; ps.nc = 1; ps.nseg = 0; ps.unpack = 0;
+    PackArgs pu = ps; pu.unpack = 1;
+    struct Msg { int peer; long off, cnt; };
+    std::vector<Msg> sends, recvs;
+    long soff = 0, roff = 0;
+    auto peer_of = [&](const int *o) -> int {          // rank at my process-grid coordinates + o, or -1
+        int pc[3];
+        for (int d = 0; d < 3; ++d) {
+            pc[d] = cm->pcoord[d] + o[d];
+            if (o[d] == 0) continue;
+            if (pc[d] < 0 || pc[d] >= cm->pgrid[d]) {
+                if (c->dom_bc[d][0] != BC_PERIODIC) return -1;
+                pc[d] = (pc[d] + cm->pgrid[d]) % cm->pgrid[d];
+            }
+        }
+        return cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])];
+    };
+    int o[3];
+    for (int pass = 0; pass < 2; ++pass)                // pass 0: sends (lexicographic), pass 1: receives (reverse)
+        for (int q = 0; q < 27; ++q) {
+            const int qq = pass == 0 ? q : 26 - q;
+            o[0] = qq % 3 - 1; o[1] = (qq / 3) % 3 - 1; o[2] = qq / 9 - 1;       // z slowest: lexicographic in (z, y, x)
+            if (o[0] == 0 && o[1] == 0 && o[2] == 0) continue;
+            bool ok = true;
+            for (int d = 0; d < 3; ++d) if (o[d] != 0 && (d >= dim || !((dmask >> d) & 1) || cm->pgrid[d] == 1)) ok = false;
+            if (!ok) continue;
+            const int peer = peer_of(o);
+            if (peer < 0) continue;
+            Seg sg; long cnt = 1;
+            for (int d = 0; d < 3; ++d) {
+                if (d >= dim) { sg.lo[d] = 0; sg.n[d] = 1; continue; }
+                // along a direction that is not split the slab also carries index n: the level arrays keep the coefficient of the high
+                // boundary / periodic-seam face there, and the ghost planes are relaxed with it (split directions: index n is the first
+                // ghost cell and comes with the edge message)
+                if (o[d] == 0) { sg.lo[d] = 0; sg.n[d] = n[d] + ((((dmask >> d) & 1) && cm->pgrid[d] > 1) ? 0 : 1); }
+                else if (pass == 0) { sg.lo[d] = o[d] < 0 ? 0 : n[d] - ng; sg.n[d] = ng; }       // my cells next to that neighbour
+                else                { sg.lo[d] = o[d] < 0 ? -ng : n[d];    sg.n[d] = ng; }       // my ghost cells on that side
+                cnt *= sg.n[d];
+            }
+            if (pass == 0) { sg.off = soff; VDN_REQUIRE(ps.nseg < 26, "too many halo segments"); ps.seg[ps.nseg++] = sg; sends.push_back({ peer, soff, cnt }); soff += cnt; }
+            else           { sg.off = roff; pu.seg[pu.nseg++] = sg; recvs.push_back({ peer, roff, cnt }); roff += cnt; }
+        }
     if (ps.nseg == 0) return;
     ensure_buf(c, (size_t)std::max(soff, roff));
     ps.buf = cm->sbuf; pu.buf = cm->rbuf;
@@ -260,6 +328,9 @@ extern "C" int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *r
             }
             ctx->wrap[d] = ctx->dom_bc[d][0] == BC_PERIODIC && cm->nbr[d][0] == rank;
         }
+        cm->coord2rank.assign(nranks, -1);
+        for (int r = 0; r < nranks; ++r) { int pc[3]; comm_coord_of(ctx, r, pc); cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])] = r; }
+        for (int r = 0; r < nranks; ++r) VDN_REQUIRE(cm->coord2rank[r] >= 0, "process grid has holes");
         ctx_rebuild_bc(ctx);
         return 0;
     } catch (const std::exception &e) { ctx->err = e.what(); return 1; }
