@@ -215,20 +215,15 @@ struct VpArgs {
 };
 
 // normal predictor + Riemann/upwind: velpred.f90:2019-2099 (x), 2105-2185 (y), 2283-2367 (z); 2-D :258-322, :330-396
-// PRE: the limited slopes of the two cells next to the face are handed in (fused kernel: every cell's slope is evaluated
-// once and shared between the two faces that use it); otherwise they are evaluated here (INL) or read from a.sl (staged path)
-template <int DIM, int D, bool INL, bool PRE = false>
-__device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int k, const double *preL = nullptr, const double *preR = nullptr)
+template <int DIM, int D, bool INL>
+__device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int k)
 {
     const int ix[3] = { i, j, k };
     const double dt2 = HALF * a.dt, h = a.g.h[D];
     const int su = a.u.st(D);
     const double *uR = &a.u(i, j, k), *uL = uR - su;
     double slL[DIM], slR[DIM];
-    if (PRE) {
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) { slL[c] = preL[c]; slR[c] = preR[c]; }
-    } else if (INL) {
+    if (INL) {
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
             const bool bl = a.sbc[c][D][0] == BC_EXT_DIR || a.sbc[c][D][0] == BC_HOEXTRAP;
@@ -287,57 +282,13 @@ __global__ void k_vp_normal(VpArgs a)
     THREAD_IJK(a.r)
     vp_normal_pt<DIM, D, false>(a, i, j, k);
 }
-// slope of comp c of cell (i,j,k) along D, as the normal predictor evaluates it
-template <int D>
-__device__ __forceinline__ double vp_cell_slope(const VpArgs &a, int i, int j, int k, int c)
-{
-    const int ix[3] = { i, j, k };
-    const bool bl = a.sbc[c][D][0] == BC_EXT_DIR || a.sbc[c][D][0] == BC_HOEXTRAP;
-    const bool bh = a.sbc[c][D][1] == BC_EXT_DIR || a.sbc[c][D][1] == BC_HOEXTRAP;
-    return slope_at(&a.u(i, j, k, c), a.u.st(D), ix[D], a.g.n[D], bl, bh, a.order);
-}
-// all three directions, slopes in registers; a.r = cells -1..n in every direction, the D-face of a cell exists for ix[D] >= 0.
-// A limited slope is needed by two faces (as the right slope of the cell's low face and the left slope of its high face):
-// along x the neighbour is the previous lane (warp shuffle), along y the previous row of the CTA (shared memory); only lane 0
-// / row 0 evaluate the neighbour's slope themselves.  Same function, same inputs: bit-identical to evaluating both per face
-// (which is what the CPU emulation build and the z direction do).
+// all three directions, slopes in registers; a.r = cells -1..n in every direction, the D-face of a cell exists for ix[D] >= 0
 __global__ void __launch_bounds__(256) k_vp_normal3(VpArgs a)
 {
-#ifdef VDN_EMU
     THREAD_IJK(a.r)
     if (i >= 0) vp_normal_pt<3, 0, true>(a, i, j, k);
     if (j >= 0) vp_normal_pt<3, 1, true>(a, i, j, k);
     if (k >= 0) vp_normal_pt<3, 2, true>(a, i, j, k);
-#else
-    __shared__ double sy_[3][4][64];
-    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = a.r.lo[2] + blockIdx.z;
-    const bool in = i <= a.r.hi[0] && j <= a.r.hi[1];
-    double sx[3], sy[3], lx[3], ly[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        sx[c] = in ? vp_cell_slope<0>(a, i, j, k, c) : ZERO;
-        sy[c] = in ? vp_cell_slope<1>(a, i, j, k, c) : ZERO;
-        lx[c] = __shfl_up_sync(0xffffffffu, sx[c], 1);
-        sy_[c][threadIdx.y][threadIdx.x] = sy[c];
-    }
-    __syncthreads();
-    if (!in) return;
-    if (i >= 0) {
-        if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) lx[c] = vp_cell_slope<0>(a, i - 1, j, k, c);
-        }
-        vp_normal_pt<3, 0, true, true>(a, i, j, k, lx, sx);
-    }
-    if (j >= 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) ly[c] = threadIdx.y > 0 ? sy_[c][threadIdx.y - 1][threadIdx.x] : vp_cell_slope<1>(a, i, j - 1, k, c);
-        vp_normal_pt<3, 1, true, true>(a, i, j, k, ly, sy);
-    }
-    if (k >= 0) vp_normal_pt<3, 2, true>(a, i, j, k);
-#endif
 }
 
 // transverse-corrected tangential state of comp C = 3-D-T on D faces, corrected by T (3-D only):
@@ -466,15 +417,14 @@ struct MfArgs {
     int order; int sbc[3][2];       // slope order and adv_bc[d][side] of this comp for in-register slopes
 };
 // 1-D extrapolation + BC + upwind: mkflux.f90:1443-1524 (x), 1530-1611 (y), 1779-1864 (z)
-template <int D, bool INL, bool PRE = false>
-__device__ __forceinline__ void mf_normal_pt(const MfArgs &a, int i, int j, int k, double preL = 0.0, double preR = 0.0)
+template <int D, bool INL>
+__device__ __forceinline__ void mf_normal_pt(const MfArgs &a, int i, int j, int k)
 {
     const int ix[3] = { i, j, k };
     const double dt2 = HALF * a.dt, h = a.g.h[D];
     const double *sR = &a.s(i, j, k), *sL = sR - a.s.st(D);
     double pLv, pRv;
-    if (PRE) { pLv = preL; pRv = preR; }
-    else if (INL) {
+    if (INL) {
         const bool bl = a.sbc[D][0] == BC_EXT_DIR || a.sbc[D][0] == BC_HOEXTRAP;
         const bool bh = a.sbc[D][1] == BC_EXT_DIR || a.sbc[D][1] == BC_HOEXTRAP;
         pLv = slope_at(sL, a.s.st(D), ix[D] - 1, a.g.n[D], bl, bh, a.order);
@@ -506,44 +456,12 @@ __global__ void k_mf_normal(MfArgs a)
     THREAD_IJK(a.r)
     mf_normal_pt<D, false>(a, i, j, k);
 }
-template <int D>
-__device__ __forceinline__ double mf_cell_slope(const MfArgs &a, int i, int j, int k)
-{
-    const int ix[3] = { i, j, k };
-    const bool bl = a.sbc[D][0] == BC_EXT_DIR || a.sbc[D][0] == BC_HOEXTRAP;
-    const bool bh = a.sbc[D][1] == BC_EXT_DIR || a.sbc[D][1] == BC_HOEXTRAP;
-    return slope_at(&a.s(i, j, k), a.s.st(D), ix[D], a.g.n[D], bl, bh, a.order);
-}
-// slopes shared between the two faces of a cell as in k_vp_normal3 (x: warp shuffle, y: shared memory)
 __global__ void __launch_bounds__(256) k_mf_normal3(MfArgs a)      // a.r = -1..n in every direction
 {
-#ifdef VDN_EMU
     THREAD_IJK(a.r)
     if (i >= 0) mf_normal_pt<0, true>(a, i, j, k);
     if (j >= 0) mf_normal_pt<1, true>(a, i, j, k);
     if (k >= 0) mf_normal_pt<2, true>(a, i, j, k);
-#else
-    __shared__ double sy_[4][64];
-    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = a.r.lo[2] + blockIdx.z;
-    const bool in = i <= a.r.hi[0] && j <= a.r.hi[1];
-    const double sx = in ? mf_cell_slope<0>(a, i, j, k) : ZERO;
-    const double sy = in ? mf_cell_slope<1>(a, i, j, k) : ZERO;
-    double lx = __shfl_up_sync(0xffffffffu, sx, 1);
-    sy_[threadIdx.y][threadIdx.x] = sy;
-    __syncthreads();
-    if (!in) return;
-    if (i >= 0) {
-        if ((threadIdx.x & 31) == 0) lx = mf_cell_slope<0>(a, i - 1, j, k);
-        mf_normal_pt<0, true, true>(a, i, j, k, lx, sx);
-    }
-    if (j >= 0) {
-        const double ly = threadIdx.y > 0 ? sy_[threadIdx.y - 1][threadIdx.x] : mf_cell_slope<1>(a, i, j - 1, k);
-        mf_normal_pt<1, true, true>(a, i, j, k, ly, sy);
-    }
-    if (k >= 0) mf_normal_pt<2, true>(a, i, j, k);
-#endif
 }
 
 // transverse-once states: simhxy :1617, simhyx :1697, simhzx :1978, simhzy :2062, simhxz :2150, simhyz :2230
