@@ -99,6 +99,12 @@ int vdn_nccl_unique_id(void *out128);
 int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo, const int *region_hi,
                   const int *dom_lo, const int *dom_hi, const int *phys_bc, int *nbr, int *pgrid, int *pcoord);
 
+/* host-only: message plan of the single-phase ghost-layer exchange of the multigrid level arrays (faces, edges and corners to the
+ * up-to-26 neighbour ranks in one NCCL group).  Arrays hold up to 26 entries; *_lo / *_n are [entry][3] local index boxes.  Entries are
+ * in issue order: NCCL matches the messages of a pair of ranks first-in first-out.  Returns 1 if more than 26 messages would be needed. */
+int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng, int dmask,
+                  int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n);
+
 /* Path-boundary copies (SURVEY 8(b) "Copies"): host box array <-> region array, ghosts included
  * where they lie outside the region's valid area.  `host` has `ng` ghosts and `ncomp` comps and
  * must match the field's fixed (ng, ncomp). */

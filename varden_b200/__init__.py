@@ -24,7 +24,7 @@ F = {name: i for i, name in enumerate(FIELDS)}
 
 ABI_SYMBOLS = [
     "vdn_params_default", "vdn_ctx_create", "vdn_ctx_destroy", "vdn_last_error", "vdn_ctx_set_comm",
-    "vdn_nccl_unique_id", "vdn_comm_plan",
+    "vdn_nccl_unique_id", "vdn_comm_plan", "vdn_halo_plan",
     "vdn_field_upload", "vdn_field_download", "vdn_field_setval", "vdn_sync", "vdn_get_stream",
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",

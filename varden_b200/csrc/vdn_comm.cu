@@ -48,10 +48,8 @@ extern "C" int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo
         const bool per = phys_bc[d * 2] == BC_PERIODIC;
         for (int s = 0; s < 2; ++s) {
             int want;                               // the lower (s=1) / upper (s=0) bound the neighbour must have along d
-            bool wrapd = false;
-            if (s == 1) { want = mhi[d] + 1; if (mhi[d] == dom_hi[d]) { if (!per) continue; want = dom_lo[d]; wrapd = true; } }
-            else        { want = mlo[d] - 1; if (mlo[d] == dom_lo[d]) { if (!per) continue; want = dom_hi[d]; wrapd = true; } }
-            (void)wrapd;
+            if (s == 1) { want = mhi[d] + 1; if (mhi[d] == dom_hi[d]) { if (!per) continue; want = dom_lo[d]; } }
+            else        { want = mlo[d] - 1; if (mlo[d] == dom_lo[d]) { if (!per) continue; want = dom_hi[d]; } }
             int found = -1;
             for (int r = 0; r < nranks; ++r) {
                 bool same = true;
@@ -184,26 +182,26 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fd
 // lexicographic order of the offset vector o (neighbour = my coordinates + o) and its receives in the reverse order -- the
 // message a peer sent for its offset o' is the one I receive for my offset -o', and negation reverses the order -- so the
 // pairing also holds when one peer is my neighbour for several offsets (two ranks along a periodic direction).
-void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask)
+// host-only message plan of the single-phase exchange (testable without a GPU: tests/test_halo_plan.py).
+//   pgrid / pcoord: process grid and this rank's coordinates; periodic[d]: the domain is periodic along d;
+//   coord2rank[x + pgrid[0]*(y + pgrid[1]*z)]: rank at those coordinates; n: local cells; dmask: split directions of the array.
+// Outputs (up to 26 entries each): peer rank and the inclusive-lo / extent boxes (local indices) of what is sent and of the ghost
+// region that is received, in ISSUE order (sends lexicographic in the neighbour offset, receives in the reverse order).
+extern "C" int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng, int dmask,
+                             int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n)
 {
-    Comm *cm = c->comm;
-    if (!cm || ng == 0) return;
-    PackArgs ps; ps.v = v; ps.nc = 1; ps.nseg = 0; ps.unpack = 0;
-    PackArgs pu = ps; pu.unpack = 1;
-    struct Msg { int peer; long off, cnt; };
-    std::vector<Msg> sends, recvs;
-    long soff = 0, roff = 0;
+    *nsend = 0; *nrecv = 0;
     auto peer_of = [&](const int *o) -> int {          // rank at my process-grid coordinates + o, or -1
         int pc[3];
         for (int d = 0; d < 3; ++d) {
-            pc[d] = cm->pcoord[d] + o[d];
+            pc[d] = pcoord[d] + o[d];
             if (o[d] == 0) continue;
-            if (pc[d] < 0 || pc[d] >= cm->pgrid[d]) {
-                if (c->dom_bc[d][0] != BC_PERIODIC) return -1;
-                pc[d] = (pc[d] + cm->pgrid[d]) % cm->pgrid[d];
+            if (pc[d] < 0 || pc[d] >= pgrid[d]) {
+                if (!periodic[d]) return -1;
+                pc[d] = (pc[d] + pgrid[d]) % pgrid[d];
             }
         }
-        return cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])];
+        return coord2rank[pc[0] + pgrid[0] * (pc[1] + pgrid[1] * pc[2])];
     };
     int o[3];
     for (int pass = 0; pass < 2; ++pass)                // pass 0: sends (lexicographic), pass 1: receives (reverse)
@@ -212,25 +210,54 @@ void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask
             o[0] = qq % 3 - 1; o[1] = (qq / 3) % 3 - 1; o[2] = qq / 9 - 1;       // z slowest: lexicographic in (z, y, x)
             if (o[0] == 0 && o[1] == 0 && o[2] == 0) continue;
             bool ok = true;
-            for (int d = 0; d < 3; ++d) if (o[d] != 0 && (d >= dim || !((dmask >> d) & 1) || cm->pgrid[d] == 1)) ok = false;
+            for (int d = 0; d < 3; ++d) if (o[d] != 0 && (d >= dim || !((dmask >> d) & 1) || pgrid[d] == 1)) ok = false;
             if (!ok) continue;
             const int peer = peer_of(o);
             if (peer < 0) continue;
-            Seg sg; long cnt = 1;
+            int lo[3], ext[3];
             for (int d = 0; d < 3; ++d) {
-                if (d >= dim) { sg.lo[d] = 0; sg.n[d] = 1; continue; }
+                if (d >= dim) { lo[d] = 0; ext[d] = 1; continue; }
                 // along a direction that is not split the slab also carries index n: the level arrays keep the coefficient of the high
                 // boundary / periodic-seam face there, and the ghost planes are relaxed with it (split directions: index n is the first
                 // ghost cell and comes with the edge message)
-                if (o[d] == 0) { sg.lo[d] = 0; sg.n[d] = n[d] + ((((dmask >> d) & 1) && cm->pgrid[d] > 1) ? 0 : 1); }
-                else if (pass == 0) { sg.lo[d] = o[d] < 0 ? 0 : n[d] - ng; sg.n[d] = ng; }       // my cells next to that neighbour
-                else                { sg.lo[d] = o[d] < 0 ? -ng : n[d];    sg.n[d] = ng; }       // my ghost cells on that side
-                cnt *= sg.n[d];
+                if (o[d] == 0) { lo[d] = 0; ext[d] = n[d] + ((((dmask >> d) & 1) && pgrid[d] > 1) ? 0 : 1); }
+                else if (pass == 0) { lo[d] = o[d] < 0 ? 0 : n[d] - ng; ext[d] = ng; }       // my cells next to that neighbour
+                else                { lo[d] = o[d] < 0 ? -ng : n[d];    ext[d] = ng; }       // my ghost cells on that side
             }
-            if (pass == 0) { sg.off = soff; VDN_REQUIRE(ps.nseg < 26, "too many halo segments"); ps.seg[ps.nseg++] = sg; sends.push_back({ peer, soff, cnt }); soff += cnt; }
-            else           { sg.off = roff; pu.seg[pu.nseg++] = sg; recvs.push_back({ peer, roff, cnt }); roff += cnt; }
+            int &cnt = pass == 0 ? *nsend : *nrecv;
+            if (cnt >= 26) return 1;
+            int *pp = pass == 0 ? send_peer : recv_peer, *pl = pass == 0 ? send_lo : recv_lo, *pn = pass == 0 ? send_n : recv_n;
+            pp[cnt] = peer;
+            for (int d = 0; d < 3; ++d) { pl[3 * cnt + d] = lo[d]; pn[3 * cnt + d] = ext[d]; }
+            ++cnt;
         }
-    if (ps.nseg == 0) return;
+    return 0;
+}
+
+void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask)
+{
+    Comm *cm = c->comm;
+    if (!cm || ng == 0) return;
+    int ns = 0, nr = 0, speer[26], rpeer[26], slo[78], sn[78], rlo[78], rn[78], per[3];
+    for (int d = 0; d < 3; ++d) per[d] = c->dom_bc[d][0] == BC_PERIODIC ? 1 : 0;
+    VDN_REQUIRE(vdn_halo_plan(dim, cm->pgrid, cm->pcoord, per, cm->coord2rank.data(), n, ng, dmask, &ns, speer, slo, sn, &nr, rpeer, rlo, rn) == 0,
+                "too many halo segments");
+    if (ns == 0 && nr == 0) return;
+    PackArgs ps; ps.v = v; ps.nc = 1; ps.nseg = 0; ps.unpack = 0;
+    PackArgs pu = ps; pu.unpack = 1;
+    struct Msg { int peer; long off, cnt; };
+    std::vector<Msg> sends, recvs;
+    long soff = 0, roff = 0;
+    for (int q = 0; q < ns; ++q) {
+        Seg sg; long cnt = 1;
+        for (int d = 0; d < 3; ++d) { sg.lo[d] = slo[3 * q + d]; sg.n[d] = sn[3 * q + d]; cnt *= sg.n[d]; }
+        sg.off = soff; ps.seg[ps.nseg++] = sg; sends.push_back({ speer[q], soff, cnt }); soff += cnt;
+    }
+    for (int q = 0; q < nr; ++q) {
+        Seg sg; long cnt = 1;
+        for (int d = 0; d < 3; ++d) { sg.lo[d] = rlo[3 * q + d]; sg.n[d] = rn[3 * q + d]; cnt *= sg.n[d]; }
+        sg.off = roff; pu.seg[pu.nseg++] = sg; recvs.push_back({ rpeer[q], roff, cnt }); roff += cnt;
+    }
     ensure_buf(c, (size_t)std::max(soff, roff));
     ps.buf = cm->sbuf; pu.buf = cm->rbuf;
     launch_pack(c, ps);
