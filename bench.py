@@ -83,18 +83,20 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(n_sample, ratio, steps=1):
-    """time the CPU oracle (OpenMP C restatement) on a bounded sample: the same problem at n_sample^3"""
-    from oracle import oracle as O
-    geom, P, st, dt = O.rt_state(n_sample, dim=3, max_grid_size=256, ratio=ratio)
-    O.advance(geom, P, st, dt)         # warm (page-in, thread pool)
-    t0 = time.perf_counter()
-    cyc = 0
-    for _ in range(steps):
-        out = O.advance(geom, P, st, dt)
-        cyc = out["mac_cycles"]
-    t = time.perf_counter() - t0
-    return geom.ncells * steps / t / 1e9, t, cyc
+class CpuOracle:
+    """the CPU oracle (C/OpenMP restatement of the reference loops, all host cores) on a bounded sample: the same RT problem at n_sample^3"""
+
+    def __init__(self, n_sample, ratio):
+        from oracle import oracle as O
+        self.O = O
+        self.geom, self.P, self.st, self.dt = O.rt_state(n_sample, dim=3, max_grid_size=256, ratio=ratio)
+        self.cycles = 0
+
+    def step(self):
+        t0 = time.perf_counter()
+        out = self.O.advance(self.geom, self.P, self.st, self.dt)
+        self.cycles = out["mac_cycles"]
+        return time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -104,15 +106,13 @@ def run_reference(args):
     cores = os.cpu_count()
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     ns = args.cpu_n
-    vals = []
-    for _ in range(args.warmup):
-        cpu_oracle_rate(ns, args.ratio, 1) if False else None     # the oracle call itself does one warm pass
-    t_tot = 0.0
-    for _ in range(args.steps):
-        v, t, cyc = cpu_oracle_rate(ns, args.ratio, 1)
-        vals.append(v); t_tot += t
-    value = float(np.mean(vals))
-    sample = "same RT problem at %d^3 (one pass per step), %d V-cycles" % (ns, cyc)
+    cpu = CpuOracle(ns, args.ratio)
+    for _ in range(max(args.warmup, 1)):
+        cpu.step()                                  # untimed: page-in, thread pool
+    times = [cpu.step() for _ in range(args.steps)]
+    t_tot = sum(times)
+    value = cpu.geom.ncells * args.steps / t_tot / 1e9
+    sample = "same RT problem at %d^3 (one pass per step, %.1f s each), %d V-cycles" % (ns, t_tot / max(args.steps, 1), cpu.cycles)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=256, help="cells per direction of the N=1 workload")
     ap.add_argument("--ratio", type=float, default=2.0)
-    ap.add_argument("--cpu-n", type=int, default=96, help="grid size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=192, help="grid size of the bounded CPU sample (192^3: a few seconds per pass on the box's host cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-grid-size", type=int, default=256)
@@ -313,10 +313,12 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
-        v, t, ccyc = cpu_oracle_rate(args.cpu_n, args.ratio, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        co = CpuOracle(args.cpu_n, args.ratio)
+        co.step()                                   # untimed: page-in, thread pool
+        t = co.step()
+        cpu = {"value": co.geom.ncells / t / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": "same RT problem at %d^3, one pass (%.1f s, %d V-cycles); C/OpenMP restatement of the reference loops, not the Fortran binary"
-                         % (args.cpu_n, t, ccyc)}
+                         % (args.cpu_n, t, co.cycles)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
