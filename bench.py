@@ -135,6 +135,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-grid-size", type=int, default=256)
+    ap.add_argument("--global-n", type=int, default=0,
+                    help="STRONG scaling (BASELINE config 3): a fixed global grid of this many cells per direction, chopped into --n^3 reference "
+                         "boxes that are divided among the GPUs (512: 8 boxes of 256^3 -> 8/4/2/1 boxes per GPU at 1/2/4/8 GPUs); default 0 = weak "
+                         "scaling, one --n^3 box per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -165,13 +169,19 @@ def main():
     if pgrid is None:
         raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
     nglob = [n * pgrid[d] for d in range(3)]
+    scaling = "weak"
+    if args.global_n:
+        if args.global_n % n != 0 or any((args.global_n // n) % pgrid[d] for d in range(3)):
+            raise SystemExit("bench.py: --global-n must be a multiple of --n that the process grid %s divides" % pgrid)
+        nglob, scaling = [args.global_n] * 3, "strong"
+    phi = [float(nglob[d]) / n for d in range(3)]            # domain [0, nglob/n]^3: dx = 1/n in every configuration
     mgs = min(args.max_grid_size, n)
     from varden_b200.problems import Geom, PERIODIC, NO_SLIP_WALL
     from varden_b200 import parallel as PAR
     gfull = Geom(3, nglob, [[PERIODIC, PERIODIC], [PERIODIC, PERIODIC], [NO_SLIP_WALL, NO_SLIP_WALL]],
-                 prob_hi=[float(p) for p in pgrid], max_grid_size=mgs)
+                 prob_hi=phi, max_grid_size=mgs)
     ids, rlo, rhi, pg = PAR.partition(gfull, world)
-    geom, st, dt = rt_problem(nglob, dim=3, max_grid_size=mgs, ratio=args.ratio, prob_hi=[float(p) for p in pgrid], box_ids=ids[rank])
+    geom, st, dt = rt_problem(nglob, dim=3, max_grid_size=mgs, ratio=args.ratio, prob_hi=phi, box_ids=ids[rank])
     ncells_global = gfull.ncells
     dim, nscal = 3, 2
     prm = V.default_params()
@@ -321,9 +331,9 @@ def main():
                          % (args.cpu_n, t, co.cycles)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3D %d^3 single-level variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, "
-                                   "MAC rel tol 1e-10, %d^3 box per GPU, global %dx%dx%d" % (n, args.ratio, n, nglob[0], nglob[1], nglob[2]),
+                                   "MAC rel tol 1e-10, %d reference box(es) of %d^3 per GPU, global %dx%dx%d" % (n, args.ratio, geom.nboxes, n, nglob[0], nglob[1], nglob[2]),
                        "parallelism": "1 region per GPU, process grid %s, NCCL halo + allreduce, coarse MG levels agglomerated" % pgrid if world > 1 else "single GPU",
                        "l2_policy": "inputs (%.1f GB of fields) exceed the 126 MB L2; no explicit flush" % (45 * 8 * (n + 6) ** 3 / 1e9),
                        "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
