@@ -435,13 +435,12 @@ void mg_halo_deep(vdn_ctx *c, MG *m, Lev &L, double *x, int ng)
     int dmask = 0;
     for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
     LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
-    // One phase (faces + edges + corners in one NCCL group; 4 GPUs: 7.8 instead of 11.2 ms of exchanges per step) where it has run on
-    // hardware -- one or two split directions (2 and 4 GPUs); three split directions (8 GPUs, corner messages) keep the direction-by-
-    // direction cascade until they have been verified on 8 GPUs (the message plan is checked by emulation for 2x2x2).
-    // VDN_HALO_ONEPHASE=0/1 overrides.
+    // One phase (faces + edges + corners in one NCCL group; 4 GPUs: 7.8 instead of 11.2 ms of exchanges per step).  Run on hardware with
+    // one and two split directions (2 and 4 GPUs); the message plan for three split directions (8 GPUs, corner messages) is checked on the
+    // CPU by tests/test_halo_plan.py (vdn_halo_plan is the function executed here).  VDN_HALO_ONEPHASE=0 selects the direction-by-direction
+    // cascade (one pack / NCCL group / unpack per split direction).
     static const char *env = getenv("VDN_HALO_ONEPHASE");
-    const int nsplit = (dmask & 1) + ((dmask >> 1) & 1) + ((dmask >> 2) & 1);
-    const bool onephase = env ? atoi(env) != 0 : nsplit <= 2;
+    const bool onephase = env ? atoi(env) != 0 : true;
     if (onephase) comm_halo_deep(c, v, L.n, m->dim, ng, dmask);
     else comm_halo(c, v, L.n, m->dim, ng, 1, -1, dmask, true, true);
 }
