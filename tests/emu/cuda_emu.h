@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <memory>
 
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 inline thread_local dim3 threadIdx, blockIdx;
@@ -53,6 +54,50 @@ void emu_launch(Kernel k, dim3 grid, int nthreads, const Args &a)
         th.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t)
             th.emplace_back([&, t]() { threadIdx = dim3(t); blockIdx = dim3(bx, by, bz); k(a); });
+        for (auto &x : th) x.join();
+    }
+}
+
+// ---- 2-D thread blocks with dynamic shared memory and warp shuffles (the plane-marching Godunov kernels) ----
+// A warp = 32 consecutive linear thread ids; a shuffle is a rendezvous of the warp's threads on a per-warp barrier.
+inline void *emu_smem = nullptr;
+inline std::vector<std::barrier<> *> emu_warp_bar;
+inline std::vector<double> emu_shfl_buf;
+inline thread_local int emu_tid = 0;
+inline double emu_shfl(double v, int delta)
+{
+    const int lane = emu_tid & 31, base = emu_tid - lane, src = lane + delta;
+    emu_shfl_buf[emu_tid] = v;
+    emu_warp_bar[emu_tid >> 5]->arrive_and_wait();
+    const double r = (src < 0 || src > 31) ? v : emu_shfl_buf[base + src];
+    emu_warp_bar[emu_tid >> 5]->arrive_and_wait();
+    return r;
+}
+inline double __shfl_up_sync(unsigned, double v, int d) { return emu_shfl(v, -d); }
+inline double __shfl_down_sync(unsigned, double v, int d) { return emu_shfl(v, d); }
+
+template <class Kernel, class Args>
+void emu_launch2(Kernel k, dim3 grid, dim3 block, size_t smem_bytes, const Args &a)
+{
+    const int nthreads = block.x * block.y * block.z;
+    blockDim = block; gridDim = grid;
+    std::vector<char> sm(smem_bytes + 64);
+    emu_smem = sm.data();
+    emu_shfl_buf.assign(nthreads, 0.0);
+    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::barrier<> bar(nthreads);
+        emu_barrier = &bar;
+        std::vector<std::unique_ptr<std::barrier<>>> wb;
+        emu_warp_bar.clear();
+        for (int w = 0; w < (nthreads + 31) / 32; ++w) { wb.emplace_back(new std::barrier<>(std::min(32, nthreads - 32 * w))); emu_warp_bar.push_back(wb.back().get()); }
+        std::vector<std::thread> th;
+        th.reserve(nthreads);
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                emu_tid = t;
+                threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y)); blockIdx = dim3(bx, by, bz);
+                k(a);
+            });
         for (auto &x : th) x.join();
     }
 }

@@ -4,6 +4,7 @@
 #include "cuda_emu.h"
 #include "../../varden_b200/csrc/vdn_common.cuh"
 #include "../../varden_b200/csrc/vdn_godunov_kernels.cuh"
+#include "../../varden_b200/csrc/vdn_godunov_march.cuh"
 
 namespace {
 struct NoScope { };
@@ -27,6 +28,11 @@ Geo mkgeo(const int *n, const int *pbc, const double *h)
     for (int d = 0; d < 3; ++d) { g.n[d] = n[d]; g.h[d] = h[d]; g.pbc[d][0] = pbc[2 * d]; g.pbc[d][1] = pbc[2 * d + 1]; g.nb[d] = 1; g.cut[d][0] = 0; g.cut[d][1] = n[d]; }
     return g;
 }
+// launcher of the plane-marching kernels: one OS thread per CUDA thread, warp shuffles and shared memory emulated
+struct MarchLauncher {
+    NoScope scope(const char *, double, int) { return NoScope(); }
+    template <class A> void run(void (*k)(A), dim3 grid, dim3 block, size_t smem, const A &a) { emu_launch2(k, grid, block, smem, a); }
+};
 struct Scratch {
     std::vector<double> buf; long sn, sy, sz, off;
     Scratch(const int *n, int nslots) {
@@ -74,5 +80,38 @@ extern "C" int emu_mkflux(int fused, const int *n, const int *pbc, const int *sb
     }
     EmuLauncher L;
     mkflux_stages<3>(L, a, fused != 0);
+    return 0;
+}
+
+// plane-marching mkflux: all ncomp components of s (ng 3), force (ng 1), sedge (ng 0, ncomp comps), flux (ng 0, comp 0 only);
+// adv_bc: [ncomp][3 dirs][2 sides]; slots = resident-CTA count the z-chunking is planned for
+extern "C" int emu_mkflux_march(const int *n, const int *pbc, const int *adv_bc, int order, int use_minion, int is_vel, int ncomp,
+                                double dt, const double *h, double eps, int slots, double *s, double *mac0, double *mac1, double *mac2, double *force,
+                                double *sedge0, double *sedge1, double *sedge2, double *flux0, double *flux1, double *flux2)
+{
+    Geo g = mkgeo(n, pbc, h);
+    View sv = mkview(s, n, 3, -1), fv = mkview(force, n, 1, -1);
+    double *mac[3] = { mac0, mac1, mac2 }, *se[3] = { sedge0, sedge1, sedge2 }, *fl[3] = { flux0, flux1, flux2 };
+    View mv[3], ev[3], xv[3];
+    for (int d = 0; d < 3; ++d) { mv[d] = mkview(mac[d], n, 1, d); ev[d] = mkview(se[d], n, 0, d); xv[d] = mkview(fl[d], n, 0, d); }
+    int bc[8][3][2];
+    for (int c = 0; c < ncomp; ++c) for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) bc[c][d][sd] = adv_bc[(c * 3 + d) * 2 + sd];
+    MarchLauncher L;
+    march::mkflux_march(L, g, sv, fv, mv, ev, xv, &eps, dt, is_vel, ncomp, order, use_minion, bc, slots);
+    return 0;
+}
+
+extern "C" int emu_velpred_march(const int *n, const int *pbc, const int *adv_bc, int order, int use_minion, double dt, const double *h,
+                                 double eps, int slots, double *u, double *force, double *umac0, double *umac1, double *umac2)
+{
+    Geo g = mkgeo(n, pbc, h);
+    View uv = mkview(u, n, 3, -1), fv = mkview(force, n, 1, -1);
+    double *um[3] = { umac0, umac1, umac2 };
+    View ov[3];
+    for (int d = 0; d < 3; ++d) ov[d] = mkview(um[d], n, 1, d);
+    int bc[3][3][2];
+    for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) bc[c][d][sd] = adv_bc[(c * 3 + d) * 2 + sd];
+    MarchLauncher L;
+    march::velpred_march(L, g, uv, fv, ov, &eps, dt, order, use_minion, bc, slots);
     return 0;
 }
