@@ -154,6 +154,10 @@ int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, do
 typedef struct vdn_host_state {
     const double *const *uold, *const *sold, *const *gp, *const *ext_vel_force, *const *ext_scal_force;   /* in  */
     double *const *unew, *const *snew, *const *rhohalf;                                                    /* out */
+    /* optional inputs, NULL when absent: lapu (ng 0, dm comps) = the explicit viscous term the reference computes before the path
+     * (get_explicit_diffusive_term, advance_timestep.f90:84-88; REQUIRED when visc_coef > 0), mac_rhs (ng 1, 1 comp; advance_timestep.f90:66,
+     * zero in VARDEN unless a divergence constraint is set) */
+    const double *const *lapu, *const *mac_rhs;
 } vdn_host_state;
 int vdn_advance_host(vdn_ctx *ctx, double dt, double mac_rel_eps, const vdn_host_state *hs, int *mac_cycles, double *mac_resnorm);
 
@@ -162,6 +166,11 @@ int vdn_divumac(vdn_ctx *ctx, double *rhmax);     /* RH = MAC_RHS - div(UMAC), m
 int vdn_mk_mac_coeffs(vdn_ctx *ctx);              /* BETA_* from SOLD comp 1, macproject.f90:280 */
 int vdn_mac_solve(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, double *resnorm); /* mac_multigrid.f90:19 */
 int vdn_mkumac(vdn_ctx *ctx);                     /* macproject.f90:403 */
+
+/* test hook: smallest level size (cells per direction) the fused smoother runs on (default 128; the parity tests lower it so that small
+ * grids exercise the production kernel) and a forced tile shape of it (-1 = the measured default per launch kind).  Drops the cached
+ * multigrid hierarchy; takes effect at the next solve. */
+int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile);
 
 /* ---- measurement: per-kernel-family CUDA-event timing on the launching stream ---- */
 int vdn_prof_enable(vdn_ctx *ctx, int on);        /* resets counters */

@@ -32,6 +32,7 @@ Geo mkgeo(const int *n, const int *pbc, const double *h)
 struct MarchLauncher {
     NoScope scope(const char *, double, int) { return NoScope(); }
     template <class A> void run(void (*k)(A), dim3 grid, dim3 block, size_t smem, const A &a) { emu_launch2(k, grid, block, smem, a); }
+    template <class A> int slots(void (*)(A), int, size_t) { return 1; }
 };
 struct Scratch {
     std::vector<double> buf; long sn, sy, sz, off;
@@ -58,7 +59,7 @@ extern "C" int emu_velpred(int fused, const int *n, const int *pbc, const int *a
         for (int t = 0; t < 3; ++t) a.X[d][t] = sc.S(0 + d * 3 + t);
     }
     EmuLauncher L;
-    velpred_stages<3>(L, a, fused != 0);
+    velpred_stages<3>(L, a);
     return 0;
 }
 
@@ -79,7 +80,7 @@ extern "C" int emu_mkflux(int fused, const int *n, const int *pbc, const int *sb
         a.sedge[d] = mkview(se[d], n, 0, d); a.flux[d] = mkview(fl[d], n, 0, d);
     }
     EmuLauncher L;
-    mkflux_stages<3>(L, a, fused != 0);
+    mkflux_stages<3>(L, a);
     return 0;
 }
 

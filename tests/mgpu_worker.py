@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--case", default="rt3d")
     ap.add_argument("--size", dest="n", type=int, default=64)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--fuse-min", type=int, default=128, help="smallest level the fused smoother runs on (16 forces it onto these small grids)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -50,6 +51,7 @@ def main():
     prm = V.default_params(nscal=nscal, bc_val=P.bcval)
     ctx = V.Context(dim, sub.boxes, geom.dlo, geom.dhi, geom.phys_bc, geom.dx, params=prm, device=local)
     PAR.init_comm(ctx, rank, world, rlo, rhi)
+    ctx.mg_tune(args.fuse_min, -1)
     pick = lambda mf: [mf[i] for i in mine]
     ctx.upload_mf("UOLD", pick(st["uold"]), 3, dim)
     ctx.upload_mf("SOLD", pick(st["sold"]), 3, nscal)

@@ -1,5 +1,5 @@
 """
-CPU execution of the REAL k_wave kernel source (varden_b200/csrc/vdn_mg_wave.cuh) under tests/emu/cuda_emu.h
+CPU execution of the REAL k_sweep3 kernel source (varden_b200/csrc/vdn_mg_fused.cuh), in the PRODUCTION tile shapes, under tests/emu/cuda_emu.h
 (one OS thread per CUDA thread, std::barrier for __syncthreads), checked against a plain numpy red-black
 Gauss-Seidel / residual / restriction / prolongation of the same operator (mac_multigrid.f90:53-62 selects these).
 """
@@ -20,10 +20,7 @@ PAD = 4          # MG_PAD in vdn_ctx.h
 def emu():
     so = os.path.join(EMU, "libemu_wave.so")
     src = [os.path.join(EMU, "emu_wave.cpp"), os.path.join(EMU, "cuda_emu.h"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_wave.cuh"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep.cuh"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep2.cuh"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_sweep3.cuh")]
+           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_fused.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
                                src[0], "-o", so])
@@ -83,18 +80,19 @@ def gsrb(phi, rhs, b, h2, mode, n, par0, sweeps):
 
 
 CASES = [
-    # n, cfg, zchunk, mode, par0
-    ((64, 32, 16), 1, 8, ((M_WRAP, M_WRAP), (M_WRAP, M_WRAP), (M_NEU, M_NEU)), 0),
-    ((64, 32, 16), 0, 16, ((M_NEU, M_DIR), (M_DIR, M_NEU), (M_NEU, M_NEU)), 1),
+    # n, cfg (tile shape: 0 32x32, 1 64x16, 2 32x16, 3 64x14, 4 32x24, 5 16x8), zchunk, mode, par0
+    ((64, 32, 16), 2, 8, ((M_WRAP, M_WRAP), (M_WRAP, M_WRAP), (M_NEU, M_NEU)), 0),
+    ((64, 32, 16), 5, 16, ((M_NEU, M_DIR), (M_DIR, M_NEU), (M_NEU, M_NEU)), 1),
     ((64, 16, 8), 1, 4, ((M_WRAP, M_WRAP), (M_NEU, M_NEU), (M_WRAP, M_WRAP)), 0),
-    ((40, 24, 12), 0, 6, ((M_NEU, M_NEU), (M_WRAP, M_WRAP), (M_DIR, M_DIR)), 0),     # ragged tiles
-    ((16, 16, 16), 0, 16, ((M_DIR, M_DIR), (M_DIR, M_NEU), (M_NEU, M_DIR)), 1),
+    ((40, 24, 12), 5, 6, ((M_NEU, M_NEU), (M_WRAP, M_WRAP), (M_DIR, M_DIR)), 0),     # ragged tiles
+    ((16, 16, 16), 5, 16, ((M_DIR, M_DIR), (M_DIR, M_NEU), (M_NEU, M_DIR)), 1),
+    ((64, 48, 8), 4, 8, ((M_WRAP, M_WRAP), (M_NEU, M_DIR), (M_NEU, M_NEU)), 1),      # 32x24: the production tile of the level-0 sweeps
+    ((64, 28, 8), 3, 4, ((M_DIR, M_NEU), (M_WRAP, M_WRAP), (M_WRAP, M_WRAP)), 0),    # 64x14
+    ((32, 64, 8), 0, 8, ((M_NEU, M_NEU), (M_WRAP, M_WRAP), (M_DIR, M_NEU)), 0),      # 32x32
 ]
 
 
-KERNELS = [("wave", 1, 0, 0), ("wave", 1, 1, 0), ("wave", 1, 0, 2), ("wave", 1, 1, 2), ("wave", 1, 0, 3), ("wave", 1, 1, 3)] + \
-          [("sweep", nsw, pre, post) for nsw in (1, 2) for pre in (0, 1) for post in (0, 2, 3)] + \
-          [(kk, 1, pre, post) for kk in ("sweep2", "sweep3") for pre in (0, 1) for post in (0, 2, 3)]
+KERNELS = [("sweep3", 1, pre, post) for pre in (0, 1) for post in (0, 2, 3)]
 
 
 @pytest.mark.parametrize("n,cfg,zchunk,mode,par0", CASES)
@@ -144,10 +142,10 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
             assert np.all(czero[CV] == 0.0)
 
 
-@pytest.mark.parametrize("kern", ["wave", "sweep", "sweep2", "sweep3"])
+@pytest.mark.parametrize("cfg", [5, 2])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
 @pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
-def test_wave_rank_ghost_layers(emu, pre, post, split, kern):
+def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, kern="sweep3"):
     """a level split across ranks: the kernel relaxes the neighbour ranks' cells held in its MG_PAD ghost layers (M_GHOST)
     redundantly; the block of every 'rank' must equal the same block of the whole-domain sweep"""
     rng = np.random.default_rng(77 + pre + 5 * post + len(split))
@@ -187,7 +185,7 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, kern):
         lc = cut(cphi, cn, [x // 2 for x in o])
         out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
         fn = getattr(emu, "emu_" + kern)
-        rc = fn(1, pre, post, 0, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
+        rc = fn(1, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
                 Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD)
         assert rc == 0
         V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))

@@ -226,12 +226,11 @@ def test_mg_high_density_ratio():
 
 
 @pytest.mark.parametrize("case", ["rt64", "mixed"])
-@pytest.mark.parametrize("fuse,tile,nsw", [(1, -1, 1), (1, 0, 1), (1, 1, 1), (2, -1, 1), (2, 0, 1), (2, 1, 1), (2, 2, 1), (2, -1, 2), (2, 0, 2), (2, 1, 2), (2, 2, 2),
-                                           (3, -1, 1), (3, 0, 1), (3, 1, 1), (3, 2, 1), (4, -1, 1), (4, 0, 1), (4, 1, 1), (4, 2, 1)])
-def test_mg_fused_wavefront(case, fuse, tile, nsw, monkeypatch):
-    """the fused wavefront smoothers (fuse 1: k_wave, fuse 2: k_sweep, fuse 3: k_sweep2, fuse 4: k_sweep3 -- GSRB sweeps + residual + restriction / prolongation in
-    one launch) against the plain per-colour kernels and the oracle: same V-cycle, so phi and the projected velocity agree to
-    the solver tolerance"""
+@pytest.mark.parametrize("tile", [-1, 0, 1, 2, 3, 4])
+def test_mg_fused_smoother(case, tile):
+    """the fused smoother k_sweep3 (GSRB sweep + residual + restriction / prolongation / norm in one launch), every tile shape the
+    launcher can pick (0: 32x32, 1: 64x16, 2: 32x16, 3: 64x14, 4: 32x24; -1: the production choice per launch kind), against the plain
+    per-colour kernels and the oracle: same V-cycle, so phi and the projected velocity agree to the solver tolerance"""
     if case == "rt64":
         geom, P, st, dt = O.rt_state(64, dim=3, max_grid_size=64)
     else:
@@ -241,11 +240,11 @@ def test_mg_fused_wavefront(case, fuse, tile, nsw, monkeypatch):
     ref = O.stagewise(geom, P, st, dt, mac_rel_eps=1e-13)
     out = {}
     for mode in ("plain", "fused"):
-        monkeypatch.setenv("VDN_MG_FUSE", "0" if mode == "plain" else str(fuse))
-        monkeypatch.setenv("VDN_MG_FUSE_MIN", "16")
-        monkeypatch.setenv("VDN_MG_TILE", str(tile))
-        monkeypatch.setenv("VDN_MG_NSW", str(nsw))
         ctx = make_ctx(geom, P)
+        if mode == "plain":
+            ctx.mg_tune(1 << 30, -1)
+        else:
+            ctx.mg_tune(16, tile)
         upload_state(ctx, geom, P, st)
         ctx.mkvelforce("SOLD", 1.0)
         ctx.velpred(dt)
@@ -266,4 +265,4 @@ def test_mg_fused_wavefront(case, fuse, tile, nsw, monkeypatch):
     # same algorithm => same cycle count (+-1 for round-off at the stopping test); far fewer launches
     assert abs(out["fused"][0] - out["plain"][0]) <= 1, (out["fused"][0], out["plain"][0])
     assert out["fused"][3] < out["plain"][3]
-    print(case, fuse, tile, nsw, "cycles fused/plain", out["fused"][0], out["plain"][0], "launches", out["fused"][3], out["plain"][3])
+    print(case, tile, "cycles fused/plain", out["fused"][0], out["plain"][0], "launches", out["fused"][3], out["plain"][3])

@@ -16,21 +16,18 @@ def _ngpu():
 
 @pytest.mark.parametrize("case,n", [("rt3d", 64), ("rand3d", 32), ("per3d", 32), ("rt2d", 64)])
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("smoother", ["plain", "fused", "fused_cascade"])
+@pytest.mark.parametrize("smoother", ["plain", "fused"])
 def test_multi_gpu_parity(case, n, world, smoother):
     """plain: per-colour kernels with a 1-layer exchange per colour; fused: the fused smoother forced onto the rank-split levels (deep
-    single-phase ghost exchange where <= 2 directions are split); fused_cascade: the same with the direction-by-direction exchange"""
+    single-phase ghost exchange: faces, edges and corners in one message set)"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     if case == "rt2d" and (world == 8 or smoother != "plain"):
         pytest.skip("2-D: 4 boxes, plain kernels only")
     env = dict(os.environ)
-    if smoother != "plain":
-        env["VDN_MG_FUSE_MIN"] = "16"
-    if smoother == "fused_cascade":
-        env["VDN_HALO_ONEPHASE"] = "0"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--size", str(n)]
+           "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--size", str(n),
+           "--fuse-min", "16" if smoother == "fused" else "128"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-2000:], r.stderr[-3000:])
     assert r.returncode == 0

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
-    "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count",
+    "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune",
 ]
 
 
@@ -44,7 +44,8 @@ class VdnParams(C.Structure):
 class VdnHostState(C.Structure):
     """vdn_host_state: one pointer per local box and multifab (include/vdn.h)"""
     _fields_ = [(k, C.POINTER(C.POINTER(C.c_double))) for k in
-                ("uold", "sold", "gp", "ext_vel_force", "ext_scal_force", "unew", "snew", "rhohalf")]
+                ("uold", "sold", "gp", "ext_vel_force", "ext_scal_force", "unew", "snew", "rhohalf", "lapu", "mac_rhs")]
+    OPTIONAL = ("lapu", "mac_rhs")
 
 
 class VdnError(RuntimeError):
@@ -73,7 +74,7 @@ def load_library():
                     break
         except Exception:
             pass
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(os.environ.get("VDN_LIB", LIB_PATH))      # VDN_LIB: a differently tuned build of the same library (kernel tuning runs)
         _lib.vdn_last_error.restype = C.c_char_p
         _lib.vdn_launch_count.restype = C.c_longlong
         _lib.vdn_get_stream.restype = C.c_void_p
@@ -210,6 +211,10 @@ class Context:
         self._chk(self.lib.vdn_mac_solve(self.h, C.c_double(rel_eps), C.c_double(abs_eps), C.byref(n), C.byref(r)))
         return n.value, r.value
 
+    def mg_tune(self, fuse_min=128, tile=-1):
+        """test hook: smallest level the fused smoother runs on, forced tile shape (-1: measured defaults)"""
+        self._chk(self.lib.vdn_mg_tune(self.h, int(fuse_min), int(tile)))
+
     def macproject(self, rel_eps=-1.0, abs_eps=-1.0):
         n, r = C.c_int(0), C.c_double(0.0)
         self._chk(self.lib.vdn_macproject(self.h, C.c_double(rel_eps), C.c_double(abs_eps), C.byref(n), C.byref(r)))
@@ -226,6 +231,8 @@ class Context:
         hs = VdnHostState()
         keep = []
         for k, _ in VdnHostState._fields_:
+            if k in VdnHostState.OPTIONAL and mfs.get(k) is None:
+                continue                                     # NULL: not handed over
             mf = mfs[k]
             assert len(mf) == len(self.boxes) and all(a.dtype == np.float64 and a.flags.f_contiguous for a in mf)
             arr = (C.POINTER(C.c_double) * len(mf))(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in mf])

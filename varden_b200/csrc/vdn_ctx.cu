@@ -106,7 +106,6 @@ static void ctx_build(vdn_ctx *c, const vdn_params *prm, int dim, int nboxes, co
     VDN_REQUIRE(prm->stencil_order == 2, "only stencil_order = 2 is implemented");
     VDN_REQUIRE(prm->slope_order == 0 || prm->slope_order == 2 || prm->slope_order == 4, "slope_order must be 0, 2 or 4");
     c->prm = *prm; c->dim = dim; c->device = device; c->nboxes = nboxes;
-    if (const char *e = getenv("VDN_GODUNOV_FUSE")) c->godunov_fuse = atoi(e);
     int ndev = 0;
     VDN_CUDA(cudaGetDeviceCount(&ndev));
     VDN_REQUIRE(ndev > 0, "no CUDA device: the hot path has no CPU fallback");
@@ -184,13 +183,16 @@ static void ctx_build(vdn_ctx *c, const vdn_params *prm, int dim, int nboxes, co
         c->f[VDN_UEDGE_X + d].nc = dm;
         alloc_field(c, VDN_SFLUX_X + d, 0, 1, d);        // only the conservative comp (density) carries a flux
     }
-    // Godunov scratch arena (S-layout: cells -1..n, faces 0..n)
-    c->nscr = 36;
-    c->s_sy = g.n[0] + 2; c->s_sz = (long)c->s_sy * (g.n[1] + 2);
-    c->s_n = c->s_sz * (dim == 3 ? g.n[2] + 2 : 1);
-    c->s_off = 1 + c->s_sy + (dim == 3 ? c->s_sz : 0);
-    VDN_CUDA(cudaMalloc(&c->scratch, sizeof(double) * c->s_n * c->nscr));
-    VDN_CUDA(cudaMemsetAsync(c->scratch, 0, sizeof(double) * c->s_n * c->nscr, c->stream));
+    // Godunov scratch arena of the staged 2-D kernels (S-layout: cells -1..n, faces 0..n); the 3-D plane-marching kernels keep
+    // every intermediate on chip and need none
+    if (dim == 2) {
+        c->nscr = 36;
+        c->s_sy = g.n[0] + 2; c->s_sz = (long)c->s_sy * (g.n[1] + 2);
+        c->s_n = c->s_sz;
+        c->s_off = 1 + c->s_sy;
+        VDN_CUDA(cudaMalloc(&c->scratch, sizeof(double) * c->s_n * c->nscr));
+        VDN_CUDA(cudaMemsetAsync(c->scratch, 0, sizeof(double) * c->s_n * c->nscr, c->stream));
+    }
     VDN_CUDA(cudaMalloc(&c->d_eps, sizeof(double) * std::max(nboxes, 1)));
     VDN_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 64));
     VDN_CUDA(cudaMallocHost(&c->h_pin, sizeof(double) * 64));
@@ -222,8 +224,7 @@ static void ctx_free(vdn_ctx *c)
     delete c;
 }
 
-// copy between a host box array and the region array: valid cells of the box plus the ghost cells that lie
-// outside the region's valid area (ghosts inside it are other boxes' valid cells).
+// copy between a host box array and the region array
 static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int ncomp, bool upload, cudaStream_t stream = nullptr, bool wait = true)
 {
     if (!stream) stream = c->stream;
@@ -233,6 +234,7 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
     VDN_REQUIRE(f.base != nullptr, "field not allocated for this dimension");
     VDN_REQUIRE(ng == f.ng && ncomp == f.nc, "host (ng, ncomp) does not match the field's fixed layout");
     if (upload && field >= VDN_UMAC_X && field <= VDN_UMAC_Z) ++c->umac_epoch;
+    if (upload && field == VDN_LAPU) c->lapu_set = true;
     VDN_CUDA(cudaSetDevice(c->device));
     int hext[3], clo[3], chi[3], hlo[3];
     for (int d = 0; d < 3; ++d) {
@@ -240,8 +242,11 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
         if (d >= c->dim) { hext[d] = 1; clo[d] = 0; chi[d] = 0; hlo[d] = 0; continue; }
         const int nod = (d == f.fdir) ? 1 : 0;
         hext[d] = hi - lo + 1 + 2 * ng + nod; hlo[d] = lo - ng;
-        clo[d] = lo - (lo == c->rlo[d] ? ng : 0);
-        chi[d] = hi + nod + (hi == c->rhi[d] ? ng : 0);
+        // upload: the box's valid cells plus the ghost cells that lie outside the region's valid area (inner ghosts are other boxes'
+        // valid cells).  download: the whole ghosted extent -- the region array holds the neighbour boxes' valid cells and the filled
+        // outer ghosts there, which is what ml_restrict_and_fill leaves in the reference's per-box ghosts (update.f90:103-107).
+        clo[d] = lo - ((!upload || lo == c->rlo[d]) ? ng : 0);
+        chi[d] = hi + nod + ((!upload || hi == c->rhi[d]) ? ng : 0);
     }
     // one box covering the region, stored with the host's own ghost width: host and device layouts coincide -> one flat copy
     bool flat = c->nboxes == 1;
@@ -282,15 +287,32 @@ static void io_final(vdn_ctx *c, int field, double *const *host)
     for (int b = 0; b < c->nboxes; ++b) box_copy(c, field, b, host[b], c->f[field].ng, c->f[field].nc, false, c->s_d2h, false);
 }
 
+// A region that does not own a whole direction of the domain needs its neighbours: without a communicator the rank-boundary ghost
+// cells would silently stay stale (st_fill_boundary / the multigrid halo do nothing).
+void ctx_require_comm(const vdn_ctx *c)
+{
+    if (c->comm) return;
+    for (int d = 0; d < c->dim; ++d) {
+        const bool whole = c->rlo[d] == c->dom_lo[d] && c->rhi[d] == c->dom_hi[d];
+        VDN_REQUIRE(whole, "the context's region is a strict part of the domain: call vdn_ctx_set_comm (one context per rank) before any stage");
+    }
+}
+
 static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles, double *resnorm)
 {
+    ctx_require_comm(c);
+    // the explicit viscous term Lu is computed by the reference Fortran (get_explicit_diffusive_term, advance_timestep.f90:84-88)
+    // and must have been handed over; it is never computed here
+    VDN_REQUIRE(c->prm.visc_coef == 0.0 || c->lapu_set, "visc_coef > 0 needs the LAPU field (vdn_field_upload / vdn_host_state.lapu)");
     // advance_timestep.f90:76-77 builds umac = 1.d20 every step; here the 1.d20 poison is set once at context creation:
     // the only faces that keep it (ghost faces outside non-periodic boundaries) are never written afterwards.
     // advance_premac (advance_premac.f90:44-51)
     io_need(c, VDN_EXT_VEL_FORCE); io_need(c, VDN_GP); io_need(c, VDN_SOLD);
+    if (c->hio && c->hio->lapu) io_need(c, VDN_LAPU);
     st_mkvelforce(c, VDN_SOLD, 1.0);
     io_need(c, VDN_UOLD);
     st_velpred(c, dt);
+    if (c->hio && c->hio->mac_rhs) io_need(c, VDN_MAC_RHS);
     // macproject (macproject.f90:20-133)
     st_divumac(c, false);
     st_mk_mac_coeffs(c);
@@ -420,10 +442,12 @@ static void advance_host_impl(vdn_ctx *c, double dt, double mac_rel_eps, const v
     // the previous pass (and whatever the caller enqueued on the context's stream) must be done with the input fields
     VDN_CUDA(cudaEventRecord(c->ev_fin[VDN_UOLD], c->stream));
     VDN_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_fin[VDN_UOLD], 0));
-    const struct { int field; const double *const *host; } up[5] = {
-        { VDN_EXT_VEL_FORCE, hs->ext_vel_force }, { VDN_GP, hs->gp }, { VDN_SOLD, hs->sold }, { VDN_UOLD, hs->uold },
-        { VDN_EXT_SCAL_FORCE, hs->ext_scal_force } };
+    VDN_REQUIRE(c->prm.visc_coef == 0.0 || hs->lapu, "vdn_advance_host: visc_coef > 0 needs vdn_host_state.lapu");
+    const struct { int field; const double *const *host; } up[7] = {
+        { VDN_EXT_VEL_FORCE, hs->ext_vel_force }, { VDN_GP, hs->gp }, { VDN_SOLD, hs->sold }, { VDN_LAPU, hs->lapu }, { VDN_UOLD, hs->uold },
+        { VDN_MAC_RHS, hs->mac_rhs }, { VDN_EXT_SCAL_FORCE, hs->ext_scal_force } };
     for (const auto &u : up) {
+        if (!u.host) continue;                       // optional inputs (lapu, mac_rhs)
         for (int b = 0; b < c->nboxes; ++b)
             box_copy(c, u.field, b, const_cast<double *>(u.host[b]), c->f[u.field].ng, c->f[u.field].nc, true, c->s_h2d);
         VDN_CUDA(cudaEventRecord(c->ev_up[u.field], c->s_h2d));
@@ -438,6 +462,12 @@ static void advance_host_impl(vdn_ctx *c, double dt, double mac_rel_eps, const v
 
 int vdn_advance_host(vdn_ctx *ctx, double dt, double mac_rel_eps, const vdn_host_state *hs, int *mac_cycles, double *mac_resnorm)
 { VDN_TRY(ctx, advance_host_impl(ctx, dt, mac_rel_eps, hs, mac_cycles, mac_resnorm)) }
+
+int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile)
+{ VDN_TRY(ctx, { VDN_REQUIRE(tile >= -1 && tile < 5, "tile shape out of range");
+                 VDN_CUDA(cudaStreamSynchronize(ctx->stream));
+                 if (ctx->mg) { mg_destroy(ctx->mg); ctx->mg = nullptr; }
+                 ctx->mg_fuse_min = fuse_min; ctx->mg_tile_force = tile; }) }
 
 int vdn_prof_enable(vdn_ctx *ctx, int on)
 { VDN_TRY(ctx, { prof_collect(ctx); ctx->prof.clear(); ctx->prof_idx.clear(); ctx->prof_on = on != 0; }) }

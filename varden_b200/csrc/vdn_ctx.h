@@ -28,7 +28,7 @@ struct vdn_ctx {
     int adv_bc[16][3][2];                               // [comp][d][side] on the region faces
     int ell_bc[3][2];                                   // pressure elliptic BC on the region faces
     bool wrap[3];                                       // periodic and owned by this rank alone in that direction
-    // Godunov scratch arena: NSCR arrays in the S-layout (cells -1..n, faces 0..n)
+    // Godunov scratch arena of the staged 2-D kernels: NSCR arrays in the S-layout (cells -1..n, faces 0..n); unused in 3-D
     double *scratch = nullptr; int nscr = 0; long s_sy = 0, s_sz = 0, s_n = 0, s_off = 0;
     double *d_eps = nullptr;                            // per-box eps
     double *d_red = nullptr;                            // reduction scratch (device)
@@ -47,7 +47,8 @@ struct vdn_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[VDN_NFIELDS] = {}, ev_fin[VDN_NFIELDS] = {};
     const vdn_host_state *hio = nullptr;
-    int godunov_fuse = 1;                               // 3-D: all directions of a Godunov stage per launch (VDN_GODUNOV_FUSE)
+    int mg_fuse_min = 128, mg_tile_force = -1;          // fused smoother: smallest level it runs on; test hook (vdn_mg_tune)
+    bool lapu_set = false;                              // LAPU has been uploaded (required when visc_coef > 0)
 
     View S(int q) const { View v; v.sy = (int)s_sy; v.sz = (int)s_sz; v.cs = (int)s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
     long ncells() const { return (long)geo.n[0] * geo.n[1] * geo.n[2]; }
@@ -62,6 +63,7 @@ struct LaunchScope {
 void prof_collect(vdn_ctx *c);
 
 // ---- stage implementations (each in its own .cu) ----
+void ctx_require_comm(const vdn_ctx *c);                  // throws when the region is part of the domain and no communicator is set
 void st_fill_boundary(vdn_ctx *c, int field);
 void st_physbc(vdn_ctx *c, int field, int bccomp, bool same_boundary);
 void st_mkvelforce(vdn_ctx *c, int rho_field, double visc_fac);

@@ -4,13 +4,15 @@
 //   slope.f90     slopex_2d :148 / slopey_2d :291 / slopez_3d :437
 //   velpred.f90   velpred_3d :1776-2765 (production form incl. its hi-x OUTLET quirk :2075), velpred_2d :125-524
 //   mkflux.f90    mkflux_3d :1186-2567, mkflux_2d :152-691
-// Design (round 1): direction-generic kernels, one stage per launch, intermediates materialised in a
-// scratch arena with one uniform "S-layout" (cells -1..n, faces 0..n in every direction) so that every
-// stage is a coalesced streaming pass; operation order follows the reference line by line so the
-// results are bit-comparable with the CPU oracle.  eps is per reference box.
+// 3-D: ONE plane-marching kernel per routine (vdn_godunov_march.cuh): a CTA marches a tile of columns along z with every
+// intermediate in registers / shared memory, so a field is read once and the edge states are written once -- no scratch arena.
+// 2-D (config 1, tiny): direction-generic staged kernels (vdn_godunov_kernels.cuh), one stage per launch, intermediates in a small
+// "S-layout" arena (cells -1..n, faces 0..n).  Operation order follows the reference line by line, so both are bit-comparable
+// with the CPU oracle.  eps is per reference box.
 #include "vdn_ctx.h"
 
 #include "vdn_godunov_kernels.cuh"
+#include "vdn_godunov_march.cuh"
 
 namespace {
 
@@ -101,7 +103,57 @@ struct CudaLauncher {
     vdn_ctx *c;
     LaunchScope scope(const char *name, double alg_bytes, int nlaunch) { return LaunchScope(c, name, alg_bytes, nlaunch); }
     template <class A> void operator()(void (*k)(A), const Range &r, const A &a) { k<<<grid3(r, BLK), BLK, 0, c->stream>>>(a); }
+    // plane-marching kernels: explicit grid / block / dynamic shared memory
+    template <class A> void run(void (*k)(A), dim3 grid, dim3 block, size_t smem, const A &a)
+    {
+        if (smem > 48 * 1024) VDN_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, block, smem, c->stream>>>(a);
+    }
+    // resident CTAs of kernel k on this device (the z-chunking fills whole waves of them)
+    template <class A> int slots(void (*k)(A), int nthreads, size_t smem)
+    {
+        static std::map<const void *, int> cache;
+        auto it = cache.find((const void *)k);
+        if (it != cache.end()) return it->second;
+        if (smem > 48 * 1024) VDN_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k, nthreads, smem));
+        VDN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        const int v = std::max(1, per_sm) * std::max(1, sms);
+        cache[(const void *)k] = v;
+        return v;
+    }
 };
+
+void velpred_march_impl(vdn_ctx *c, double dt)
+{
+    compute_eps(c, false);
+    View out[3];
+    for (int d = 0; d < 3; ++d) out[d] = c->f[VDN_UMAC_X + d].view();
+    CudaLauncher L{c};
+    march::velpred_march(L, c->geo, c->f[VDN_UOLD].view(), c->f[VDN_VEL_FORCE].view(), out, c->d_eps, dt,
+                         c->prm.slope_order, c->prm.use_minion, c->adv_bc, 0);
+    VDN_CUDA(cudaGetLastError());
+}
+
+void mkflux_march_impl(vdn_ctx *c, int is_vel, double dt)
+{
+    // scalar_advance passes divu == 0 as mac_rhs (scalar_advance.f90:102) and no velocity component is conservative
+    // (velocity_advance.f90:51), so the s*mac_rhs term of mkflux.f90:2340-2345 never contributes: x - dt2*s*0 == x exactly.
+    compute_eps(c, true);
+    const int ncomp = is_vel ? 3 : c->prm.nscal;
+    View mac[3], sedge[3], flux[3];
+    for (int d = 0; d < 3; ++d) {
+        mac[d] = c->f[VDN_UMAC_X + d].view();
+        sedge[d] = c->f[(is_vel ? VDN_UEDGE_X : VDN_SEDGE_X) + d].view();
+        flux[d] = c->f[VDN_SFLUX_X + d].view();
+    }
+    CudaLauncher L{c};
+    march::mkflux_march(L, c->geo, c->f[is_vel ? VDN_UOLD : VDN_SOLD].view(), c->f[is_vel ? VDN_VEL_FORCE : VDN_SCAL_FORCE].view(),
+                        mac, sedge, flux, c->d_eps, dt, is_vel, ncomp, c->prm.slope_order, c->prm.use_minion,
+                        c->adv_bc + (is_vel ? 0 : 3), 0);
+    VDN_CUDA(cudaGetLastError());
+}
 
 template <int DIM>
 void velpred_impl(vdn_ctx *c, double dt)
@@ -117,7 +169,7 @@ void velpred_impl(vdn_ctx *c, double dt)
         for (int t = 0; t < 3; ++t) a.X[d][t] = c->S(SL0 + d * 3 + t);     // transverse states reuse the slope slots
     }
     CudaLauncher L{c};
-    velpred_stages<DIM>(L, a, c->godunov_fuse != 0);
+    velpred_stages<DIM>(L, a);
     VDN_CUDA(cudaGetLastError());
 }
 
@@ -149,7 +201,7 @@ void mkflux_impl(vdn_ctx *c, int is_vel, double dt)
             a.sedge[d] = c->f[(is_vel ? VDN_UEDGE_X : VDN_SEDGE_X) + q].view().comp(comp);
             a.flux[d] = is_vel ? a.sedge[d] : c->f[VDN_SFLUX_X + q].view().comp(comp);
         }
-        mkflux_stages<DIM>(L, a, c->godunov_fuse != 0);
+        mkflux_stages<DIM>(L, a);
     }
     VDN_CUDA(cudaGetLastError());
 }
@@ -158,14 +210,14 @@ void mkflux_impl(vdn_ctx *c, int is_vel, double dt)
 
 void st_velpred(vdn_ctx *c, double dt)
 {
-    VDN_REQUIRE(c->nscr >= NSCR_NEEDED, "scratch arena too small for velpred");
-    if (c->dim == 3) velpred_impl<3>(c, dt); else velpred_impl<2>(c, dt);
+    if (c->dim == 3) velpred_march_impl(c, dt);
+    else { VDN_REQUIRE(c->nscr >= NSCR_NEEDED, "scratch arena too small for velpred"); velpred_impl<2>(c, dt); }
     ++c->umac_epoch;
     for (int d = 0; d < c->dim; ++d) st_fill_boundary(c, VDN_UMAC_X + d);      // velpred.f90:107-112
 }
 
 void st_mkflux(vdn_ctx *c, int is_vel, double dt)
 {
-    VDN_REQUIRE(c->nscr >= MF_NSCR, "scratch arena too small for mkflux");
-    if (c->dim == 3) mkflux_impl<3>(c, is_vel, dt); else mkflux_impl<2>(c, is_vel, dt);
+    if (c->dim == 3) mkflux_march_impl(c, is_vel, dt);
+    else { VDN_REQUIRE(c->nscr >= MF_NSCR, "scratch arena too small for mkflux"); mkflux_impl<2>(c, is_vel, dt); }
 }

@@ -198,14 +198,15 @@ __device__ __forceinline__ double bc_edge(double v, double el, double er, int d,
     const int ix[3] = { i, j, k }; (void)ix;
 
 // ------------------------------------------------------------------------------------------
-// velpred.  Every stage is a per-point device function (one face of direction D at (i,j,k)); the stage kernels
-// either run one direction per launch (2-D, or VDN_GODUNOV_FUSE=0) or all directions of a stage in ONE launch
-// with the limited slopes evaluated in registers (3-D default): same arithmetic per point, ~half the HBM traffic.
+// velpred, staged form: every stage is a per-point device function (one face of direction D at (i,j,k)), one direction per
+// launch, intermediates in the S-layout scratch arena.  This is the 2-D path (velpred_2d / mkflux_2d; config 1 is tiny); 3-D
+// runs the plane-marching kernels of vdn_godunov_march.cuh.  The templates stay DIM-generic so that the CPU test tier can run
+// the staged 3-D form as an independent second implementation against the marching kernels.
 // ------------------------------------------------------------------------------------------
 struct VpArgs {
     Geo g; Range r;
     View u, force;
-    View sl[3];                     // slopes along D, DIM comps (staged path only)
+    View sl[3];                     // slopes along D, DIM comps
     View ul[3], ur[3], uimh[3];     // per direction, DIM comps each
     View X[3][3];                   // transverse-corrected states X[D][T] (3-D)
     View out[3];                    // umac_D (field views)
@@ -215,7 +216,7 @@ struct VpArgs {
 };
 
 // normal predictor + Riemann/upwind: velpred.f90:2019-2099 (x), 2105-2185 (y), 2283-2367 (z); 2-D :258-322, :330-396
-template <int DIM, int D, bool INL>
+template <int DIM, int D>
 __device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int k)
 {
     const int ix[3] = { i, j, k };
@@ -223,15 +224,7 @@ __device__ __forceinline__ void vp_normal_pt(const VpArgs &a, int i, int j, int 
     const int su = a.u.st(D);
     const double *uR = &a.u(i, j, k), *uL = uR - su;
     double slL[DIM], slR[DIM];
-    if (INL) {
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) {
-            const bool bl = a.sbc[c][D][0] == BC_EXT_DIR || a.sbc[c][D][0] == BC_HOEXTRAP;
-            const bool bh = a.sbc[c][D][1] == BC_EXT_DIR || a.sbc[c][D][1] == BC_HOEXTRAP;
-            slL[c] = slope_at(uL + a.u.cs * c, su, ix[D] - 1, a.g.n[D], bl, bh, a.order);
-            slR[c] = slope_at(uR + a.u.cs * c, su, ix[D], a.g.n[D], bl, bh, a.order);
-        }
-    } else {
+    {
         const int ss = a.sl[D].st(D);
         const double *sR = &a.sl[D](i, j, k), *sL = sR - ss;
 #pragma unroll
@@ -280,15 +273,7 @@ template <int DIM, int D>
 __global__ void k_vp_normal(VpArgs a)
 {
     THREAD_IJK(a.r)
-    vp_normal_pt<DIM, D, false>(a, i, j, k);
-}
-// all three directions, slopes in registers; a.r = cells -1..n in every direction, the D-face of a cell exists for ix[D] >= 0
-__global__ void __launch_bounds__(256) k_vp_normal3(VpArgs a)
-{
-    THREAD_IJK(a.r)
-    if (i >= 0) vp_normal_pt<3, 0, true>(a, i, j, k);
-    if (j >= 0) vp_normal_pt<3, 1, true>(a, i, j, k);
-    if (k >= 0) vp_normal_pt<3, 2, true>(a, i, j, k);
+    vp_normal_pt<DIM, D>(a, i, j, k);
 }
 
 // transverse-corrected tangential state of comp C = 3-D-T on D faces, corrected by T (3-D only):
@@ -317,25 +302,6 @@ __global__ void k_vp_trans(VpArgs a)
 {
     THREAD_IJK(a.r)
     vp_trans_pt<D, T>(a, i, j, k);
-}
-// index ranges of the six transverse states (velpred.f90:1986-2004 / mkflux.f90 allocate list): X[D][T] lives on D faces
-// 0..n_D, cells 0..n_T-1 along T and cells -1..n along the third direction
-template <int D, int T>
-__device__ __forceinline__ bool trans_in_range(const Geo &g, int i, int j, int k)
-{
-    const int ix[3] = { i, j, k };
-    constexpr int O = 3 - D - T;
-    return ix[D] >= 0 && ix[D] <= g.n[D] && ix[T] >= 0 && ix[T] <= g.n[T] - 1 && ix[O] >= -1 && ix[O] <= g.n[O];
-}
-__global__ void __launch_bounds__(256) k_vp_trans6(VpArgs a)       // a.r = -1..n in every direction
-{
-    THREAD_IJK(a.r)
-    if (trans_in_range<0, 1>(a.g, i, j, k)) vp_trans_pt<0, 1>(a, i, j, k);
-    if (trans_in_range<1, 0>(a.g, i, j, k)) vp_trans_pt<1, 0>(a, i, j, k);
-    if (trans_in_range<2, 0>(a.g, i, j, k)) vp_trans_pt<2, 0>(a, i, j, k);
-    if (trans_in_range<2, 1>(a.g, i, j, k)) vp_trans_pt<2, 1>(a, i, j, k);
-    if (trans_in_range<0, 2>(a.g, i, j, k)) vp_trans_pt<0, 2>(a, i, j, k);
-    if (trans_in_range<1, 2>(a.g, i, j, k)) vp_trans_pt<1, 2>(a, i, j, k);
 }
 
 // final MAC velocity: umac :2617-2659, vmac :2665-2707, wmac :2373-2419 ; 2-D :402-444, :454-496
@@ -382,31 +348,14 @@ __global__ void k_vp_final(VpArgs a)
     THREAD_IJK(a.r)
     vp_final_pt<DIM, D>(a, i, j, k);
 }
-// valid faces of direction D: 0..n_D along D, 0..n-1 along the others
-template <int D>
-__device__ __forceinline__ bool face_in_range(const Geo &g, int i, int j, int k)
-{
-    const int ix[3] = { i, j, k };
-    bool ok = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) ok = ok && ix[d] >= 0 && ix[d] <= g.n[d] - (d == D ? 0 : 1);
-    return ok;
-}
-__global__ void __launch_bounds__(256) k_vp_final3(VpArgs a)       // a.r = 0..n in every direction
-{
-    THREAD_IJK(a.r)
-    if (face_in_range<0>(a.g, i, j, k)) vp_final_pt<3, 0>(a, i, j, k);
-    if (face_in_range<1>(a.g, i, j, k)) vp_final_pt<3, 1>(a, i, j, k);
-    if (face_in_range<2>(a.g, i, j, k)) vp_final_pt<3, 2>(a, i, j, k);
-}
 
 // ------------------------------------------------------------------------------------------
-// mkflux (one component per pass; same staged / fused structure as velpred)
+// mkflux, staged form (one component per pass)
 // ------------------------------------------------------------------------------------------
 struct MfArgs {
     Geo g; Range r;
     View s;                         // comp already selected
-    View sl[3];                     // slope along D of this comp (staged path only)
+    View sl[3];                     // slope along D of this comp
     View mac[3];                    // MAC velocities
     View force, mac_rhs;
     View l[3], rr[3], simh[3];      // 1-D extrapolated L/R states and their upwinded value, per direction
@@ -417,19 +366,14 @@ struct MfArgs {
     int order; int sbc[3][2];       // slope order and adv_bc[d][side] of this comp for in-register slopes
 };
 // 1-D extrapolation + BC + upwind: mkflux.f90:1443-1524 (x), 1530-1611 (y), 1779-1864 (z)
-template <int D, bool INL>
+template <int D>
 __device__ __forceinline__ void mf_normal_pt(const MfArgs &a, int i, int j, int k)
 {
     const int ix[3] = { i, j, k };
     const double dt2 = HALF * a.dt, h = a.g.h[D];
     const double *sR = &a.s(i, j, k), *sL = sR - a.s.st(D);
     double pLv, pRv;
-    if (INL) {
-        const bool bl = a.sbc[D][0] == BC_EXT_DIR || a.sbc[D][0] == BC_HOEXTRAP;
-        const bool bh = a.sbc[D][1] == BC_EXT_DIR || a.sbc[D][1] == BC_HOEXTRAP;
-        pLv = slope_at(sL, a.s.st(D), ix[D] - 1, a.g.n[D], bl, bh, a.order);
-        pRv = slope_at(sR, a.s.st(D), ix[D], a.g.n[D], bl, bh, a.order);
-    } else {
+    {
         const double *pR = &a.sl[D](i, j, k), *pL = pR - a.sl[D].st(D);
         pLv = pL[0]; pRv = pR[0];
     }
@@ -454,14 +398,7 @@ template <int D>
 __global__ void k_mf_normal(MfArgs a)
 {
     THREAD_IJK(a.r)
-    mf_normal_pt<D, false>(a, i, j, k);
-}
-__global__ void __launch_bounds__(256) k_mf_normal3(MfArgs a)      // a.r = -1..n in every direction
-{
-    THREAD_IJK(a.r)
-    if (i >= 0) mf_normal_pt<0, true>(a, i, j, k);
-    if (j >= 0) mf_normal_pt<1, true>(a, i, j, k);
-    if (k >= 0) mf_normal_pt<2, true>(a, i, j, k);
+    mf_normal_pt<D>(a, i, j, k);
 }
 
 // transverse-once states: simhxy :1617, simhyx :1697, simhzx :1978, simhzy :2062, simhxz :2150, simhyz :2230
@@ -492,16 +429,6 @@ __global__ void k_mf_trans(MfArgs a)
 {
     THREAD_IJK(a.r)
     mf_trans_pt<D, T>(a, i, j, k);
-}
-__global__ void __launch_bounds__(256) k_mf_trans6(MfArgs a)       // a.r = -1..n in every direction
-{
-    THREAD_IJK(a.r)
-    if (trans_in_range<0, 1>(a.g, i, j, k)) mf_trans_pt<0, 1>(a, i, j, k);
-    if (trans_in_range<1, 0>(a.g, i, j, k)) mf_trans_pt<1, 0>(a, i, j, k);
-    if (trans_in_range<2, 0>(a.g, i, j, k)) mf_trans_pt<2, 0>(a, i, j, k);
-    if (trans_in_range<2, 1>(a.g, i, j, k)) mf_trans_pt<2, 1>(a, i, j, k);
-    if (trans_in_range<0, 2>(a.g, i, j, k)) mf_trans_pt<0, 2>(a, i, j, k);
-    if (trans_in_range<1, 2>(a.g, i, j, k)) mf_trans_pt<1, 2>(a, i, j, k);
 }
 
 // final edge state + flux: sedgex :2310-2408, sedgey :2414-2512, sedgez :1870-1972 ; 2-D :470-566, :572-666
@@ -571,13 +498,6 @@ __global__ void k_mf_final(MfArgs a)
     THREAD_IJK(a.r)
     mf_final_pt<DIM, D>(a, i, j, k);
 }
-__global__ void __launch_bounds__(256) k_mf_final3(MfArgs a)       // a.r = 0..n in every direction
-{
-    THREAD_IJK(a.r)
-    if (face_in_range<0>(a.g, i, j, k)) mf_final_pt<3, 0>(a, i, j, k);
-    if (face_in_range<1>(a.g, i, j, k)) mf_final_pt<3, 1>(a, i, j, k);
-    if (face_in_range<2>(a.g, i, j, k)) mf_final_pt<3, 2>(a, i, j, k);
-}
 
 
 // ------------------------------------------------------------------------------------------
@@ -586,20 +506,12 @@ __global__ void __launch_bounds__(256) k_mf_final3(MfArgs a)       // a.r = 0..n
 // ------------------------------------------------------------------------------------------
 
 template <int DIM, class L>
-void velpred_stages(L &launch, VpArgs a, bool fused)
+void velpred_stages(L &launch, VpArgs a)
 {
     const Geo &g = a.g;
     const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
     const int zl = DIM == 3 ? -1 : 0, zh = DIM == 3 ? n2 : 0;       // grown z range
     const double cells = (double)n0 * n1 * n2;
-    if (fused && DIM == 3) {
-        // velpred.f90:1776-2765 in three launches (all directions per stage, slopes in registers):
-        // compulsory traffic R u 24 + W (ul,ur,uimh) 216 | R 216 + W X 48 | R (ul,ur,uimh,X) ~120 + force 24 + W umac 24
-        { auto ls = launch.scope("vp_normal3", cells * 8.0 * (3 + 27), 1); a.r = mk_range(-1, n0, -1, n1, -1, n2); launch(k_vp_normal3, a.r, a); }
-        { auto ls = launch.scope("vp_trans6", cells * 8.0 * (27 + 6), 1);  a.r = mk_range(-1, n0, -1, n1, -1, n2); launch(k_vp_trans6, a.r, a); }
-        { auto ls = launch.scope("vp_final3", cells * 8.0 * (6 + 3 + 6 + 3 + 3), 1); a.r = mk_range(0, n0, 0, n1, 0, n2); launch(k_vp_final3, a.r, a); }
-        return;
-    }
     // slopes on cells -1..n (velpred.f90:1848-1852)
     {
         auto ls = launch.scope("vp_slopes", cells * 8.0 * (DIM + DIM * DIM), 1);
@@ -637,19 +549,12 @@ void velpred_stages(L &launch, VpArgs a, bool fused)
 
 // one component of mkflux (a.s, a.force, a.sedge, a.flux, a.comp, a.cons, a.sbc select it)
 template <int DIM, class L>
-void mkflux_stages(L &launch, MfArgs a, bool fused)
+void mkflux_stages(L &launch, MfArgs a)
 {
     const Geo &g = a.g;
     const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
     const int zl = DIM == 3 ? -1 : 0, zh = DIM == 3 ? n2 : 0;
     const double cells = (double)n0 * n1 * n2;
-    if (fused && DIM == 3) {
-        // mkflux.f90:1186-2567 for one component in three launches (all directions per stage, slopes in registers)
-        { auto ls = launch.scope("mf_normal3", cells * 8.0 * (1 + 3 + 9), 1); a.r = mk_range(-1, n0, -1, n1, -1, n2); launch(k_mf_normal3, a.r, a); }
-        { auto ls = launch.scope("mf_trans6", cells * 8.0 * (9 + 3 + 6), 1);  a.r = mk_range(-1, n0, -1, n1, -1, n2); launch(k_mf_trans6, a.r, a); }
-        { auto ls = launch.scope("mf_final3", cells * 8.0 * (6 + 6 + 3 + 2 + 3 + (a.cons ? 3 : 0)), 1); a.r = mk_range(0, n0, 0, n1, 0, n2); launch(k_mf_final3, a.r, a); }
-        return;
-    }
     {
         auto ls = launch.scope("mf_slopes", cells * 8.0 * (1 + DIM), 1);
         SlopeArgs sa; sa.g = g; sa.s = a.s; sa.ncomp = 1; sa.order = a.order;

@@ -909,19 +909,28 @@ inline void fill_consts(const Geo &g, double dt, double &dt2, double *c2, double
 #ifndef MARCH_TYT
 #define MARCH_TYT 16
 #endif
+#ifndef MARCH_TYT_VP
+#define MARCH_TYT_VP MARCH_TYT
+#endif
 #ifndef MARCH_NCG
 #define MARCH_NCG 1          // components per mkflux launch
 #endif
 
+template <int TYT, class L, class A>
+void march_launch(L &launch, void (*k)(A), A &a, const Geo &g, size_t smem, int slots)
+{
+    const Plan p = make_plan(g, TYT, slots > 0 ? slots : launch.slots(k, TXT * TYT, smem));
+    a.zchunk = p.zchunk;
+    launch.run(k, dim3(p.ntx, p.nty, p.nzc), dim3(TXT, TYT, 1), smem, a);
+}
 template <int NC, class L>
-void mkflux_march_group(L &launch, MfmArgs &a, int consmask, bool gen, const Plan &p)
+void mkflux_march_group(L &launch, MfmArgs &a, int consmask, bool gen, int slots)
 {
     constexpr int TYT = MARCH_TYT;
-    const dim3 grid(p.ntx, p.nty, p.nzc), block(TXT, TYT, 1);
     const size_t smem = sizeof(double) * TXT * TYT * mf_smem_slots<NC>();
     a.nc = NC;
-    if (consmask) { if (gen) launch.run(k_mkflux_march<NC, 1, TYT, true>, grid, block, smem, a); else launch.run(k_mkflux_march<NC, 1, TYT, false>, grid, block, smem, a); }
-    else          { if (gen) launch.run(k_mkflux_march<NC, 0, TYT, true>, grid, block, smem, a); else launch.run(k_mkflux_march<NC, 0, TYT, false>, grid, block, smem, a); }
+    if (consmask) { if (gen) march_launch<TYT>(launch, k_mkflux_march<NC, 1, TYT, true>, a, a.g, smem, slots); else march_launch<TYT>(launch, k_mkflux_march<NC, 1, TYT, false>, a, a.g, smem, slots); }
+    else          { if (gen) march_launch<TYT>(launch, k_mkflux_march<NC, 0, TYT, true>, a, a.g, smem, slots); else march_launch<TYT>(launch, k_mkflux_march<NC, 0, TYT, false>, a, a.g, smem, slots); }
 }
 
 // mkflux.f90:16 for ncomp components of s.  adv_bc: [comp][3][2] of these components.  Conservative: comp 0 of the scalars.
@@ -934,8 +943,6 @@ void mkflux_march(L &launch, const Geo &g, const View &s, const View &force, con
     a.s_sy = s.sy; a.s_sz = s.sz; a.f_sy = force.sy; a.f_sz = force.sz;
     for (int d = 0; d < 3; ++d) { a.mac[d] = mac[d].p; a.m_sy[d] = mac[d].sy; a.m_sz[d] = mac[d].sz; a.e_sy[d] = sedge[d].sy; a.e_sz[d] = sedge[d].sz; }
     fill_consts(g, dt, a.dt2, a.c2, a.c3, a.c4, a.c6, a.hinv, a.hp2);
-    const Plan p = make_plan(g, MARCH_TYT, slots);
-    a.zchunk = p.zchunk;
     const bool gen = !(order == 4 && !use_minion);
     const double cells = (double)g.n[0] * g.n[1] * g.n[2];
     for (int c0 = 0; c0 < ncomp; ) {
@@ -953,12 +960,12 @@ void mkflux_march(L &launch, const Geo &g, const View &s, const View &force, con
         // SURVEY 8(a) a3 bytes: R s + force per comp, the three MAC velocities per launch; W three edge states per comp (+ fluxes)
         const double bytes = cells * 8.0 * (nc * (1 + 1 + 3) + 3 + ((consmask & 1) ? 3 : 0));
         auto ls = launch.scope(is_vel ? "mkflux_vel" : "mkflux_scal", bytes, 1);
-        if (nc == 1) mkflux_march_group<1>(launch, a, consmask, gen, p);
+        if (nc == 1) mkflux_march_group<1>(launch, a, consmask, gen, slots);
 #if MARCH_NCG >= 2
-        else if (nc == 2) mkflux_march_group<2>(launch, a, consmask, gen, p);
+        else if (nc == 2) mkflux_march_group<2>(launch, a, consmask, gen, slots);
 #endif
 #if MARCH_NCG >= 3
-        else if (nc == 3) mkflux_march_group<3>(launch, a, consmask, gen, p);
+        else if (nc == 3) mkflux_march_group<3>(launch, a, consmask, gen, slots);
 #endif
         c0 += nc;
     }
@@ -969,7 +976,7 @@ template <class L>
 void velpred_march(L &launch, const Geo &g, const View &u, const View &force, const View *out, const double *eps, double dt,
                    int order, int use_minion, const int (*adv_bc)[3][2], int slots)
 {
-    constexpr int TYT = MARCH_TYT;
+    constexpr int TYT = MARCH_TYT_VP;
     VpmArgs a; memset(&a, 0, sizeof a);
     a.g = g; a.eps = eps; a.order = order; a.use_minion = use_minion;
     a.u_sy = u.sy; a.u_sz = u.sz; a.f_sy = force.sy; a.f_sz = force.sz;
@@ -980,14 +987,11 @@ void velpred_march(L &launch, const Geo &g, const View &u, const View &force, co
         a.out[c] = out[c].p; a.o_sy[c] = out[c].sy; a.o_sz[c] = out[c].sz;
         for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) a.sbc[c][d][sd] = adv_bc[c][d][sd];
     }
-    const Plan p = make_plan(g, TYT, slots);
-    a.zchunk = p.zchunk;
-    const dim3 grid(p.ntx, p.nty, p.nzc), block(TXT, TYT, 1);
     const size_t smem = sizeof(double) * TXT * TYT * vp_smem_slots();
     // SURVEY 8(a) a2 bytes: R u 24 + force 24, W three face arrays 24
     auto ls = launch.scope("velpred", (double)g.n[0] * g.n[1] * g.n[2] * 72.0, 1);
-    if (order == 4 && !use_minion) launch.run(k_velpred_march<TYT, false>, grid, block, smem, a);
-    else                           launch.run(k_velpred_march<TYT, true>, grid, block, smem, a);
+    if (order == 4 && !use_minion) march_launch<TYT>(launch, k_velpred_march<TYT, false>, a, g, smem, slots);
+    else                           march_launch<TYT>(launch, k_velpred_march<TYT, true>, a, g, smem, slots);
 }
 
 } // namespace march

@@ -13,10 +13,7 @@
 // directions owned by one rank wrap by index, so a single GPU needs no ghost-fill launches at all.
 #include "vdn_ctx.h"
 #include "vdn_comm.h"
-#include "vdn_mg_wave.cuh"
-#include "vdn_mg_sweep.cuh"
-#include "vdn_mg_sweep2.cuh"
-#include "vdn_mg_sweep3.cuh"
+#include "vdn_mg_fused.cuh"
 #include <algorithm>
 
 
@@ -47,11 +44,9 @@ struct MG {
     MG *tail = nullptr;
     double *agg_send = nullptr, *agg_recv = nullptr;
     int *d_coords = nullptr;                    // [nranks][3] process-grid coordinates
-    // fused wavefront smoother (k_wave): levels 0..nfused-1 of a rank-local 3-D hierarchy
-    int nfused = 0;                             // number of leading levels that run the fused kernels
-    int fuse_nsw = 1;                           // GSRB sweeps fused per launch
-    int fuse_kind = 2;                          // 1: k_wave (operator rings in shared memory), 2: k_sweep (2x2 column blocks)
-    int tile_force = -1, zchunk_force = 0;      // tuning overrides (VDN_MG_TILE, VDN_MG_ZCHUNK)
+    // fused smoother (k_sweep3): levels 0..nfused-1 of a 3-D hierarchy
+    int nfused = 0;                             // number of leading levels that run the fused kernel
+    int tile_force = -1;                        // test hook (vdn_mg_tune): force one tile shape
     int sm_count = 148;
 };
 
@@ -324,22 +319,17 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
 }
 
 
-// fused wavefront smoother on the leading (large) levels of a 3-D hierarchy.  Rank-local levels wrap by index; levels that
-// are split across ranks relax MG_PAD ghost layers redundantly after ONE deep halo exchange per launch.
+// fused smoother on the leading (large) levels of a 3-D hierarchy.  Rank-local levels wrap by index; levels that are split
+// across ranks relax up to 3 ghost layers redundantly after ONE deep halo exchange per launch.
 void mg_pick_fused(vdn_ctx *c, MG *m)
 {
-    auto envi = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
-    const int fuse = envi("VDN_MG_FUSE", 4), fmin_ = envi("VDN_MG_FUSE_MIN", 128);
-    m->tile_force = envi("VDN_MG_TILE", -1); m->zchunk_force = envi("VDN_MG_ZCHUNK", 0);
     cudaDeviceProp pr; VDN_CUDA(cudaGetDeviceProperties(&pr, c->device)); m->sm_count = pr.multiProcessorCount;
-    if (fuse <= 0 || c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
-    m->fuse_kind = fuse >= 4 ? 4 : fuse >= 3 ? 3 : fuse >= 2 ? 2 : 1;
-    m->fuse_nsw = m->fuse_kind == 2 ? std::max(1, std::min(2, envi("VDN_MG_NSW", 1))) : 1;
-    if (m->distributed) m->fuse_nsw = 1;                        // two sweeps need 5 ghost layers, the level arrays carry MG_PAD
+    m->tile_force = c->mg_tile_force;
+    if (c->dim != 3 || c->prm.mg_nu1 < 1 || c->prm.mg_nu2 < 1) return;
     const int last = m->tail ? m->agg_level : m->nlev - 1;      // the agglomerated / bottom level is never fused
     while (m->nfused < last) {
         const Lev &L = m->L[m->nfused];
-        if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
+        if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(c->mg_fuse_min, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
         ++m->nfused;
     }
 }
@@ -435,14 +425,8 @@ void mg_halo_deep(vdn_ctx *c, MG *m, Lev &L, double *x, int ng)
     int dmask = 0;
     for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
     LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
-    // One phase (faces + edges + corners in one NCCL group; 4 GPUs: 7.8 instead of 11.2 ms of exchanges per step).  Run on hardware with
-    // one and two split directions (2 and 4 GPUs); the message plan for three split directions (8 GPUs, corner messages) is checked on the
-    // CPU by tests/test_halo_plan.py (vdn_halo_plan is the function executed here).  VDN_HALO_ONEPHASE=0 selects the direction-by-direction
-    // cascade (one pack / NCCL group / unpack per split direction).
-    static const char *env = getenv("VDN_HALO_ONEPHASE");
-    const bool onephase = env ? atoi(env) != 0 : true;
-    if (onephase) comm_halo_deep(c, v, L.n, m->dim, ng, dmask);
-    else comm_halo(c, v, L.n, m->dim, ng, 1, -1, dmask, true, true);
+    // one phase: faces, edges and corners travel in one NCCL group bracketed by one pack and one unpack launch
+    comm_halo_deep(c, v, L.n, m->dim, ng, dmask);
 }
 
 void smooth(vdn_ctx *c, MG *m, int l, int sweeps)
@@ -469,119 +453,9 @@ void residual(vdn_ctx *c, MG *m, int l, double *nrm)
 }
 
 
-// ---- fused wavefront launcher ----
+// ---- fused smoother launcher ----
 struct WaveVariant { const void *fn = nullptr; size_t smem = 0; int occ = 0; int H = 0, W = 0, HH = 0, TX = 0, TY = 0, NT = 0; };
-template <int NSW, int PRE, int POST, int TX, int TY, int NT, int PF>
-WaveVariant wave_variant()
-{
-    using C = WaveCfg<NSW, PRE, POST, TX, TY, NT, PF>;
-    WaveVariant v;
-    v.fn = (const void *)k_wave<NSW, PRE, POST, TX, TY, NT, PF>;
-    v.smem = C::SMEM;
-    v.H = C::H; v.W = C::W; v.HH = C::HH; v.TX = TX; v.TY = TY; v.NT = NT;
-    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, NT, v.smem));
-    VDN_REQUIRE(v.occ >= 1, "k_wave variant does not fit on an SM");
-    return v;
-}
-// [tile cfg][pre][post: 0 -> 0, 1 -> 2 (restrict), 2 -> 3 (norm)]; one GSRB sweep per launch (the operator rings of two
-// sweeps do not fit in 227 KB of shared memory at a useful tile size)
-WaveVariant &wave_get(int cfg, int nsw, int pre, int post)
-{
-    static WaveVariant tab[2][2][3];
-    VDN_REQUIRE(nsw == 1, "k_wave is instantiated for one sweep per launch");
-    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
-    WaveVariant &v = tab[cfg][pre][pi];
-    if (v.fn) return v;
-#define WV(C, TX, TY, NT, PF) \
-    if (cfg == C) { \
-        if (pre == 0 && post == 0) v = wave_variant<1, 0, 0, TX, TY, NT, PF>(); \
-        if (pre == 0 && post == 2) v = wave_variant<1, 0, 2, TX, TY, NT, PF>(); \
-        if (pre == 0 && post == 3) v = wave_variant<1, 0, 3, TX, TY, NT, PF>(); \
-        if (pre == 1 && post == 0) v = wave_variant<1, 1, 0, TX, TY, NT, PF>(); \
-        if (pre == 1 && post == 2) v = wave_variant<1, 1, 2, TX, TY, NT, PF>(); \
-        if (pre == 1 && post == 3) v = wave_variant<1, 1, 3, TX, TY, NT, PF>(); \
-    }
-    WV(0, 32, 16, 512, 2)
-    WV(1, 32, 8, 256, 2)
-#undef WV
-    VDN_REQUIRE(v.fn != nullptr, "no such k_wave variant");
-    return v;
-}
-
-// k_sweep variants: [tile cfg][nsw-1][pre][post index]
-template <int NSW, int PRE, int POST, int TX, int TY, int MINB>
-WaveVariant sweep_variant()
-{
-    using C = SweepCfg<NSW, PRE, POST, TX, TY>;
-    WaveVariant v;
-    v.fn = (const void *)k_sweep<NSW, PRE, POST, TX, TY, MINB>;
-    v.smem = C::SMEM;
-    v.H = C::H; v.W = C::X; v.HH = C::Y; v.TX = TX; v.TY = TY; v.NT = C::NT;
-    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, C::NT, v.smem));
-    VDN_REQUIRE(v.occ >= 1, "k_sweep variant does not fit on an SM");
-    return v;
-}
 constexpr int SWEEP_NCFG = 5;
-WaveVariant &sweep_get(int cfg, int nsw, int pre, int post)
-{
-    static WaveVariant tab[SWEEP_NCFG][2][2][3];
-    VDN_REQUIRE(nsw == 1 || nsw == 2, "k_sweep is instantiated for one or two sweeps per launch");
-    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
-    WaveVariant &v = tab[cfg][nsw - 1][pre][pi];
-    if (v.fn) return v;
-#define SV1(C, NSW, TX, TY, MB) \
-    if (cfg == C && nsw == NSW) { \
-        if (pre == 0 && post == 0) v = sweep_variant<NSW, 0, 0, TX, TY, MB>(); \
-        if (pre == 0 && post == 2) v = sweep_variant<NSW, 0, 2, TX, TY, MB>(); \
-        if (pre == 0 && post == 3) v = sweep_variant<NSW, 0, 3, TX, TY, MB>(); \
-        if (pre == 1 && post == 0) v = sweep_variant<NSW, 1, 0, TX, TY, MB>(); \
-        if (pre == 1 && post == 2) v = sweep_variant<NSW, 1, 2, TX, TY, MB>(); \
-        if (pre == 1 && post == 3) v = sweep_variant<NSW, 1, 3, TX, TY, MB>(); \
-    }
-    SV1(0, 1, 64, 32, 1) SV1(1, 1, 64, 16, 2) SV1(2, 1, 32, 16, 3)
-    SV1(0, 2, 64, 16, 1) SV1(1, 2, 32, 16, 2) SV1(2, 2, 32, 8, 2)
-#undef SV1
-    VDN_REQUIRE(v.fn != nullptr, "no such k_sweep variant");
-    return v;
-}
-
-// k_sweep2 variants (operator data staged through shared memory): [tile cfg][pre][post index], one sweep per launch
-template <int PRE, int POST, int TX, int TY>
-WaveVariant sweep2_variant()
-{
-    using C = Sweep2Cfg<PRE, POST, TX, TY>;
-    WaveVariant v;
-    v.fn = (const void *)k_sweep2<PRE, POST, TX, TY>;
-    v.smem = C::SMEM;
-    v.H = C::H; v.W = C::RX; v.HH = C::RY; v.TX = TX; v.TY = TY; v.NT = C::NT;
-    VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    VDN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.occ, v.fn, C::NT, v.smem));
-    VDN_REQUIRE(v.occ >= 1, "k_sweep2 variant does not fit on an SM");
-    return v;
-}
-WaveVariant &sweep2_get(int cfg, int nsw, int pre, int post)
-{
-    static WaveVariant tab[SWEEP_NCFG][2][3];
-    VDN_REQUIRE(nsw == 1, "k_sweep2 is instantiated for one sweep per launch");
-    const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
-    WaveVariant &v = tab[cfg][pre][pi];
-    if (v.fn) return v;
-#define SV2(C, TX, TY) \
-    if (cfg == C) { \
-        if (pre == 0 && post == 0) v = sweep2_variant<0, 0, TX, TY>(); \
-        if (pre == 0 && post == 2) v = sweep2_variant<0, 2, TX, TY>(); \
-        if (pre == 0 && post == 3) v = sweep2_variant<0, 3, TX, TY>(); \
-        if (pre == 1 && post == 0) v = sweep2_variant<1, 0, TX, TY>(); \
-        if (pre == 1 && post == 2) v = sweep2_variant<1, 2, TX, TY>(); \
-        if (pre == 1 && post == 3) v = sweep2_variant<1, 3, TX, TY>(); \
-    }
-    SV2(0, 64, 16) SV2(1, 32, 32) SV2(2, 32, 16)
-#undef SV2
-    VDN_REQUIRE(v.fn != nullptr, "no such k_sweep2 variant");
-    return v;
-}
 
 // k_sweep3 variants (one column of cell pairs per thread, register-pipelined operator data): [tile cfg][pre][post index]
 template <int PRE, int POST, int TX, int TY>
@@ -597,10 +471,9 @@ WaveVariant sweep3_variant()
     VDN_REQUIRE(v.occ >= 1, "k_sweep3 variant does not fit on an SM");
     return v;
 }
-WaveVariant &sweep3_get(int cfg, int nsw, int pre, int post)
+WaveVariant &sweep3_get(int cfg, int pre, int post)
 {
     static WaveVariant tab[SWEEP_NCFG][2][3];
-    VDN_REQUIRE(nsw == 1, "k_sweep3 is instantiated for one sweep per launch");
     const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
     WaveVariant &v = tab[cfg][pre][pi];
     if (v.fn) return v;
@@ -619,29 +492,25 @@ WaveVariant &sweep3_get(int cfg, int nsw, int pre, int post)
     return v;
 }
 
-// one fused launch on level l: nsw sweeps reading L.phi, writing L.res; then the two buffers swap roles
-void wave_launch(vdn_ctx *c, MG *m, int l, int nsw, int pre, int post)
+// one fused launch on level l: one sweep reading L.phi, writing L.res; then the two buffers swap roles
+void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
 {
     Lev &L = m->L[l];
+    const int nsw = 1;
     // pick tile shape and z-chunking: cost ~ waves * CTAs sharing an SM * iterations * plane cells
     int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
-    const int kind = m->fuse_kind;
-    auto variant = [&](int cfg) -> const WaveVariant & {
-        return kind == 4 ? sweep3_get(cfg, nsw, pre, post) : kind == 3 ? sweep2_get(cfg, nsw, pre, post) : kind == 2 ? sweep_get(cfg, nsw, pre, post) : wave_get(cfg, nsw, pre, post);
-    };
-    for (int cfg = 0; cfg < (kind >= 2 ? SWEEP_NCFG : 2); ++cfg) {
+    auto variant = [&](int cfg) -> const WaveVariant & { return sweep3_get(cfg, pre, post); };
+    for (int cfg = 0; cfg < SWEEP_NCFG; ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
-        // measured defaults (profiles/r01_bench_256_v3_* / _v5_*): k_sweep / k_sweep2: the largest tile on every level; k_sweep3: 32x24 (640 threads,
-        // 96 registers) for the plain / prolongating sweeps of the finest level and for sweep + norm, 64x16 for the plain sweeps of smaller
-        // levels, 32x16 for sweep + residual + restriction (an 864-thread 64x16 CTA is capped at 72 registers and spills)
-        if (m->tile_force < 0 && (kind == 2 || kind == 3) && cfg != 0) continue;
-        if (m->tile_force < 0 && kind == 4 && cfg != (post == 2 ? 2 : (post == 3 || L.n[0] >= 256) ? 4 : 1)) continue;
+        // measured defaults (profiles/r01_bench_256_v5_*): 32x24 (640 threads, 96 registers) for the plain / prolongating sweeps of the finest
+        // level and for sweep + norm, 64x16 for the plain sweeps of smaller levels, 32x16 for sweep + residual + restriction (an 864-thread
+        // 64x16 CTA is capped at 72 registers and spills)
+        if (m->tile_force < 0 && cfg != (post == 2 ? 2 : (post == 3 || L.n[0] >= 256) ? 4 : 1)) continue;
         const WaveVariant &v = variant(cfg);
         const long ntiles = (long)cdiv(L.n[0], v.TX) * cdiv(L.n[1], v.TY);
         const long slots = (long)m->sm_count * v.occ;
         for (int nz = 1; nz <= std::max(1, L.n[2] / 8); ++nz) {
-            int ch = (cdiv(L.n[2], nz) + 1) & ~1;
-            if (m->zchunk_force > 0) ch = m->zchunk_force & ~1;
+            const int ch = (cdiv(L.n[2], nz) + 1) & ~1;
             const long ctas = ntiles * cdiv(L.n[2], ch);
             const long waves = (ctas + slots - 1) / slots;
             const long per_sm = std::min<long>(v.occ, (ctas + m->sm_count - 1) / m->sm_count);
@@ -707,7 +576,7 @@ void vcycle(vdn_ctx *c, MG *m, int l)
     }
     Lev &C = m->L[l + 1];
     if (l < m->nfused) {
-        // fused wavefront path: [sweeps ... + residual + restriction] -> coarse -> [prolongation + sweeps ... (+ norm)]
+        // fused path: [sweeps ... + residual + restriction] -> coarse -> [prolongation + sweeps ... (+ norm)]
         auto coarse = [&]() {
             if (m->coarse_graph && l + 1 == m->graph_level) {
                 LaunchScope ls(c, "mg_coarse_levels_graph", 0.0, m->coarse_graph_launches);
@@ -716,12 +585,12 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         };
         if (l > 0) mg_halo_deep(c, m, L, L.rhs, MG_PAD);        // restricted by the level above: valid cells only
         int rem = c->prm.mg_nu1;
-        while (rem > 0) { const int nsw = std::min(m->fuse_nsw, rem); rem -= nsw; wave_launch(c, m, l, nsw, 0, rem == 0 ? 2 : 0); }
+        while (rem > 0) { --rem; wave_launch(c, m, l, 0, rem == 0 ? 2 : 0); }
         coarse();
         mg_halo_deep(c, m, C, C.phi, 2);                        // the prolongation under 3 fine ghost layers reads 2 coarse ones
         rem = c->prm.mg_nu2;
         bool first = true;
-        while (rem > 0) { const int nsw = std::min(m->fuse_nsw, rem); rem -= nsw; wave_launch(c, m, l, nsw, first ? 1 : 0, (rem == 0 && l == 0) ? 3 : 0); first = false; }
+        while (rem > 0) { --rem; wave_launch(c, m, l, first ? 1 : 0, (rem == 0 && l == 0) ? 3 : 0); first = false; }
         return;
     }
     smooth(c, m, l, c->prm.mg_nu1);

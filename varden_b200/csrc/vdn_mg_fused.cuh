@@ -1,29 +1,82 @@
-// vdn_mg_sweep3.cuh -- k_sweep3: the fused red-black smoother with ONE column of cell pairs per thread and the operator data
-// of the leading stage software-pipelined through registers.
+// vdn_mg_fused.cuh -- k_sweep3: the fused red-black multigrid smoother (included by vdn_mg.cu; also compiled as plain C++ by
+// tests/emu/, where one OS thread plays each CUDA thread, so the kernel logic runs in the CPU-only test tier).
 //
-// Lessons of the two earlier kernels (profiles/r01_ncu_full_ksweep_v3.txt, r01_ncu_full_ksweep2_v4.txt):
-//   k_sweep  (2x2 columns per thread, operator data loaded where used): 20 warps/SM, 4.6 of 11 stall cycles per issue are
-//            long-scoreboard waits -- both colour stages of a step wait for their global loads --, half of the shared-memory
-//            wavefronts are 2-way bank conflicts of the strided pair layout;
-//   k_sweep2 (operator data staged in shared memory by cp.async): the global latency is gone but 185-222 KB of shared memory
-//            leave 11 warps/SM, which cannot cover shared-memory and FP64 dependency latencies (31 % issue utilisation).
-// Here a thread owns the two cells (x, 2j) and (x, 2j+1) of a column pair: one is red, one is black, so every thread has
-// exactly ONE active cell per step and runs all colour stages on it (stage s on plane t-s; z-neighbours in program order,
-// x/y-neighbours written one step earlier -> one barrier per plane, as in k_sweep).  Consecutive lanes are consecutive x:
-// global accesses are coalesced 8-byte words, shared-memory rows are read conflict-free (the two interleaved rows of a warp
-// fall into disjoint banks).  A 32x32 core tile needs 648 threads and 41 KB: 21 warps per SM.  The operator data of stage 0
-// of step t+1 (new lines, HBM latency) is loaded into registers at the top of step t; stage 1 (and the residual stage) read
-// lines that were streamed one (two) steps earlier and are L1/L2-resident; both are issued before the phi traffic of the step.
+// One launch applies a full red-black Gauss-Seidel sweep (S = 2 colour stages) to a whole level while phi streams through
+// shared memory ONCE (input array -> output array, ping-pong), with
+//   PRE  = 1 : prolongation of the coarse correction added as a plane lands (k_prolong fused),
+//   POST = 2 : residual of the finished plane averaged 2x2x2 into the coarse right-hand side, coarse phi zeroed
+//              (k_residual + k_restrict fused; the fine residual is never stored),
+//   POST = 3 : inf-norm of the residual reduced (the convergence test of the V-cycle, one atomic per CTA).
+// A CTA owns a (TX x TY) tile of columns plus a halo of H cells and marches along z; in step t colour stage s relaxes plane
+// t-s, so every stage sees exactly the neighbour values the plain sweep order gives it; halo cells (and, between ranks, the
+// neighbour's cells held in the level's ghost layers, M_GHOST) are relaxed redundantly; periodic directions wrap by index.
+// After the last (black) stage the residual of the black cells is zero to round-off -- a cell that was just relaxed satisfies
+// its equation when its neighbours no longer change -- so the residual stage visits red cells only.
+// HBM traffic per launch: phi in + out, rhs, 3 face-coefficient arrays = 48 B/cell (x tile halo) for two colour stages +
+// residual + transfer operator, against 48 B/cell for EVERY colour stage (and again for the residual) of the plain kernels.
+//
+// Thread mapping (third generation; the captures that led here are profiles/r01_ncu_full_wave_v2 / _ksweep_v3 / _ksweep2_v4):
+// a thread owns the two cells (x, 2j) and (x, 2j+1) of a column pair: one is red, one is black, so every thread has exactly
+// ONE active cell per step and runs all colour stages on it (z-neighbours in program order, x/y-neighbours written one step
+// earlier -> one barrier per plane).  Consecutive lanes are consecutive x: global accesses are coalesced 8-byte words,
+// shared-memory rows are read conflict-free.  The operator data of stage 0 of step t+1 (new lines, HBM latency) is loaded
+// into registers at the top of step t; stage 1 (and the residual stage) read lines that were streamed one (two) steps earlier
+// and are L1/L2-resident; both are issued before the phi traffic of the step.
 #pragma once
-#include "vdn_mg_sweep.cuh"
+
+enum : int { M_GHOST = 0, M_NEU = 1, M_DIR = 2, M_WRAP = 3 };
+
+struct WaveArgs {
+    int n[3]; long s1, s2, off;
+    double h2[3]; int mode[3][2]; int par0;
+    const double *rhs, *b0, *b1, *b2;
+    const double *in; double *out;
+    const double *cphi; double *crhs, *czero; long cs1, cs2, coff;   // coarse level (PRE / POST == 2)
+    double *nrm;
+    int zchunk;
+};
+
+
+// index of a tile cell in the level arrays, or WAVE_NONE.  Cells that take part in the relaxation: the level's own cells,
+// periodic images (M_WRAP, wrap by index) and neighbour-rank cells held in the level's ghost layers (M_GHOST) ...
+constexpr int WAVE_NONE = -(1 << 28);
+template <int H>
+__device__ __forceinline__ int wave_idx(int g, int n, int mlo, int mhi)
+{
+    if (g < 0) { if (g < -H) return WAVE_NONE; return mlo == M_WRAP ? g + n : (mlo == M_GHOST ? g : WAVE_NONE); }
+    if (g >= n) { if (g >= n + H) return WAVE_NONE; return mhi == M_WRAP ? g - n : (mhi == M_GHOST ? g : WAVE_NONE); }
+    return g;
+}
+// A*phi contribution and diagonal of one direction (same face formulas as cell_op in vdn_mg.cu)
+__device__ __forceinline__ void wave_dir(double blo, double bhi, double h2, double p0, double pm, double pp,
+                                         bool atlo, bool athi, int mlo, int mhi, double &a, double &g)
+{
+    if (atlo && mlo == M_NEU) { }
+    else if (atlo && mlo == M_DIR) { a += blo * (3.0 * p0 - pp * (1.0 / 3.0)) * h2; g += 3.0 * blo * h2; }
+    else { a += blo * (p0 - pm) * h2; g += blo * h2; }
+    if (athi && mhi == M_NEU) { }
+    else if (athi && mhi == M_DIR) { a += bhi * (3.0 * p0 - pm * (1.0 / 3.0)) * h2; g += 3.0 * bhi * h2; }
+    else { a += bhi * (p0 - pp) * h2; g += bhi * h2; }
+}
+
+// relaxation operands of one cell: phi neighbours from the shared-memory ring, operator data in registers
+struct SweepCoef { double rhs, xl, xh, yl, yh, zl, zh; };
+
+__device__ __forceinline__ void sweep_load(SweepCoef &c, const WaveArgs &a, long g)
+{
+    c.rhs = __ldg(a.rhs + g);
+    c.xl = __ldg(a.b0 + g); c.xh = __ldg(a.b0 + g + 1);
+    c.yl = __ldg(a.b1 + g); c.yh = __ldg(a.b1 + g + a.s1);
+    c.zl = __ldg(a.b2 + g); c.zh = __ldg(a.b2 + g + a.s2);
+}
 
 #ifdef VDN_EMU
-inline double emu_shfl_buf[2048];
+inline double emu_xor_buf[2048];
 inline double __shfl_xor_sync(unsigned, double v, int m)
 {
-    emu_shfl_buf[threadIdx.x] = v;
+    emu_xor_buf[threadIdx.x] = v;
     __syncthreads();
-    const double r = emu_shfl_buf[threadIdx.x ^ m];
+    const double r = emu_xor_buf[threadIdx.x ^ m];
     __syncthreads();
     return r;
 }

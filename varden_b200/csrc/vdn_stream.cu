@@ -384,6 +384,7 @@ void st_mkumac(vdn_ctx *c)
 // then z over the x,y-ghosted range) so that edge and corner ghost cells receive the diagonal images.
 void st_fill_boundary(vdn_ctx *c, int field)
 {
+    ctx_require_comm(c);
     DField &f = c->f[field];
     if (f.ng == 0) return;
     const Geo &g = c->geo;
