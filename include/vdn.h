@@ -92,6 +92,8 @@ const char *vdn_last_error(const vdn_ctx *ctx);   /* ctx may be NULL: last creat
  */
 int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *region_lo, const int *region_hi,
                      const void *nccl_unique_id);
+/* CUDA devices visible to this process (the Fortran shim maps MPI rank -> device = rank mod count); 0 when there is none */
+int vdn_device_count(void);
 /* rank 0 creates the 128-byte id (ncclGetUniqueId) that the caller broadcasts to every rank */
 int vdn_nccl_unique_id(void *out128);
 /* host-only: neighbour ranks nbr[3][2] (-1 = physical boundary, own rank = periodic self-wrap), process grid and this

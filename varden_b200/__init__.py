@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
-    "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune",
+    "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune", "vdn_device_count",
 ]
 
 

@@ -367,6 +367,7 @@ int vdn_ctx_create(const vdn_params *prm, int dim, int nboxes, const int *box_lo
     catch (const std::exception &e) { g_create_err = e.what(); ctx_free(c); return 1; }
 }
 void vdn_ctx_destroy(vdn_ctx *ctx) { ctx_free(ctx); }
+int vdn_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 const char *vdn_last_error(const vdn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int vdn_field_upload(vdn_ctx *ctx, int field, int ibox, const double *host, int ng, int ncomp)
