@@ -2,16 +2,21 @@
 """
 bench.py -- throughput of the VARDEN advection + MAC-projection hot path on B200.
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 256] [--ratio 2]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 3|2|4|5] [--ratio R]
 
 A "step" is one pass of the path advance_timestep.f90:95-124 (advance_premac -> macproject -> scalar_advance ->
 make_at_halftime -> velocity_advance) over the synthetic density-stratified Rayleigh-Taylor state of SURVEY 8(d).
-N=1 workload = BASELINE.json configs[1]: 3-D 256^3 single level, density ratio 2:1, FP64, one B200.
+Default workload at EVERY N = BASELINE.json configs[2], the configuration the metric / north_star target is quoted on:
+3-D 512^3 single level, eight 256^3 reference boxes (max_grid_size = 256, initialize.f90:199), STRONG scaling: 8/4/2/1 boxes per
+GPU at 1/2/4/8 GPUs (it fits one B200).  --config 2: 256^3 on one GPU / one 256^3 box per GPU (weak); --config 4: 512^3 per GPU (weak,
+1024^3 on 8); --config 5: config 3 at density ratio 1000:1.
 Metric = Gcell-updates/s (cells x steps / device time).  Prints ONE JSON line (see the task contract) with
   value     : inputs resident in HBM, device time by CUDA events on the library's stream (max over ranks)
   e2e       : through the C ABI from pinned HOST buffers: H2D of uold/sold/gp/ext forces + step + D2H of unew/snew/rhohalf
   roofline  : dominant kernel family: algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (C restatement, OpenMP, all host cores) on a bounded sample of the same workload
+  phases    : device ms per step of the reference's own timers (advance_timestep.f90:160-164): MAC / Scalar / Velocity
+  nvlink    : bytes this step sent to other ranks / (900 GB/s per direction per GPU) vs the time the exchanges took
+  cpu_baseline : the CPU oracle (C restatement, OpenMP, all host cores, -O3 -march=native timing build) on a bounded sample
 --impl reference times that CPU restatement alone (the reference Fortran cannot be built here: no Fortran compiler,
 FBoxLib absent) and prints the same line with "impl": "reference".
 """
@@ -83,12 +88,21 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 class CpuOracle:
-    """the CPU oracle (C/OpenMP restatement of the reference loops, all host cores) on a bounded sample: the same RT problem at n_sample^3"""
+    """the CPU oracle (C/OpenMP restatement of the reference loops, all host cores, timing build: -O3 -march=native, contraction on)
+    on a bounded sample: the same RT problem at n_sample^3 (one 256^3 reference box of the workload by default)"""
 
     def __init__(self, n_sample, ratio):
         from oracle import oracle as O
         self.O = O
+        self.threads = O.use_timing_build(host_cores())      # sets the OpenMP thread count explicitly (torchrun exports OMP_NUM_THREADS=1)
         self.geom, self.P, self.st, self.dt = O.rt_state(n_sample, dim=3, max_grid_size=256, ratio=ratio)
         self.cycles = 0
 
@@ -99,26 +113,46 @@ class CpuOracle:
         return time.perf_counter() - t0
 
 
+def workload(args, world):
+    """(cells per direction of a reference box, global grid, scaling, density ratio, label) of the selected BASELINE config"""
+    cfg = args.config
+    ratio = args.ratio if args.ratio else (1000.0 if cfg == 5 else 2.0)
+    n = args.n
+    pgrid = {1: [1, 1, 1], 2: [1, 1, 2], 4: [1, 2, 2], 8: [2, 2, 2]}.get(world)
+    if pgrid is None:
+        raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
+    if cfg in (3, 5):
+        g = args.global_n or 2 * n
+        return n, [g] * 3, "strong", ratio, pgrid, "BASELINE configs[%d]: 3D %d^3 single-level, %d^3 reference boxes, strong scaling" % (cfg - 1, g, n)
+    if cfg == 2:
+        return n, [n * pgrid[d] for d in range(3)], "weak", ratio, pgrid, "BASELINE configs[1]: 3D %d^3 per GPU (one reference box), weak scaling" % n
+    if cfg == 4:
+        return n, [2 * n * pgrid[d] for d in range(3)], "weak", ratio, pgrid, "BASELINE configs[3]: 3D %d^3 per GPU (eight %d^3 boxes), weak scaling" % (2 * n, n)
+    raise SystemExit("bench.py: --config must be 2, 3, 4 or 5")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    n, nglob, scaling, ratio, pgrid, label = workload(args, max(world, 1) if world in (1, 2, 4, 8) else 1)
     ns = args.cpu_n
-    cpu = CpuOracle(ns, args.ratio)
-    for _ in range(max(args.warmup, 1)):
+    cpu = CpuOracle(ns, ratio)
+    for _ in range(max(min(args.warmup, 1), 1)):
         cpu.step()                                  # untimed: page-in, thread pool
     times = [cpu.step() for _ in range(args.steps)]
     t_tot = sum(times)
     value = cpu.geom.ncells * args.steps / t_tot / 1e9
-    sample = "same RT problem at %d^3 (one pass per step, %.1f s each), %d V-cycles" % (ns, t_tot / max(args.steps, 1), cpu.cycles)
+    same = [ns] * 3 == list(nglob)
+    sample = "same RT problem at %d^3 = %s of the %dx%dx%d workload (one pass per step, %.1f s each), %d V-cycles" % (
+        ns, "all" if same else "1/%d" % round(nglob[0] * nglob[1] * nglob[2] / ns ** 3), nglob[0], nglob[1], nglob[2], t_tot / max(args.steps, 1), cpu.cycles)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D %d^3 single-level RT ratio %g:1 (bounded CPU sample %d^3)" % (args.n, args.ratio, ns)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample + "; C/OpenMP restatement of the reference loops (oracle/), not the Fortran binary"},
+            "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "same_config": same,
+            "config": {"workload": label + " (RT ratio %g:1); CPU arm on a bounded sample: %d^3" % (ratio, ns)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port",
+                             "sample": sample + "; C/OpenMP restatement of the reference loops (oracle/, -O3 -march=native build), not the Fortran binary"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -129,16 +163,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=256, help="cells per direction of the N=1 workload")
-    ap.add_argument("--ratio", type=float, default=2.0)
-    ap.add_argument("--cpu-n", type=int, default=192, help="grid size of the bounded CPU sample (192^3: a few seconds per pass on the box's host cores)")
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json config: 3 (default: 512^3 strong scaling, eight 256^3 boxes), 2 (256^3 per GPU, weak), "
+                                                          "4 (512^3 per GPU, weak), 5 (config 3 at ratio 1000:1)")
+    ap.add_argument("--n", type=int, default=256, help="cells per direction of a reference box (max_grid_size)")
+    ap.add_argument("--ratio", type=float, default=0.0, help="density ratio (default 2, config 5: 1000)")
+    ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU sample (256^3 = one reference box: a few seconds per pass)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--max-grid-size", type=int, default=256)
-    ap.add_argument("--global-n", type=int, default=0,
-                    help="STRONG scaling (BASELINE config 3): a fixed global grid of this many cells per direction, chopped into --n^3 reference "
-                         "boxes that are divided among the GPUs (512: 8 boxes of 256^3 -> 8/4/2/1 boxes per GPU at 1/2/4/8 GPUs); default 0 = weak "
-                         "scaling, one --n^3 box per GPU")
+    ap.add_argument("--global-n", type=int, default=0, help="configs 3/5: global cells per direction (default 2 x --n)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -163,19 +195,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # weak scaling: one 256^3 reference box (max_grid_size = 256, _parameters:27) per GPU; the process grid fills z, y, x
-    n = args.n
-    pgrid = {1: [1, 1, 1], 2: [1, 1, 2], 4: [1, 2, 2], 8: [2, 2, 2]}.get(world)
-    if pgrid is None:
-        raise SystemExit("bench.py: --gpus must be 1, 2, 4 or 8")
-    nglob = [n * pgrid[d] for d in range(3)]
-    scaling = "weak"
-    if args.global_n:
-        if args.global_n % n != 0 or any((args.global_n // n) % pgrid[d] for d in range(3)):
-            raise SystemExit("bench.py: --global-n must be a multiple of --n that the process grid %s divides" % pgrid)
-        nglob, scaling = [args.global_n] * 3, "strong"
+    n, nglob, scaling, ratio, pgrid, label = workload(args, world)
+    if any(nglob[d] % (n * pgrid[d]) for d in range(3)):
+        raise SystemExit("bench.py: the process grid %s does not divide the %s grid of %d^3 boxes" % (pgrid, nglob, n))
+    args.ratio = ratio
     phi = [float(nglob[d]) / n for d in range(3)]            # domain [0, nglob/n]^3: dx = 1/n in every configuration
-    mgs = min(args.max_grid_size, n)
+    mgs = n
     from varden_b200.problems import Geom, PERIODIC, NO_SLIP_WALL
     from varden_b200 import parallel as PAR
     gfull = Geom(3, nglob, [[PERIODIC, PERIODIC], [PERIODIC, PERIODIC], [NO_SLIP_WALL, NO_SLIP_WALL]],
@@ -233,6 +258,7 @@ def main():
     ctx.sync()
     ctx.prof_enable(True)
     l0 = ctx.launch_count()
+    cb0 = ctx.comm_bytes()
     sampler = ClockSampler(local); sampler.start()
     xs = torch.cuda.ExternalStream(ctx.stream_ptr())        # the library's launching stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -262,11 +288,14 @@ def main():
     launches = ctx.launch_count() - l0
     prof = ctx.prof_report()
     ctx.prof_enable(False)
+    phases = {k[6:]: v["ms"] / args.steps for k, v in prof.items() if k.startswith("phase:")}
+    prof = {k: v for k, v in prof.items() if not k.startswith("phase:")}
     dev_ms = sum(p["ms"] for p in prof.values())
     # one in-order stream; the host only syncs for the per-V-cycle residual norm, so event time ~ host wall time
     ms_per_step = 1e3 * wall / args.steps
     value = ncells_global * args.steps / wall / 1e9
 
+    comm_bytes = (ctx.comm_bytes() - cb0) / args.steps
     # ---- e2e timing (host buffers, copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
@@ -322,23 +351,31 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
         co = CpuOracle(args.cpu_n, args.ratio)
         co.step()                                   # untimed: page-in, thread pool
         t = co.step()
-        cpu = {"value": co.geom.ncells / t / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "same RT problem at %d^3, one pass (%.1f s, %d V-cycles); C/OpenMP restatement of the reference loops, not the Fortran binary"
-                         % (args.cpu_n, t, co.cycles)}
+        cpu = {"value": co.geom.ncells / t / 1e9, "unit": UNIT, "cores": co.threads, "kind": "port",
+               "sample": "same RT problem at %d^3 (1/%d of the workload), one pass (%.1f s, %d V-cycles); C/OpenMP restatement of the reference loops "
+                         "(-O3 -march=native build), not the Fortran binary" % (args.cpu_n, round(ncells_global / args.cpu_n ** 3), t, co.cycles)}
+    # NVLink: what this rank sent to other ranks per step against 900 GB/s per direction per GPU, and against the time the exchanges took
+    nvlink = None
+    if world > 1:
+        t_x = sum(fam[k]["ms_total"] for k in fam if k in ("mg_halo_exchange", "halo_exchange", "mg_agglomerate")) / args.steps
+        nvlink = {"bytes_sent_per_step_per_gpu": comm_bytes, "peak_gbs_per_direction": 900.0, "wire_ms_at_peak": comm_bytes / 900e9 * 1e3,
+                  "exchange_ms_per_step": t_x, "achieved_gbs": (comm_bytes / 1e9) / (t_x / 1e3) if t_x > 0 else None,
+                  "frac": (comm_bytes / 900e9 * 1e3) / t_x if t_x > 0 else None,
+                  "note": "latency-bound: the exchanges move surface data only; frac = wire time at peak / measured exchange time"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D %d^3 single-level variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, "
-                                   "MAC rel tol 1e-10, %d reference box(es) of %d^3 per GPU, global %dx%dx%d" % (n, args.ratio, geom.nboxes, n, nglob[0], nglob[1], nglob[2]),
+            "config": {"workload": label + "; variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, MAC rel tol 1e-10, "
+                                   "%d reference box(es) of %d^3 per GPU, global %dx%dx%d; the same input state every step" % (args.ratio, geom.nboxes, n, nglob[0], nglob[1], nglob[2]),
                        "parallelism": "1 region per GPU, process grid %s, NCCL halo + allreduce, coarse MG levels agglomerated" % pgrid if world > 1 else "single GPU",
-                       "l2_policy": "inputs (%.1f GB of fields) exceed the 126 MB L2; no explicit flush" % (45 * 8 * (n + 6) ** 3 / 1e9),
+                       "l2_policy": "inputs (%.1f GB of fields per GPU) exceed the 126 MB L2; no explicit flush" % (45 * 8 * geom.nboxes * (n + 6) ** 3 / 1e9),
                        "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
                        "host_wall_ms_per_step": 1e3 * wall_host / args.steps},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "phases_ms_per_step": phases, "nvlink": nvlink,
             "kernels": fam}
     if rank == 0:
         print(json.dumps(line))

@@ -180,6 +180,7 @@ int vdn_prof_count(vdn_ctx *ctx);                 /* number of kernel families s
 /* name (<=63 chars), launches, total device ms, algorithmic bytes (SURVEY 8(a) figure x cells) */
 int vdn_prof_get(vdn_ctx *ctx, int idx, char *name, long long *launches, double *ms, double *alg_bytes);
 long long vdn_launch_count(vdn_ctx *ctx);         /* kernels launched since creation */
+long long vdn_comm_bytes(vdn_ctx *ctx);           /* bytes this rank sent to other ranks over NVLink since creation (halo exchanges, all-gathers) */
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,24 @@ def build(force=False):
 
 
 _lib = None
+_timing = False
+
+
+def use_timing_build(threads=None):
+    """bench.py only: load the -O3 -march=native build (compiled HERE, on the machine that runs it) instead of the parity build, and
+    set the OpenMP thread count explicitly (torchrun exports OMP_NUM_THREADS=1).  Must be called before the first lib() use."""
+    global _lib, _timing
+    assert _lib is None, "use_timing_build must come before the first oracle call"
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    # always rebuilt: -march=native must match the machine that runs it, and a snapshot may carry a build from another host
+    subprocess.check_call(["make", "-B", "-C", _HERE, "fast"], stdout=subprocess.DEVNULL)
+    _lib = C.CDLL(os.path.join(_HERE, "_fast", "liboracle_fast.so"))
+    _timing = True
+    if threads:
+        _lib.orc_set_threads(int(threads))
+    return int(_lib.orc_get_threads())
+
 
 
 def lib():

@@ -385,3 +385,13 @@ int orc_advance_mf(const orc_geom *g, const orc_params *P, double **uold, double
     for (int d = 0; d < dim; ++d) { mf_free(g, sedge[d]); mf_free(g, sflux[d]); mf_free(g, uedge[d]); mf_free(g, uflux[d]); }
     return cycles;
 }
+
+/* thread control for the timing runs (bench.py): torchrun exports OMP_NUM_THREADS=1, which libgomp reads at load time */
+#ifdef _OPENMP
+#include <omp.h>
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_get_threads(void) { return omp_get_max_threads(); }
+#else
+void orc_set_threads(int n) { (void)n; }
+int orc_get_threads(void) { return 1; }
+#endif

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
-    "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune", "vdn_device_count",
+    "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune", "vdn_device_count", "vdn_comm_bytes",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library():
         _lib = C.CDLL(os.environ.get("VDN_LIB", LIB_PATH))      # VDN_LIB: a differently tuned build of the same library (kernel tuning runs)
         _lib.vdn_last_error.restype = C.c_char_p
         _lib.vdn_launch_count.restype = C.c_longlong
+        _lib.vdn_comm_bytes.restype = C.c_longlong
         _lib.vdn_get_stream.restype = C.c_void_p
     return _lib
 
@@ -263,3 +264,6 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.vdn_launch_count(self.h))
+
+    def comm_bytes(self):
+        return int(self.lib.vdn_comm_bytes(self.h))

@@ -165,6 +165,7 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fd
     }
     if (ps.nseg == 0) return;
     ensure_buf(c, (size_t)std::max(soff, roff));
+    c->comm_bytes += 8LL * soff;
     ps.buf = cm->sbuf; pu.buf = cm->rbuf;
     launch_pack(c, ps);
     VDN_NCCL(ncclGroupStart());
@@ -259,6 +260,7 @@ void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask
         sg.off = roff; pu.seg[pu.nseg++] = sg; recvs.push_back({ rpeer[q], roff, cnt }); roff += cnt;
     }
     ensure_buf(c, (size_t)std::max(soff, roff));
+    c->comm_bytes += 8LL * soff;
     ps.buf = cm->sbuf; pu.buf = cm->rbuf;
     launch_pack(c, ps);
     VDN_NCCL(ncclGroupStart());
@@ -298,6 +300,7 @@ bool comm_has_neighbor(const vdn_ctx *c, int d, int s) { return c->comm && c->co
 // all-gather equal-sized blocks (count doubles per rank): send -> recv[nranks*count]
 void comm_allgather(vdn_ctx *c, const double *send, double *recv, size_t count)
 {
+    c->comm_bytes += 8LL * (long long)count * (c->comm->nranks - 1);
     VDN_NCCL(ncclAllGather(send, recv, count, ncclDouble, c->comm->nccl, c->stream));
 }
 // coordinates of rank r in the process grid

@@ -307,33 +307,50 @@ static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles,
     // advance_timestep.f90:76-77 builds umac = 1.d20 every step; here the 1.d20 poison is set once at context creation:
     // the only faces that keep it (ghost faces outside non-periodic boundaries) are never written afterwards.
     // advance_premac (advance_premac.f90:44-51)
-    io_need(c, VDN_EXT_VEL_FORCE); io_need(c, VDN_GP); io_need(c, VDN_SOLD);
-    if (c->hio && c->hio->lapu) io_need(c, VDN_LAPU);
-    st_mkvelforce(c, VDN_SOLD, 1.0);
-    io_need(c, VDN_UOLD);
-    st_velpred(c, dt);
-    if (c->hio && c->hio->mac_rhs) io_need(c, VDN_MAC_RHS);
-    // macproject (macproject.f90:20-133)
-    st_divumac(c, false);
-    st_mk_mac_coeffs(c);
-    st_setval(c, VDN_PHI, 0.0);
-    int rc = st_mac_solve(c, mac_rel_eps > 0 ? mac_rel_eps : 1.0e-10, -1.0, cycles, resnorm);
-    st_mkumac(c);
-    // scalar_advance (scalar_advance.f90:96-119)
-    io_need(c, VDN_EXT_SCAL_FORCE);
-    st_mkscalforce(c, 1.0);
-    st_mkflux(c, 0, dt);
-    st_mkscalforce(c, 0.0);
-    st_update(c, 0, dt);
+    // phase brackets = the reference's own timers (advance_timestep.f90:97-131, printed at :160-164)
+    int rc;
+    {
+        LaunchScope ph(c, "phase:advance_premac", 0.0, 0);
+        io_need(c, VDN_EXT_VEL_FORCE); io_need(c, VDN_GP); io_need(c, VDN_SOLD);
+        if (c->hio && c->hio->lapu) io_need(c, VDN_LAPU);
+        st_mkvelforce(c, VDN_SOLD, 1.0);
+        io_need(c, VDN_UOLD);
+        st_velpred(c, dt);
+    }
+    {
+        // macproject (macproject.f90:20-133)
+        LaunchScope ph(c, "phase:MAC_Project", 0.0, 0);
+        if (c->hio && c->hio->mac_rhs) io_need(c, VDN_MAC_RHS);
+        st_divumac(c, false);
+        st_mk_mac_coeffs(c);
+        st_setval(c, VDN_PHI, 0.0);
+        rc = st_mac_solve(c, mac_rel_eps > 0 ? mac_rel_eps : 1.0e-10, -1.0, cycles, resnorm);
+        st_mkumac(c);
+    }
+    {
+        // scalar_advance (scalar_advance.f90:96-119)
+        LaunchScope ph(c, "phase:Scalar_update", 0.0, 0);
+        io_need(c, VDN_EXT_SCAL_FORCE);
+        st_mkscalforce(c, 1.0);
+        st_mkflux(c, 0, dt);
+        st_mkscalforce(c, 0.0);
+        st_update(c, 0, dt);
+    }
     if (c->hio) io_final(c, VDN_SNEW, c->hio->snew);
-    // make_at_halftime (advance_timestep.f90:114)
-    st_make_at_halftime(c);
+    {
+        // make_at_halftime (advance_timestep.f90:114)
+        LaunchScope ph(c, "phase:make_at_halftime", 0.0, 0);
+        st_make_at_halftime(c);
+    }
     if (c->hio) io_final(c, VDN_RHOHALF, c->hio->rhohalf);
-    // velocity_advance (velocity_advance.f90:70-93)
-    st_mkvelforce(c, VDN_SOLD, 1.0);
-    st_mkflux(c, 1, dt);
-    st_mkvelforce(c, VDN_RHOHALF, 0.0);
-    st_update(c, 1, dt);
+    {
+        // velocity_advance (velocity_advance.f90:70-93)
+        LaunchScope ph(c, "phase:Velocity_update", 0.0, 0);
+        st_mkvelforce(c, VDN_SOLD, 1.0);
+        st_mkflux(c, 1, dt);
+        st_mkvelforce(c, VDN_RHOHALF, 0.0);
+        st_update(c, 1, dt);
+    }
     if (c->hio) io_final(c, VDN_UNEW, c->hio->unew);
     if (rc != 0) throw VdnError("MAC multigrid did not converge within mg_max_cycles");
 }
@@ -485,5 +502,6 @@ int vdn_prof_get(vdn_ctx *ctx, int idx, char *name, long long *launches, double 
     return 0;
 }
 long long vdn_launch_count(vdn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+long long vdn_comm_bytes(vdn_ctx *ctx) { return ctx ? ctx->comm_bytes : 0; }
 
 } // extern "C"

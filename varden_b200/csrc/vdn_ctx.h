@@ -36,6 +36,7 @@ struct vdn_ctx {
     double *stage = nullptr; size_t stage_bytes = 0;    // pinned staging buffer for pageable uploads
     std::string err;
     long long launches = 0;
+    long long comm_bytes = 0;                           // bytes this rank sent to other ranks (halo exchanges, all-gathers) since creation
     bool prof_on = false;
     std::vector<ProfEntry> prof;
     std::map<std::string, int> prof_idx;
