@@ -101,6 +101,11 @@ int vdn_nccl_unique_id(void *out128);
 int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo, const int *region_hi,
                   const int *dom_lo, const int *dom_hi, const int *phys_bc, int *nbr, int *pgrid, int *pcoord);
 
+/* host-only: the general exchange plan (cell- or face-centred arrays, multigrid level arrays with carry_n = 1); recv_shift: peer index = my
+ * index + shift for every received box (what the peer-memory transport reads); see vdn_comm.cu */
+int vdn_halo_plan_ex(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng,
+                     int dmask, int nodal, int carry_n,
+                     int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n, int *recv_shift);
 /* host-only: message plan of the single-phase ghost-layer exchange of the multigrid level arrays (faces, edges and corners to the
  * up-to-26 neighbour ranks in one NCCL group).  Arrays hold up to 26 entries; *_lo / *_n are [entry][3] local index boxes.  Entries are
  * in issue order: NCCL matches the messages of a pair of ranks first-in first-out.  Returns 1 if more than 26 messages would be needed. */
@@ -173,6 +178,10 @@ int vdn_mkumac(vdn_ctx *ctx);                     /* macproject.f90:403 */
  * grids exercise the production kernel) and a forced tile shape of it (-1 = the measured default per launch kind).  Drops the cached
  * multigrid hierarchy; takes effect at the next solve. */
 int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile);
+
+/* test / measurement hook, before vdn_ctx_set_comm: force_nccl != 0 keeps the NCCL transport (pack + grouped send/recv + unpack) for the ghost
+ * exchanges instead of the peer-memory transport (CUDA-IPC mapped symmetric heap, one pull kernel per exchange) */
+int vdn_comm_tune(vdn_ctx *ctx, int force_nccl);
 
 /* ---- measurement: per-kernel-family CUDA-event timing on the launching stream ---- */
 int vdn_prof_enable(vdn_ctx *ctx, int on);        /* resets counters */

@@ -24,7 +24,7 @@ F = {name: i for i, name in enumerate(FIELDS)}
 
 ABI_SYMBOLS = [
     "vdn_params_default", "vdn_ctx_create", "vdn_ctx_destroy", "vdn_last_error", "vdn_ctx_set_comm",
-    "vdn_nccl_unique_id", "vdn_comm_plan", "vdn_halo_plan",
+    "vdn_nccl_unique_id", "vdn_comm_plan", "vdn_halo_plan", "vdn_halo_plan_ex", "vdn_comm_tune",
     "vdn_field_upload", "vdn_field_download", "vdn_field_setval", "vdn_sync", "vdn_get_stream",
     "vdn_fill_boundary", "vdn_fill_and_physbc", "vdn_mkvelforce", "vdn_mkscalforce", "vdn_velpred",
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
@@ -211,6 +211,10 @@ class Context:
         n, r = C.c_int(0), C.c_double(0.0)
         self._chk(self.lib.vdn_mac_solve(self.h, C.c_double(rel_eps), C.c_double(abs_eps), C.byref(n), C.byref(r)))
         return n.value, r.value
+
+    def comm_tune(self, force_nccl):
+        """measurement hook, before set_comm: keep the NCCL transport for the ghost exchanges"""
+        self._chk(self.lib.vdn_comm_tune(self.h, int(force_nccl)))
 
     def mg_tune(self, fuse_min=128, tile=-1):
         """test hook: smallest level the fused smoother runs on, forced tile shape (-1: measured defaults)"""

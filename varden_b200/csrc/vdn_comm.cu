@@ -1,12 +1,17 @@
-// vdn_comm.cu -- inter-rank plumbing of the hot path: one rank per GPU, NCCL over NVLink/NVSwitch.
+// vdn_comm.cu -- inter-rank plumbing of the hot path: one rank per GPU over NVLink / NVSwitch.
 //
 // Replaces FBoxLib's MPI layer for this path:
-//   multifab_fill_boundary between boxes of different ranks  -> pack kernel + grouped ncclSend/ncclRecv + unpack kernel,
-//       direction by direction (x, then y over the x-ghosted range, then z) so edge/corner ghosts need no diagonal messages
+//   multifab_fill_boundary between boxes of different ranks and the ghost-layer fills inside the multigrid -> ONE exchange plan
+//       (faces, edges and corners of the up-to-26 neighbour ranks in a single phase) executed by one of two transports:
+//         * peer memory (default inside a node): every rank allocates its exchanged arrays from one "symmetric heap" whose CUDA-IPC handle
+//           all ranks map; an exchange is ONE kernel that announces "my stream has reached exchange e" in a flag of its own heap, spins on
+//           the flags of the ranks it reads from and then copies their boundary cells straight out of their memory into its own ghost cells
+//           -- no pack buffers, no NCCL launch, ~1 launch instead of 3 + a group of up to 34 messages;
+//         * NCCL (fallback when IPC mapping is not possible): pack kernel + grouped ncclSend/ncclRecv + unpack kernel of the same plan.
 //   norm_inf / parallel_reduce (macproject.f90:65,203; F_MG residual norms) -> ncclAllReduce(double, MAX/SUM)
 //   F_MG coarse levels -> agglomeration: ncclAllGather of the coarse right-hand side / coefficients, every GPU then
 //       finishes the V-cycle locally on the whole coarse domain (no scatter step needed)
-// The decomposition must be a tensor-product grid of rectangular regions (what boxarray_maxsize + a block map gives).
+// The decomposition must be a tensor-product grid of equal rectangular regions (what boxarray_maxsize + a block map gives).
 #include "vdn_ctx.h"
 #include "vdn_comm.h"
 #include <nccl.h>
@@ -25,7 +30,14 @@ struct Comm {
     std::vector<int> coord2rank;   // process-grid coordinates (x fastest) -> rank
     double *sbuf = nullptr, *rbuf = nullptr; size_t buf_doubles = 0;
     double *d_scal = nullptr;
+    // peer-memory transport
+    bool p2p = false;
+    char *heap = nullptr; size_t heap_bytes = 0, heap_used = 0;     // symmetric heap: same layout on every rank
+    std::vector<char *> peer_base;                                  // base of rank r's heap in MY address space (own rank: heap)
+    char **d_peer_base = nullptr;
+    unsigned long long epoch = 0;                                   // exchanges issued so far (the same sequence on every rank)
 };
+constexpr size_t HEAP_RESERVED = 256;                               // flag word (+ padding) at the start of every heap
 
 // ---- host-only planning (testable without a GPU) ----
 extern "C" int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo, const int *region_hi,
@@ -114,82 +126,22 @@ static void ensure_buf(vdn_ctx *c, size_t doubles)
     VDN_CUDA(cudaMalloc(&cm->rbuf, sizeof(double) * cm->buf_doubles));
 }
 
-// Exchange along the directions in `dirs` (bit mask) of an array described by (v, n, ng, nc, fdir).
-// grow_prev: transverse range includes ghosts in directions < d (the x->y->z cascade that fills corners).
-void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fdir, int dmask, bool grow_prev, bool incl_n, int dmask_all)
-{
-    if (dmask_all < 0) dmask_all = dmask;
-    Comm *cm = c->comm;
-    if (!cm || ng == 0) return;
-    // the x -> y -> z cascade: the slab sent along d carries the ghost cells of the directions before it, so those directions must be
-    // complete (received AND unpacked) before the slab is packed -- one phase per direction, not one pack for all of them
-    if (grow_prev && (dmask & (dmask - 1)) != 0) {
-        for (int d = 0; d < dim; ++d) if ((dmask >> d) & 1) comm_halo(c, v, n, dim, ng, nc, fdir, 1 << d, true, incl_n, dmask_all);
-        return;
-    }
-    PackArgs ps; ps.v = v; ps.nc = nc; ps.nseg = 0; ps.unpack = 0;
-    PackArgs pu = ps; pu.unpack = 1;
-    struct Msg { int peer; long off, cnt; };
-    std::vector<Msg> sends, recvs;
-    long soff = 0, roff = 0;
-    for (int d = 0; d < dim; ++d) {
-        if (!((dmask >> d) & 1)) continue;
-        const int nod = (fdir == d) ? 1 : 0;
-        int tlo[3], tn[3];
-        for (int t = 0; t < 3; ++t) {
-            if (t >= dim) { tlo[t] = 0; tn[t] = 1; continue; }
-            const int ext = n[t] + (fdir == t ? 1 : 0);
-            if (grow_prev && t < d) { tlo[t] = -ng; tn[t] = ext + 2 * ng; }
-            else { tlo[t] = 0; tn[t] = ext + ((incl_n && t != d && !(((dmask_all >> t) & 1) && cm->pgrid[t] > 1)) ? 1 : 0); }
-        }
-        Msg rcv_of_side[2]; bool has[2] = { false, false };
-        for (int s = 0; s < 2; ++s) {
-            const int peer = cm->nbr[d][s];
-            if (peer < 0 || peer == cm->rank) continue;
-            Seg snd, rcv;
-            for (int t = 0; t < 3; ++t) { snd.lo[t] = rcv.lo[t] = tlo[t]; snd.n[t] = rcv.n[t] = tn[t]; }
-            snd.n[d] = rcv.n[d] = ng;
-            if (s == 0) { snd.lo[d] = nod ? 1 : 0;  rcv.lo[d] = -ng; }                       // to/from the lo neighbour
-            else        { snd.lo[d] = n[d] - ng;    rcv.lo[d] = n[d] + nod; }                // to/from the hi neighbour
-            const long cnt = (long)snd.n[0] * snd.n[1] * snd.n[2] * nc;
-            snd.off = soff; rcv.off = roff;
-            ps.seg[ps.nseg++] = snd; pu.seg[pu.nseg++] = rcv;
-            sends.push_back({ peer, soff, cnt });
-            rcv_of_side[s] = { peer, roff, cnt }; has[s] = true;
-            soff += cnt; roff += cnt;
-        }
-        // messages to one peer are matched in issue order: sends go (lo, hi), receives (hi, lo), so that with a single
-        // peer on both sides (2 ranks along a periodic direction) its lo slab lands in my hi ghost and vice versa
-        if (has[1]) recvs.push_back(rcv_of_side[1]);
-        if (has[0]) recvs.push_back(rcv_of_side[0]);
-    }
-    if (ps.nseg == 0) return;
-    ensure_buf(c, (size_t)std::max(soff, roff));
-    c->comm_bytes += 8LL * soff;
-    ps.buf = cm->sbuf; pu.buf = cm->rbuf;
-    launch_pack(c, ps);
-    VDN_NCCL(ncclGroupStart());
-    for (const Msg &m : sends) VDN_NCCL(ncclSend(cm->sbuf + m.off, (size_t)m.cnt, ncclDouble, m.peer, cm->nccl, c->stream));
-    for (const Msg &m : recvs) VDN_NCCL(ncclRecv(cm->rbuf + m.off, (size_t)m.cnt, ncclDouble, m.peer, cm->nccl, c->stream));
-    VDN_NCCL(ncclGroupEnd());
-    launch_pack(c, pu);
-}
-
-// Ghost layers of depth ng of a cell-centred array in ONE phase: faces, edges and corners travel as separate messages to the
-// (up to 26) neighbour ranks of the process grid inside one NCCL group, bracketed by one pack and one unpack launch.  The
-// direction-by-direction cascade above needs one pack / group / unpack per split direction; the fused multigrid smoother
-// calls this once per launch, so the latency of a phase is what limits multi-GPU scaling.
-// Message matching: NCCL pairs the sends and receives of two ranks in issue order.  Every rank issues its sends in
-// lexicographic order of the offset vector o (neighbour = my coordinates + o) and its receives in the reverse order -- the
-// message a peer sent for its offset o' is the one I receive for my offset -o', and negation reverses the order -- so the
-// pairing also holds when one peer is my neighbour for several offsets (two ranks along a periodic direction).
-// host-only message plan of the single-phase exchange (testable without a GPU: tests/test_halo_plan.py).
+// ------------------------------------------------------------------------------------------
+// The exchange plan (host only; tests/test_halo_plan.py plays every rank of a process grid through it on the CPU).
 //   pgrid / pcoord: process grid and this rank's coordinates; periodic[d]: the domain is periodic along d;
-//   coord2rank[x + pgrid[0]*(y + pgrid[1]*z)]: rank at those coordinates; n: local cells; dmask: split directions of the array.
-// Outputs (up to 26 entries each): peer rank and the inclusive-lo / extent boxes (local indices) of what is sent and of the ghost
-// region that is received, in ISSUE order (sends lexicographic in the neighbour offset, receives in the reverse order).
-extern "C" int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng, int dmask,
-                             int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n)
+//   coord2rank[x + pgrid[0]*(y + pgrid[1]*z)]: rank at those coordinates; n: local cells; ng: ghost layers to fill;
+//   dmask: split directions to exchange; nodal: direction in which the array is face-centred (-1: cell-centred);
+//   carry_n: multigrid level arrays -- along a direction that is NOT split a slab also carries index n (they keep the coefficient of the
+//            high boundary / periodic-seam face there, and the ghost planes are relaxed with it).
+// Outputs (up to 26 entries each, in ISSUE order): peer rank, inclusive-lo / extent boxes (local indices) of what is sent and of the ghost
+// region that is received, and for a received box the index shift into the PEER's local numbering (peer index = my index + shift).
+// NCCL matches the messages of a pair of ranks first-in first-out: sends are issued in lexicographic order of the neighbour offset o and
+// receives in the reverse order -- the message a peer sent for its offset o' is the one I receive for my offset -o', and negation reverses
+// the order -- so the pairing also holds when one peer is my neighbour for several offsets (two ranks along a periodic direction).
+// ------------------------------------------------------------------------------------------
+extern "C" int vdn_halo_plan_ex(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng,
+                                int dmask, int nodal, int carry_n,
+                                int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n, int *recv_shift)
 {
     *nsend = 0; *nrecv = 0;
     auto peer_of = [&](const int *o) -> int {          // rank at my process-grid coordinates + o, or -1
@@ -215,47 +167,114 @@ extern "C" int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const
             if (!ok) continue;
             const int peer = peer_of(o);
             if (peer < 0) continue;
-            int lo[3], ext[3];
+            int lo[3], ext[3], sh[3];
             for (int d = 0; d < 3; ++d) {
+                sh[d] = 0;
                 if (d >= dim) { lo[d] = 0; ext[d] = 1; continue; }
-                // along a direction that is not split the slab also carries index n: the level arrays keep the coefficient of the high
-                // boundary / periodic-seam face there, and the ghost planes are relaxed with it (split directions: index n is the first
-                // ghost cell and comes with the edge message)
-                if (o[d] == 0) { lo[d] = 0; ext[d] = n[d] + ((((dmask >> d) & 1) && pgrid[d] > 1) ? 0 : 1); }
-                else if (pass == 0) { lo[d] = o[d] < 0 ? 0 : n[d] - ng; ext[d] = ng; }       // my cells next to that neighbour
-                else                { lo[d] = o[d] < 0 ? -ng : n[d];    ext[d] = ng; }       // my ghost cells on that side
+                const int nod = (d == nodal) ? 1 : 0;
+                const bool split = ((dmask >> d) & 1) && pgrid[d] > 1;
+                if (o[d] == 0) { lo[d] = 0; ext[d] = n[d] + nod + ((carry_n && !split) ? 1 : 0); }
+                else if (pass == 0) { lo[d] = o[d] < 0 ? nod : n[d] - ng; ext[d] = ng; }               // my cells / faces next to that neighbour
+                else                { lo[d] = o[d] < 0 ? -ng : n[d] + nod; ext[d] = ng; sh[d] = -o[d] * n[d]; }   // my ghosts on that side
             }
             int &cnt = pass == 0 ? *nsend : *nrecv;
             if (cnt >= 26) return 1;
             int *pp = pass == 0 ? send_peer : recv_peer, *pl = pass == 0 ? send_lo : recv_lo, *pn = pass == 0 ? send_n : recv_n;
             pp[cnt] = peer;
-            for (int d = 0; d < 3; ++d) { pl[3 * cnt + d] = lo[d]; pn[3 * cnt + d] = ext[d]; }
+            for (int d = 0; d < 3; ++d) { pl[3 * cnt + d] = lo[d]; pn[3 * cnt + d] = ext[d]; if (pass == 1 && recv_shift) recv_shift[3 * cnt + d] = sh[d]; }
             ++cnt;
         }
     return 0;
 }
+// the multigrid form (cell-centred level arrays): kept as the entry point the round-1 tests bind
+extern "C" int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng, int dmask,
+                             int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n)
+{
+    return vdn_halo_plan_ex(dim, pgrid, pcoord, periodic, coord2rank, n, ng, dmask, -1, 1, nsend, send_peer, send_lo, send_n, nrecv, recv_peer, recv_lo, recv_n, nullptr);
+}
 
-void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask)
+// ---- peer-memory transport: one kernel per exchange ----
+struct PullSeg { int peer; int lo[3], n[3], shift[3]; };
+struct PullArgs {
+    long arr_off;                   // byte offset, inside the symmetric heap, of the array's local element (0,0,0), comp 0
+    int sy, sz, cs, nc;
+    int nseg; PullSeg seg[26];
+    char *const *peer_base; int me;
+    unsigned long long epoch;
+};
+__global__ void k_halo_pull(PullArgs a)
+{
+    const PullSeg &s = a.seg[blockIdx.y];
+    if (threadIdx.x == 0) {
+        // everything my stream produced before this kernel is complete: publish it, then wait until the rank this block reads from has
+        // published the same exchange (its producing kernels are complete too)
+        volatile unsigned long long *mine = (volatile unsigned long long *)a.peer_base[a.me];
+        __threadfence_system();
+        *mine = a.epoch;
+        volatile unsigned long long *theirs = (volatile unsigned long long *)a.peer_base[s.peer];
+        while (*theirs < a.epoch) { }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const double *src = (const double *)(a.peer_base[s.peer] + a.arr_off);
+    double *dst = (double *)(a.peer_base[a.me] + a.arr_off);
+    const long per = (long)s.n[0] * s.n[1] * s.n[2];
+    const long tot = per * a.nc;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t / per); const long q = t - (long)c * per;
+        const int i = s.lo[0] + (int)(q % s.n[0]), j = s.lo[1] + (int)((q / s.n[0]) % s.n[1]), k = s.lo[2] + (int)(q / ((long)s.n[0] * s.n[1]));
+        const long d_ix = i + (long)a.sy * j + (long)a.sz * k + (long)a.cs * c;
+        const long s_ix = (i + s.shift[0]) + (long)a.sy * (j + s.shift[1]) + (long)a.sz * (k + s.shift[2]) + (long)a.cs * c;
+        dst[d_ix] = __ldcv(src + s_ix);             // peer memory: never through a stale L1 line
+    }
+}
+
+static bool in_heap(const Comm *cm, const void *p)
+{
+    return cm->p2p && (const char *)p >= cm->heap && (const char *)p < cm->heap + cm->heap_bytes;
+}
+
+// Fill ng ghost layers of an array along the split directions in dmask (faces, edges and corners in one phase).
+// nodal: face-centred direction of the array or -1; carry_n: multigrid level arrays (see vdn_halo_plan_ex).
+void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int nodal, int dmask, bool carry_n)
 {
     Comm *cm = c->comm;
     if (!cm || ng == 0) return;
-    int ns = 0, nr = 0, speer[26], rpeer[26], slo[78], sn[78], rlo[78], rn[78], per[3];
+    int ns = 0, nr = 0, speer[26], rpeer[26], slo[78], sn[78], rlo[78], rn[78], rsh[78], per[3];
     for (int d = 0; d < 3; ++d) per[d] = c->dom_bc[d][0] == BC_PERIODIC ? 1 : 0;
-    VDN_REQUIRE(vdn_halo_plan(dim, cm->pgrid, cm->pcoord, per, cm->coord2rank.data(), n, ng, dmask, &ns, speer, slo, sn, &nr, rpeer, rlo, rn) == 0,
-                "too many halo segments");
+    VDN_REQUIRE(vdn_halo_plan_ex(dim, cm->pgrid, cm->pcoord, per, cm->coord2rank.data(), n, ng, dmask, nodal, carry_n ? 1 : 0,
+                                 &ns, speer, slo, sn, &nr, rpeer, rlo, rn, rsh) == 0, "too many halo segments");
     if (ns == 0 && nr == 0) return;
-    PackArgs ps; ps.v = v; ps.nc = 1; ps.nseg = 0; ps.unpack = 0;
+    if (in_heap(cm, v.p)) {
+        PullArgs a;
+        a.arr_off = (long)((const char *)v.p - cm->heap); a.sy = v.sy; a.sz = v.sz; a.cs = v.cs; a.nc = nc;
+        a.nseg = nr; a.peer_base = cm->d_peer_base; a.me = cm->rank; a.epoch = ++cm->epoch;
+        long mx = 1, bytes = 0;
+        for (int q = 0; q < nr; ++q) {
+            a.seg[q].peer = rpeer[q];
+            long cnt = nc;
+            for (int d = 0; d < 3; ++d) { a.seg[q].lo[d] = rlo[3 * q + d]; a.seg[q].n[d] = rn[3 * q + d]; a.seg[q].shift[d] = rsh[3 * q + d]; cnt *= rn[3 * q + d]; }
+            mx = std::max(mx, cnt); bytes += 8 * cnt;
+        }
+        c->comm_bytes += bytes;                      // pulled = what the peers would have sent (equal regions: symmetric)
+        // few blocks per segment: they all spin until their peer arrives, and the segments are surface data
+        dim3 gr((unsigned)std::min<long>(32, (mx + 255) / 256), nr);
+        k_halo_pull<<<gr, 256, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+        return;
+    }
+    PackArgs ps; ps.v = v; ps.nc = nc; ps.nseg = 0; ps.unpack = 0;
     PackArgs pu = ps; pu.unpack = 1;
     struct Msg { int peer; long off, cnt; };
     std::vector<Msg> sends, recvs;
     long soff = 0, roff = 0;
     for (int q = 0; q < ns; ++q) {
-        Seg sg; long cnt = 1;
+        Seg sg; long cnt = nc;
         for (int d = 0; d < 3; ++d) { sg.lo[d] = slo[3 * q + d]; sg.n[d] = sn[3 * q + d]; cnt *= sg.n[d]; }
         sg.off = soff; ps.seg[ps.nseg++] = sg; sends.push_back({ speer[q], soff, cnt }); soff += cnt;
     }
     for (int q = 0; q < nr; ++q) {
-        Seg sg; long cnt = 1;
+        Seg sg; long cnt = nc;
         for (int d = 0; d < 3; ++d) { sg.lo[d] = rlo[3 * q + d]; sg.n[d] = rn[3 * q + d]; cnt *= sg.n[d]; }
         sg.off = roff; pu.seg[pu.nseg++] = sg; recvs.push_back({ rpeer[q], roff, cnt }); roff += cnt;
     }
@@ -270,11 +289,38 @@ void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask
     launch_pack(c, pu);
 }
 
-void comm_exchange(vdn_ctx *c, int field, int d)
+// multifab_fill_boundary between ranks for a field: every split direction at once (vdn_stream.cu then wraps the periodic directions this
+// rank owns alone over the ghosted range, which completes the edge and corner ghosts)
+void comm_exchange_field(vdn_ctx *c, int field)
 {
     DField &f = c->f[field];
-    LaunchScope ls(c, "halo_exchange", 0.0, 2);
-    comm_halo(c, f.view(), c->geo.n, c->dim, f.ng, f.nc, f.fdir, 1 << d, true);
+    Comm *cm = c->comm;
+    if (!cm) return;
+    int dmask = 0;
+    for (int d = 0; d < c->dim; ++d) if (cm->pgrid[d] > 1) dmask |= 1 << d;
+    if (!dmask) return;
+    LaunchScope ls(c, "halo_exchange", 0.0, in_heap(cm, f.base) ? 1 : 2);
+    comm_halo(c, f.view(), c->geo.n, c->dim, f.ng, f.nc, f.fdir, dmask, false);
+}
+
+// symmetric allocation: from the heap when the peer-memory transport is up (every rank must allocate the same sequence of sizes), else
+// a plain cudaMalloc.  *owned tells the caller whether it has to cudaFree the block.
+double *comm_sym_alloc(vdn_ctx *c, size_t bytes, bool *owned)
+{
+    Comm *cm = c->comm;
+    if (cm && cm->p2p) {
+        const size_t al = (bytes + 255) & ~(size_t)255;
+        if (cm->heap_used + al <= cm->heap_bytes) {
+            double *p = (double *)(cm->heap + cm->heap_used);
+            cm->heap_used += al;
+            *owned = false;
+            return p;
+        }
+        throw VdnError("symmetric heap exhausted");
+    }
+    double *p; VDN_CUDA(cudaMalloc(&p, bytes));
+    *owned = true;
+    return p;
 }
 
 static double allreduce(vdn_ctx *c, double v, ncclRedOp_t op)
@@ -294,6 +340,7 @@ double comm_allreduce_sum(vdn_ctx *c, double v) { return allreduce(c, v, ncclSum
 int comm_rank(const vdn_ctx *c) { return c->comm ? c->comm->rank : 0; }
 int comm_nranks(const vdn_ctx *c) { return c->comm ? c->comm->nranks : 1; }
 const int *comm_pgrid(const vdn_ctx *c) { return c->comm->pgrid; }
+const int *comm_pgrid_or_null(const vdn_ctx *c) { return c->comm ? c->comm->pgrid : nullptr; }
 const int *comm_pcoord(const vdn_ctx *c) { return c->comm->pcoord; }
 bool comm_has_neighbor(const vdn_ctx *c, int d, int s) { return c->comm && c->comm->nbr[d][s] >= 0 && c->comm->nbr[d][s] != c->comm->rank; }
 
@@ -321,10 +368,103 @@ void comm_destroy(Comm *cm)
     if (cm->sbuf) cudaFree(cm->sbuf);
     if (cm->rbuf) cudaFree(cm->rbuf);
     if (cm->d_scal) cudaFree(cm->d_scal);
+    for (int r = 0; r < (int)cm->peer_base.size(); ++r) if (r != cm->rank && cm->peer_base[r]) cudaIpcCloseMemHandle(cm->peer_base[r]);
+    if (cm->d_peer_base) cudaFree(cm->d_peer_base);
+    if (cm->heap) cudaFree(cm->heap);
     delete cm;
 }
 
 void ctx_rebuild_bc(vdn_ctx *c);      // vdn_ctx.cu
+
+// Peer-memory transport: one symmetric heap per rank holding every array that is exchanged (all fields + the distributed multigrid levels),
+// its CUDA-IPC handle gathered over NCCL and mapped by every rank.  Any failure leaves the NCCL transport in place (all ranks agree).
+static void p2p_setup(vdn_ctx *c)
+{
+    Comm *cm = c->comm;
+    if (c->comm_force_nccl) return;
+    // size: the fields + the multigrid arrays that are not aliases of fields (level 0: 1 array; coarser distributed levels: 6 each)
+    size_t need = HEAP_RESERVED;
+    for (int i = 0; i < VDN_NFIELDS; ++i) {
+        if (i >= VDN_SEDGE_X && i <= VDN_SEDGE_Z) continue;
+        if (c->f[i].base) need += (c->f[i].bytes + 255) & ~(size_t)255;
+    }
+    {
+        int nn[3] = { c->geo.n[0], c->geo.n[1], c->geo.n[2] };
+        for (int l = 0; l < 32; ++l) {
+            size_t tot = 1;
+            for (int d = 0; d < c->dim; ++d) tot *= (size_t)(nn[d] + 2 * MG_PAD);
+            need += (l == 0 ? 1 : 6) * ((tot * 8 + 255) & ~(size_t)255);
+            bool ok = true;
+            for (int d = 0; d < c->dim; ++d) if (nn[d] % 2 != 0 || nn[d] / 2 < 2) ok = false;
+            if (!ok) break;
+            for (int d = 0; d < c->dim; ++d) nn[d] /= 2;
+        }
+    }
+    need += 1 << 20;
+    int ok = 1;
+    char *heap = nullptr;
+    if (cudaMalloc(&heap, need) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof mine);
+    if (ok && cudaIpcGetMemHandle(&mine, heap) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    // gather (ok flag, handle) of every rank
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const int rec = 64 + 8;
+    std::vector<char> all((size_t)rec * cm->nranks, 0);
+    char *d_all = nullptr;
+    VDN_CUDA(cudaMalloc(&d_all, all.size()));
+    { char mrec[72]; memset(mrec, 0, sizeof mrec); memcpy(mrec, &mine, 64); mrec[64] = (char)ok;
+      VDN_CUDA(cudaMemcpyAsync(d_all + (size_t)rec * cm->rank, mrec, rec, cudaMemcpyHostToDevice, c->stream)); }
+    VDN_NCCL(ncclAllGather(d_all + (size_t)rec * cm->rank, d_all, rec, ncclChar, cm->nccl, c->stream));
+    VDN_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost, c->stream));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < cm->nranks; ++r) if (!all[(size_t)rec * r + 64]) ok = 0;
+    std::vector<char *> peer(cm->nranks, nullptr);
+    if (ok) {
+        for (int r = 0; r < cm->nranks && ok; ++r) {
+            if (r == cm->rank) { peer[r] = heap; continue; }
+            cudaIpcMemHandle_t h; memcpy(&h, &all[(size_t)rec * r], 64);
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            peer[r] = (char *)p;
+        }
+    }
+    // every rank must have mapped every heap
+    { double v = ok ? 1.0 : 0.0;
+      VDN_CUDA(cudaMemcpyAsync(cm->d_scal, &v, 8, cudaMemcpyHostToDevice, c->stream));
+      VDN_NCCL(ncclAllReduce(cm->d_scal, cm->d_scal, 1, ncclDouble, ncclMin, cm->nccl, c->stream));
+      VDN_CUDA(cudaMemcpyAsync(&v, cm->d_scal, 8, cudaMemcpyDeviceToHost, c->stream));
+      VDN_CUDA(cudaStreamSynchronize(c->stream));
+      ok = v > 0.5; }
+    cudaFree(d_all);
+    if (!ok) {
+        for (int r = 0; r < cm->nranks; ++r) if (r != cm->rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
+        if (heap) cudaFree(heap);
+        return;
+    }
+    cm->heap = heap; cm->heap_bytes = need; cm->heap_used = HEAP_RESERVED; cm->peer_base = peer; cm->p2p = true;
+    VDN_CUDA(cudaMemsetAsync(heap, 0, HEAP_RESERVED, c->stream));
+    VDN_CUDA(cudaMalloc(&cm->d_peer_base, sizeof(char *) * cm->nranks));
+    VDN_CUDA(cudaMemcpyAsync(cm->d_peer_base, peer.data(), sizeof(char *) * cm->nranks, cudaMemcpyHostToDevice, c->stream));
+    // move the fields into the heap (nothing has been uploaded yet: contents = the initial values of vdn_ctx_create)
+    for (int i = 0; i < VDN_NFIELDS; ++i) {
+        if (i >= VDN_SEDGE_X && i <= VDN_SEDGE_Z) continue;
+        DField &f = c->f[i];
+        if (!f.base) continue;
+        bool owned;
+        double *p = comm_sym_alloc(c, f.bytes, &owned);
+        VDN_CUDA(cudaMemcpyAsync(p, f.base, f.bytes, cudaMemcpyDeviceToDevice, c->stream));
+        VDN_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(f.base);
+        f.base = p; f.in_heap = true;
+    }
+    for (int d = 0; d < c->dim; ++d) {          // SEDGE_* alias UEDGE_*
+        const int nc = c->f[VDN_SEDGE_X + d].nc;
+        c->f[VDN_SEDGE_X + d] = c->f[VDN_UEDGE_X + d]; c->f[VDN_SEDGE_X + d].nc = nc;
+    }
+    // all ranks finish mapping before anyone starts exchanging
+    VDN_NCCL(ncclAllReduce(cm->d_scal, cm->d_scal, 1, ncclDouble, ncclMin, cm->nccl, c->stream));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+}
 
 extern "C" int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *region_lo, const int *region_hi, const void *nccl_unique_id)
 {
@@ -362,6 +502,7 @@ extern "C" int vdn_ctx_set_comm(vdn_ctx *ctx, int rank, int nranks, const int *r
         for (int r = 0; r < nranks; ++r) { int pc[3]; comm_coord_of(ctx, r, pc); cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])] = r; }
         for (int r = 0; r < nranks; ++r) VDN_REQUIRE(cm->coord2rank[r] >= 0, "process grid has holes");
         ctx_rebuild_bc(ctx);
+        p2p_setup(ctx);
         return 0;
     } catch (const std::exception &e) { ctx->err = e.what(); return 1; }
 }

@@ -1,11 +1,13 @@
-// vdn_comm.h -- inter-rank helpers used by the multigrid (implemented in vdn_comm.cu)
+// vdn_comm.h -- inter-rank helpers used by the multigrid and the field ghost fills (implemented in vdn_comm.cu)
 #pragma once
 #include "vdn_ctx.h"
 
-// incl_n: transverse ranges of directions that are not split also carry index n (multigrid level arrays keep the high boundary /
-// periodic-seam face coefficient there); dmask_all: every split direction of the array (defaults to dmask)
-void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int fdir, int dmask, bool grow_prev, bool incl_n = false, int dmask_all = -1);
-void comm_halo_deep(vdn_ctx *c, View v, const int *n, int dim, int ng, int dmask);
+// Fill ng ghost layers of an array along the split directions in dmask: faces, edges and corners of the neighbour ranks in one phase.
+// nodal: face-centred direction of the array (-1: cell-centred); carry_n: multigrid level arrays -- transverse ranges of directions that
+// are not split also carry index n (the level layout keeps the high boundary / periodic-seam face coefficient there).
+void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int nodal, int dmask, bool carry_n);
+void comm_exchange_field(vdn_ctx *c, int field);          // multifab_fill_boundary between ranks, every split direction at once
+double *comm_sym_alloc(vdn_ctx *c, size_t bytes, bool *owned);   // symmetric-heap allocation (peer-memory transport) or cudaMalloc
 int comm_rank(const vdn_ctx *c);
 int comm_nranks(const vdn_ctx *c);
 const int *comm_pgrid(const vdn_ctx *c);

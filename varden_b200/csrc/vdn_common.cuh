@@ -74,6 +74,7 @@ struct DField {
     size_t bytes = 0;
     long sy = 0, sz = 0, cs = 0;
     int ngd[3] = {0, 0, 0};     // ghost width per direction (0 in the unused 3rd direction of 2-D)
+    bool in_heap = false;       // storage lives in the symmetric heap of the peer-memory transport (not cudaFree'd on its own)
     View view() const {
         View v; v.sy = (int)sy; v.sz = (int)sz; v.cs = (int)cs;
         v.p = base + ngd[0] + sy * ngd[1] + sz * ngd[2];

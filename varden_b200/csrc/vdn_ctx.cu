@@ -210,7 +210,7 @@ static void ctx_free(vdn_ctx *c)
     if (c->comm) comm_destroy(c->comm);
     for (int i = 0; i < VDN_NFIELDS; ++i) {
         if (i >= VDN_SEDGE_X && i <= VDN_SEDGE_Z) continue;      // aliases UEDGE
-        if (c->f[i].base) cudaFree(c->f[i].base);
+        if (c->f[i].base && !c->f[i].in_heap) cudaFree(c->f[i].base);
     }
     if (c->scratch) cudaFree(c->scratch);
     if (c->d_eps) cudaFree(c->d_eps);
@@ -486,6 +486,9 @@ int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile)
                  VDN_CUDA(cudaStreamSynchronize(ctx->stream));
                  if (ctx->mg) { mg_destroy(ctx->mg); ctx->mg = nullptr; }
                  ctx->mg_fuse_min = fuse_min; ctx->mg_tile_force = tile; }) }
+
+int vdn_comm_tune(vdn_ctx *ctx, int force_nccl)
+{ VDN_TRY(ctx, { VDN_REQUIRE(!ctx->comm, "vdn_comm_tune must be called before vdn_ctx_set_comm"); ctx->comm_force_nccl = force_nccl != 0; }) }
 
 int vdn_prof_enable(vdn_ctx *ctx, int on)
 { VDN_TRY(ctx, { prof_collect(ctx); ctx->prof.clear(); ctx->prof_idx.clear(); ctx->prof_on = on != 0; }) }

@@ -49,6 +49,7 @@ struct vdn_ctx {
     cudaEvent_t ev_up[VDN_NFIELDS] = {}, ev_fin[VDN_NFIELDS] = {};
     const vdn_host_state *hio = nullptr;
     int mg_fuse_min = 128, mg_tile_force = -1;          // fused smoother: smallest level it runs on; test hook (vdn_mg_tune)
+    bool comm_force_nccl = false;                       // test / measurement hook (vdn_comm_tune): keep the NCCL transport
     bool lapu_set = false;                              // LAPU has been uploaded (required when visc_coef > 0)
 
     View S(int q) const { View v; v.sy = (int)s_sy; v.sz = (int)s_sz; v.cs = (int)s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
@@ -81,6 +82,7 @@ void st_setval(vdn_ctx *c, int field, double val);
 double st_absmax_valid(vdn_ctx *c, int field);           // norm_inf over valid cells/faces, all comps
 void mg_destroy(MG *mg);
 void comm_destroy(Comm *cm);
-void comm_exchange(vdn_ctx *c, int field, int d);         // halo exchange along d with the neighbour ranks (vdn_comm.cu)
+void comm_exchange_field(vdn_ctx *c, int field);          // ghost cells owned by neighbour ranks, every split direction at once (vdn_comm.cu)
+const int *comm_pgrid_or_null(const vdn_ctx *c);
 double comm_allreduce_max(vdn_ctx *c, double v);
 double comm_allreduce_sum(vdn_ctx *c, double v);

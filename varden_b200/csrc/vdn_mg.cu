@@ -276,6 +276,8 @@ __global__ void k_blk_extract(ExtArgs a)        // local phi <- my block of the 
 MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, const int (*mode)[2], bool alias0, int max_levels)
 {
     MG *m = new MG();
+    bool sym = false;                                    // any face shared with another rank
+    for (int d = 0; d < c->dim; ++d) for (int s = 0; s < 2; ++s) if (mode[d][s] == M_GHOST) sym = true;
     m->dim = c->dim;
     int nn[3] = { n_in[0], n_in[1], n_in[2] };
     int nlev = 1;
@@ -300,7 +302,13 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         L.off = MG_PAD * (1 + L.s[1] + (c->dim == 3 ? L.s[2] : 0));
         L.par0 = (glo[0] + glo[1] + (c->dim == 3 ? glo[2] : 0)) & 1;
         for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) { L.mode[d][s] = d < c->dim ? mode[d][s] : M_NEU; if (L.mode[d][s] == M_GHOST) m->distributed = true; }
-        auto dalloc = [&](long cnt) { double *p; VDN_CUDA(cudaMalloc(&p, sizeof(double) * cnt)); VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cnt, c->stream)); m->owned.push_back(p); return p; };
+        // rank-split hierarchies live in the symmetric heap of the peer-memory transport (every rank allocates the same sequence)
+        auto dalloc = [&](long cnt) {
+            bool owned = true; double *p;
+            if (sym) p = comm_sym_alloc(c, sizeof(double) * cnt, &owned); else VDN_CUDA(cudaMalloc(&p, sizeof(double) * cnt));
+            VDN_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cnt, c->stream));
+            if (owned) m->owned.push_back(p);
+            return p; };
         if (l == 0 && alias0) {
             L.phi = c->f[VDN_PHI].base; L.rhs = c->f[VDN_RH].base;
             for (int d = 0; d < c->dim; ++d) L.b[d] = c->f[VDN_BETA_X + d].base;
@@ -412,8 +420,9 @@ void mg_halo(vdn_ctx *c, MG *m, Lev &L, double *x)
     View v; v.p = x + L.off; v.sy = L.s[1]; v.sz = L.s[2]; v.cs = L.ntot;
     int dmask = 0;
     for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
-    LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
-    comm_halo(c, v, L.n, m->dim, 1, 1, -1, dmask, false);
+    LaunchScope ls(c, "mg_halo_exchange", 0.0, 1);
+    // the 7-point stencil of the plain kernels reads face neighbours only, but one plan serves every exchange (edges / corners: a few cells)
+    comm_halo(c, v, L.n, m->dim, 1, 1, -1, dmask, true);
 }
 
 // ghost layers of depth ng of one level array, all split directions at once (x, then y over the x-ghosted range, then z: the
@@ -424,9 +433,8 @@ void mg_halo_deep(vdn_ctx *c, MG *m, Lev &L, double *x, int ng)
     View v; v.p = x + L.off; v.sy = L.s[1]; v.sz = L.s[2]; v.cs = L.ntot;
     int dmask = 0;
     for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
-    LaunchScope ls(c, "mg_halo_exchange", 0.0, 2);
-    // one phase: faces, edges and corners travel in one NCCL group bracketed by one pack and one unpack launch
-    comm_halo_deep(c, v, L.n, m->dim, ng, dmask);
+    LaunchScope ls(c, "mg_halo_exchange", 0.0, 1);
+    comm_halo(c, v, L.n, m->dim, ng, 1, -1, dmask, true);
 }
 
 void smooth(vdn_ctx *c, MG *m, int l, int sweeps)

@@ -380,32 +380,34 @@ void st_mkumac(vdn_ctx *c)
     for (int d = 0; d < c->dim; ++d) st_fill_boundary(c, VDN_UMAC_X + d);       // macproject.f90:491-493
 }
 
-// multifab_fill_boundary on the merged region: direction by direction (x, then y over the x-ghosted range,
-// then z over the x,y-ghosted range) so that edge and corner ghost cells receive the diagonal images.
+// multifab_fill_boundary on the merged region.  Directions split across ranks: one exchange fills the ghost cells of all of them (faces,
+// edges and corners of the neighbour ranks, valid range along the other directions).  Periodic directions this rank owns alone then wrap in
+// order x, y, z, each over the ghosted range of the split directions and of the wrapped directions before it, so that edge and corner ghost
+// cells receive the diagonal images.
 void st_fill_boundary(vdn_ctx *c, int field)
 {
     ctx_require_comm(c);
     DField &f = c->f[field];
     if (f.ng == 0) return;
     const Geo &g = c->geo;
+    const int *pg = comm_pgrid_or_null(c);
+    if (pg) comm_exchange_field(c, field);
     for (int d = 0; d < c->dim; ++d) {
-        if (c->wrap[d]) {
-            WrapArgs a; a.d = d; a.n = g.n[d]; a.ng = f.ng; a.nodal = (f.fdir == d); a.ncomp = f.nc; a.v = f.view();
-            int lo[3], hi[3];
-            for (int t = 0; t < 3; ++t) {
-                if (t >= c->dim) { lo[t] = 0; hi[t] = 0; }
-                else if (t < d) { lo[t] = -f.ng; hi[t] = g.n[t] - 1 + (f.fdir == t) + f.ng; }      // already filled directions: full
-                else            { lo[t] = 0;     hi[t] = g.n[t] - 1 + (f.fdir == t); }              // not yet: valid only
-            }
-            lo[d] = 1; hi[d] = f.ng;
-            a.r = mk_range(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
-            LaunchScope ls(c, "fill_boundary", 0.0);
-            if (d == 0 && f.ng <= 4) k_wrap_x<<<dim3(cdiv(hi[1] - lo[1] + 1, 64), hi[2] - lo[2] + 1), BLK, 0, c->stream>>>(a);
-            else k_wrap<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
-            VDN_CUDA(cudaGetLastError());
-        } else if (c->comm) {
-            comm_exchange(c, field, d);
+        if (!c->wrap[d]) continue;
+        WrapArgs a; a.d = d; a.n = g.n[d]; a.ng = f.ng; a.nodal = (f.fdir == d); a.ncomp = f.nc; a.v = f.view();
+        int lo[3], hi[3];
+        for (int t = 0; t < 3; ++t) {
+            const bool filled = t < c->dim && t != d && ((pg && pg[t] > 1) || (c->wrap[t] && t < d));
+            if (t >= c->dim) { lo[t] = 0; hi[t] = 0; }
+            else if (filled) { lo[t] = -f.ng; hi[t] = g.n[t] - 1 + (f.fdir == t) + f.ng; }       // already filled directions: full
+            else             { lo[t] = 0;     hi[t] = g.n[t] - 1 + (f.fdir == t); }               // not (yet) filled: valid only
         }
+        lo[d] = 1; hi[d] = f.ng;
+        a.r = mk_range(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+        LaunchScope ls(c, "fill_boundary", 0.0);
+        if (d == 0 && f.ng <= 4) k_wrap_x<<<dim3(cdiv(hi[1] - lo[1] + 1, 64), hi[2] - lo[2] + 1), BLK, 0, c->stream>>>(a);
+        else k_wrap<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
     }
 }
 
