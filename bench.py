@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="cells per direction of a reference box (max_grid_size)")
     ap.add_argument("--ratio", type=float, default=0.0, help="density ratio (default 2, config 5: 1000)")
     ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU sample (256^3 = one reference box: a few seconds per pass)")
+    ap.add_argument("--force-nccl", action="store_true", help="A/B: ghost exchanges through NCCL send/recv instead of the peer-memory transport")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--global-n", type=int, default=0, help="configs 3/5: global cells per direction (default 2 x --n)")
@@ -212,6 +213,8 @@ def main():
     prm = V.default_params()
     ctx = V.Context(3, geom.boxes, gfull.dlo, gfull.dhi, gfull.phys_bc, gfull.dx, params=prm, device=local)
     if world > 1:
+        if args.force_nccl:
+            ctx.comm_tune(True)
         PAR.init_comm(ctx, rank, world, rlo, rhi)
 
     # ---- pinned host buffers = what the Fortran driver would hand over (ghosts filled as varden.f90:291-300) ----
@@ -370,7 +373,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": label + "; variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, MAC rel tol 1e-10, "
                                    "%d reference box(es) of %d^3 per GPU, global %dx%dx%d; the same input state every step" % (args.ratio, geom.nboxes, n, nglob[0], nglob[1], nglob[2]),
-                       "parallelism": "1 region per GPU, process grid %s, NCCL halo + allreduce, coarse MG levels agglomerated" % pgrid if world > 1 else "single GPU",
+                       "parallelism": ("1 region per GPU, process grid %s, %s ghost exchanges, NCCL allreduce, coarse MG levels agglomerated"
+                                       % (pgrid, "NCCL send/recv" if args.force_nccl else "peer-memory (CUDA-IPC)")) if world > 1 else "single GPU",
                        "l2_policy": "inputs (%.1f GB of fields per GPU) exceed the 126 MB L2; no explicit flush" % (45 * 8 * geom.nboxes * (n + 6) ** 3 / 1e9),
                        "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
                        "host_wall_ms_per_step": 1e3 * wall_host / args.steps},

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--case", default="rt3d")
     ap.add_argument("--size", dest="n", type=int, default=64)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--force-nccl", type=int, default=0, help="1: NCCL transport instead of the peer-memory transport")
     ap.add_argument("--fuse-min", type=int, default=128, help="smallest level the fused smoother runs on (16 forces it onto these small grids)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -50,6 +51,8 @@ def main():
     sub = geom.subset(mine)
     prm = V.default_params(nscal=nscal, bc_val=P.bcval)
     ctx = V.Context(dim, sub.boxes, geom.dlo, geom.dhi, geom.phys_bc, geom.dx, params=prm, device=local)
+    if args.force_nccl:
+        ctx.comm_tune(True)
     PAR.init_comm(ctx, rank, world, rlo, rhi)
     ctx.mg_tune(args.fuse_min, -1)
     pick = lambda mf: [mf[i] for i in mine]
@@ -64,6 +67,9 @@ def main():
         got = [np.full_like(a, np.nan) for a in pick(ref[key])]
         ctx.download_mf(fld, got, ng, nc)
         errs[key] = relerr(sub, got, pick(ref[key]), ng, full=False)
+        # ghost cells too (downloads carry the box's whole ghosted extent): only where the reference has them filled the same way --
+        # the whole-domain oracle run fills every box's ghosts by fill_boundary + physbc, as the device does for its region
+        errs[key + "_ghost"] = relerr(sub, got, pick(ref[key]), ng, full=True)
     ctx.close()
     worst = torch.tensor([max(errs.values())], dtype=torch.float64, device="cuda")
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)

@@ -86,6 +86,11 @@ def test_stagewise_parity(case):
     errs["vel_force_2"] = relerr(geom, download_like(ctx, geom, "VEL_FORCE", ref["vel_force_2"], 1, dim), ref["vel_force_2"], 1)
     ctx.update(True, dt)
     errs["unew"] = relerr(geom, download_like(ctx, geom, "UNEW", ref["unew"], 3, dim), ref["unew"], 3)
+    # ghost cells of every box, inter-box ghosts included (what ml_restrict_and_fill leaves behind, update.f90:103-107; hgproject's
+    # create_uvec reads rhohalf(lo-1:hi+1)): a download carries the box's whole ghosted extent
+    errs["snew_ghost"] = relerr(geom, download_like(ctx, geom, "SNEW", ref["snew"], 3, nscal), ref["snew"], 3, full=True)
+    errs["unew_ghost"] = relerr(geom, download_like(ctx, geom, "UNEW", ref["unew"], 3, dim), ref["unew"], 3, full=True)
+    errs["rhohalf_ghost"] = relerr(geom, download_like(ctx, geom, "RHOHALF", ref["rhohalf"], 1, 1), ref["rhohalf"], 1, full=True)
     ctx.close()
     print(case, {k: "%.2e" % v for k, v in errs.items()}, "vcycles", ncyc)
     bad = {k: v for k, v in errs.items() if not k.startswith("umac_proj") and not (v <= TOL_EDGE)}
@@ -123,9 +128,9 @@ def test_advance_host_pipelined(case):
         hs = ctx.host_state(uold=st["uold"], sold=st["sold"], gp=st["gp"], ext_vel_force=st["ext_vel_force"],
                             ext_scal_force=st["ext_scal_force"], **out)
         ctx.advance_host(dt, hs, mac_rel_eps=1e-13)
-        e_s = relerr(geom, out["snew"], ref["snew"], 3)
-        e_u = relerr(geom, out["unew"], ref["unew"], 3)
-        e_r = relerr(geom, out["rhohalf"], ref["rhohalf"], 1)
+        e_s = relerr(geom, out["snew"], ref["snew"], 3, full=True)          # ghost cells of every box included
+        e_u = relerr(geom, out["unew"], ref["unew"], 3, full=True)
+        e_r = relerr(geom, out["rhohalf"], ref["rhohalf"], 1, full=True)
         print(case, rep, "snew %.2e unew %.2e rhohalf %.2e" % (e_s, e_u, e_r))
         assert e_s <= 1e-10 and e_u <= 1e-10 and e_r <= 1e-10
     ctx.close()

@@ -16,10 +16,11 @@ def _ngpu():
 
 @pytest.mark.parametrize("case,n", [("rt3d", 64), ("rand3d", 32), ("per3d", 32), ("rt2d", 64)])
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("smoother", ["plain", "fused"])
+@pytest.mark.parametrize("smoother", ["plain", "fused", "fused_nccl"])
 def test_multi_gpu_parity(case, n, world, smoother):
     """plain: per-colour kernels with a 1-layer exchange per colour; fused: the fused smoother forced onto the rank-split levels (deep
-    single-phase ghost exchange: faces, edges and corners in one message set)"""
+    single-phase ghost exchange: faces, edges and corners in one message set); both through the peer-memory transport; fused_nccl: the same
+    exchanges through the NCCL transport"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     if case == "rt2d" and (world == 8 or smoother != "plain"):
@@ -27,7 +28,7 @@ def test_multi_gpu_parity(case, n, world, smoother):
     env = dict(os.environ)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--size", str(n),
-           "--fuse-min", "16" if smoother == "fused" else "128"]
+           "--fuse-min", "16" if smoother != "plain" else "128", "--force-nccl", "1" if smoother == "fused_nccl" else "0"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-2000:], r.stderr[-3000:])
     assert r.returncode == 0
