@@ -4,7 +4,10 @@
 #include "cuda_emu.h"
 #include "../../varden_b200/csrc/vdn_common.cuh"
 #include "../../varden_b200/csrc/vdn_godunov_kernels.cuh"
-#include "../../varden_b200/csrc/vdn_godunov_march.cuh"
+#ifndef MARCH_HEADER            // development: -DMARCH_HEADER='"/path/to/a/working/copy.cuh"'
+#define MARCH_HEADER "../../varden_b200/csrc/vdn_godunov_march.cuh"
+#endif
+#include MARCH_HEADER
 
 namespace {
 struct NoScope { };

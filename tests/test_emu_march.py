@@ -21,13 +21,16 @@ EMU = os.path.join(HERE, "emu")
 
 
 def build(ncg):
-    so = os.path.join(EMU, "libemu_march_ncg%d.so" % ncg)
+    dev = os.environ.get("VDN_MARCH_HEADER")                     # development: test a working copy of the kernel header
+    so = os.path.join(EMU, "libemu_march_ncg%d%s.so" % (ncg, "_dev" if dev else ""))
     csrc = os.path.join(HERE, "..", "varden_b200", "csrc")
     src = [os.path.join(EMU, "emu_godunov.cpp"), os.path.join(EMU, "cuda_emu.h"), os.path.join(csrc, "vdn_godunov_march.cuh"),
            os.path.join(csrc, "vdn_godunov_kernels.cuh"), os.path.join(csrc, "vdn_common.cuh")]
+    if dev:
+        src.append(dev)
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-DMARCH_TYT=6", "-DMARCH_NCG=%d" % ncg, src[0], "-o", so])
+                               "-DMARCH_TYT=6", "-DMARCH_NCG=%d" % ncg] + (['-DMARCH_HEADER="%s"' % dev] if dev else []) + [src[0], "-o", so])
     return C.CDLL(so)
 
 
@@ -39,6 +42,10 @@ def emu(request):
 CASES = {
     # periodic x,y / walls z (the bench problem), 2 x 4 tiles, 1 chunk
     "rt": lambda: O.rt_state([32, 12, 8], dim=3, max_grid_size=64),
+    # every spacing a power of two: the instantiation with x / h compiled as the exact product x * (1/h)
+    "rt_pow2": lambda: O.rt_state([32, 8, 16], dim=3, max_grid_size=64),
+    "mixed_pow2": lambda: O.random_state([16, 8, 8], dim=3, max_grid_size=64, phys_bc=[[W, IN], [PER, PER], [OUT, NS]], seed=21,
+                                         prob_hi=[1.0, 0.5, 0.5]),
     # every override type, non-cubic, tiles straddle every boundary
     "mixed": lambda: O.random_state([34, 10, 12], dim=3, max_grid_size=64, phys_bc=[[IN, OUT], [NS, W], [PER, PER]], seed=2),
     "outx_so2": lambda: O.random_state([12, 16, 12], dim=3, max_grid_size=32, phys_bc=[[OUT, IN], [PER, PER], [W, OUT]], seed=3,

@@ -194,7 +194,7 @@ extern "C" int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const
 }
 
 // ---- peer-memory transport: one kernel per exchange ----
-struct PullSeg { int peer; int lo[3], n[3], shift[3]; };
+struct PullSeg { int peer; int lo[3], n[3], shift[3]; int blk0; };      // blk0: first block of the flattened grid that works on this segment
 struct PullArgs {
     long arr_off;                   // byte offset, inside the symmetric heap, of the array's local element (0,0,0), comp 0
     int sy, sz, cs, nc;
@@ -202,9 +202,15 @@ struct PullArgs {
     char *const *peer_base; int me;
     unsigned long long epoch;
 };
-__global__ void k_halo_pull(PullArgs a)
+constexpr int PULL_NT = 256, PULL_UNR = 4;      // a block moves PULL_NT * PULL_UNR elements: all loads in flight before the first store
+// Reads over NVLink are latency-bound (~2 us round trip): the grid covers every element at once (one short block per 1024 elements) so
+// that the whole exchange costs about two round trips -- the flag, then the data -- instead of one per loop iteration.
+__global__ void __launch_bounds__(PULL_NT) k_halo_pull(PullArgs a)
 {
-    const PullSeg &s = a.seg[blockIdx.y];
+    int q = 0;
+#pragma unroll 1
+    for (int t = 1; t < a.nseg; ++t) if ((int)blockIdx.x >= a.seg[t].blk0) q = t;
+    const PullSeg &s = a.seg[q];
     if (threadIdx.x == 0) {
         // everything my stream produced before this kernel is complete: publish it, then wait until the rank this block reads from has
         // published the same exchange (its producing kernels are complete too)
@@ -220,13 +226,22 @@ __global__ void k_halo_pull(PullArgs a)
     double *dst = (double *)(a.peer_base[a.me] + a.arr_off);
     const long per = (long)s.n[0] * s.n[1] * s.n[2];
     const long tot = per * a.nc;
-    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(t / per); const long q = t - (long)c * per;
-        const int i = s.lo[0] + (int)(q % s.n[0]), j = s.lo[1] + (int)((q / s.n[0]) % s.n[1]), k = s.lo[2] + (int)(q / ((long)s.n[0] * s.n[1]));
-        const long d_ix = i + (long)a.sy * j + (long)a.sz * k + (long)a.cs * c;
-        const long s_ix = (i + s.shift[0]) + (long)a.sy * (j + s.shift[1]) + (long)a.sz * (k + s.shift[2]) + (long)a.cs * c;
-        dst[d_ix] = __ldcv(src + s_ix);             // peer memory: never through a stale L1 line
+    const long t0 = (long)((int)blockIdx.x - s.blk0) * (PULL_NT * PULL_UNR) + threadIdx.x;
+    double v[PULL_UNR]; long dix[PULL_UNR];
+#pragma unroll
+    for (int u = 0; u < PULL_UNR; ++u) {
+        const long t = t0 + (long)u * PULL_NT;
+        dix[u] = -1;
+        if (t < tot) {
+            const int c = (int)(t / per); const long r = t - (long)c * per;
+            const int i = s.lo[0] + (int)(r % s.n[0]), j = s.lo[1] + (int)((r / s.n[0]) % s.n[1]), k = s.lo[2] + (int)(r / ((long)s.n[0] * s.n[1]));
+            dix[u] = i + (long)a.sy * j + (long)a.sz * k + (long)a.cs * c;
+            const long s_ix = (i + s.shift[0]) + (long)a.sy * (j + s.shift[1]) + (long)a.sz * (k + s.shift[2]) + (long)a.cs * c;
+            v[u] = __ldcv(src + s_ix);              // peer memory: never through a stale L1 line
+        }
     }
+#pragma unroll
+    for (int u = 0; u < PULL_UNR; ++u) if (dix[u] >= 0) dst[dix[u]] = v[u];
 }
 
 static bool in_heap(const Comm *cm, const void *p)
@@ -249,17 +264,17 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int no
         PullArgs a;
         a.arr_off = (long)((const char *)v.p - cm->heap); a.sy = v.sy; a.sz = v.sz; a.cs = v.cs; a.nc = nc;
         a.nseg = nr; a.peer_base = cm->d_peer_base; a.me = cm->rank; a.epoch = ++cm->epoch;
-        long mx = 1, bytes = 0;
+        long bytes = 0; int nblk = 0;
         for (int q = 0; q < nr; ++q) {
             a.seg[q].peer = rpeer[q];
             long cnt = nc;
             for (int d = 0; d < 3; ++d) { a.seg[q].lo[d] = rlo[3 * q + d]; a.seg[q].n[d] = rn[3 * q + d]; a.seg[q].shift[d] = rsh[3 * q + d]; cnt *= rn[3 * q + d]; }
-            mx = std::max(mx, cnt); bytes += 8 * cnt;
+            a.seg[q].blk0 = nblk;
+            nblk += (int)((cnt + PULL_NT * PULL_UNR - 1) / (PULL_NT * PULL_UNR));
+            bytes += 8 * cnt;
         }
         c->comm_bytes += bytes;                      // pulled = what the peers would have sent (equal regions: symmetric)
-        // few blocks per segment: they all spin until their peer arrives, and the segments are surface data
-        dim3 gr((unsigned)std::min<long>(32, (mx + 255) / 256), nr);
-        k_halo_pull<<<gr, 256, 0, c->stream>>>(a);
+        k_halo_pull<<<nblk, PULL_NT, 0, c->stream>>>(a);
         VDN_CUDA(cudaGetLastError());
         return;
     }

@@ -18,6 +18,9 @@
 //     states that contain it; it needs the face value of the upper neighbour (shuffle down / shared memory / next iteration).
 //   * limited slopes: cen/lim/fromm (slope.f90:227-234) are evaluated once per cell and direction and exchanged the same way
 //     (the z direction keeps them in registers across iterations).
+//   * state that lives from one iteration to the next (the 1-D states of plane k-1, the z-face states of face k-1, in velpred also the z
+//     window / slope parts) is kept in per-thread "keep" words of shared memory, not in registers: at 512 threads per CTA a thread has 128
+//     registers, and the first build (all state in registers) spilled 140 B (mkflux) / 1 KB (velpred) per thread to local memory.
 // Operation order inside every expression follows the reference (the file is compiled with -fmad=false), so the results
 // are bit-identical to the staged kernels and to the CPU oracle; only the evaluation SITE of shared sub-expressions moves.
 //
@@ -135,23 +138,34 @@ struct MfmArgs {
     double dt2, c2[3], c3[3], c4[3], c6[3], hinv[3]; int hp2[3];
 };
 
-// ---- y exchange through shared memory: slot q holds one double per thread of the CTA ----
+// ---- per-CTA shared memory: slot q holds one double per thread of the CTA ----
+//  * exchange slots: a value written by row ty is read by row ty-1 / ty+1 after a barrier (conflict-free: consecutive lanes, consecutive words)
+//  * keep slots: per-thread state that lives from one iteration to the next (the L/R states of plane k-1, the z-face states of face k-1 ...).
+//    Holding it in registers costs more than 128 of them per thread (ncu, round 2 call 1: 23 local-memory loads + 11 stores per iteration,
+//    long-scoreboard the top stall); a thread reads and writes only its own word, so no barrier is involved.
 template <int TYT> struct YSlots {
     double *sm; int own, lo, hi;
     __device__ __forceinline__ YSlots(double *base, int tx, int ty) : sm(base), own(ty * TXT + tx),
         lo((ty > 0 ? ty - 1 : ty) * TXT + tx), hi((ty < TYT - 1 ? ty + 1 : ty) * TXT + tx) {}
     __device__ __forceinline__ void put(int q, double v) const { sm[q * (TXT * TYT) + own] = v; }
+    __device__ __forceinline__ double get(int q) const { return sm[q * (TXT * TYT) + own]; }       // own word (keep slots)
     __device__ __forceinline__ double from_lo(int q) const { return sm[q * (TXT * TYT) + lo]; }    // value of row ty-1
     __device__ __forceinline__ double from_hi(int q) const { return sm[q * (TXT * TYT) + hi]; }    // value of row ty+1
 };
-template <int NC> constexpr int mf_smem_slots() { return 4 * NC; }
+// MK_LXP .. MK_RYP are double-buffered by iteration parity (set 4*(k&1)): plane k-1 is still read in F after plane k was stored in T
+enum { MK_LXP = 0, MK_RXP, MK_LYP, MK_RYP, MK_LZH = 8, MK_LZXH, MK_LZYH, MK_LZF, MK_QZP, MK_XZXP, MK_XZYP, MK_FP, MK_NKEEP };
+template <int NC> constexpr int mf_smem_slots() { return (4 + MK_NKEEP) * NC; }
+
+// slope.f90:227-234 without the sign (recomputed from cen where it is needed: one LOP3)
+struct PartsZ { double cen, lim, fromm; };
 
 // ------------------------------------------------------------------------------------------
 // mkflux_3d.  NC components per launch (they share the MAC velocities, eps and all index work); bit c of CONSMASK:
 // component c is conservative (scalar_advance.f90:54-57).  GEN = false: slope_order 4, use_minion = F compiled in.
+// HP2: every mesh spacing is a power of two, so x / h is the exact product x * (1/h) (no division sequence, no branch).
 // grid = (tiles_x, tiles_y, z chunks), block = (32, TYT).
 // ------------------------------------------------------------------------------------------
-template <int NC, int CONSMASK, int TYT, bool GEN>
+template <int NC, int CONSMASK, int TYT, bool GEN, bool HP2>
 __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
 {
     VDN_DYN_SMEM(smem);
@@ -165,22 +179,22 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
     const int kb = (ka + a.zchunk < n2) ? ka + a.zchunk : n2;
     const bool lastchunk = kb == n2;
     const YSlots<TYT> Y(smem, tx, ty);
+    constexpr int KB = 4 * NC;                            // first keep slot
     const int order = GEN ? a.order : 4;
     const bool minion = GEN ? (a.use_minion != 0) : false;
 
     const bool inner = tx >= 1 && tx <= TXT - 2 && ty >= 1 && ty <= TYT - 2 && it <= n0 && jt <= n1;
     const bool st_x = inner && jt < n1, st_y = inner && it < n0, st_z = inner && it < n0 && jt < n1;
 
-    // physical-BC overrides on the region faces
+    // physical-BC overrides on the region faces (periodic / rank-interior faces have none: those tiles never enter the BC code)
     const int bcx0 = a.g.pbc[0][0], bcx1 = a.g.pbc[0][1], bcy0 = a.g.pbc[1][0], bcy1 = a.g.pbc[1][1], bcz0 = a.g.pbc[2][0], bcz1 = a.g.pbc[2][1];
     const bool xlo = bc_overrides(bcx0) && i == 0, xhi_c = bc_overrides(bcx1) && i == n0 - 1, xhi_f = bc_overrides(bcx1) && i == n0;
     const bool ylo = bc_overrides(bcy0) && j == 0, yhi_c = bc_overrides(bcy1) && j == n1 - 1, yhi_f = bc_overrides(bcy1) && j == n1;
-    // does any column of this CTA touch a physical x / y boundary, or need one-sided slopes there?  (uniform)
-    const bool tile_x = (blockIdx.x == 0) || ((int)blockIdx.x * TXO + TXT >= n0);
-    const bool tile_y = (blockIdx.y == 0) || ((int)blockIdx.y * (TYT - 2) + TYT >= n1);
+    const bool tile_x = (bc_overrides(bcx0) && blockIdx.x == 0) || (bc_overrides(bcx1) && (int)blockIdx.x * TXO + TXT >= n0);
+    const bool tile_y = (bc_overrides(bcy0) && blockIdx.y == 0) || (bc_overrides(bcy1) && (int)blockIdx.y * (TYT - 2) + TYT >= n1);
     const bool tile_xy = tile_x || tile_y;
 
-    // element offsets of (i, j, k = 0) in each layout; advanced by one plane per iteration through kofs
+    // element offsets of (i, j, k = 0) in each layout
     const int so = is + a.s_sy * js, fo = i + a.f_sy * j;
     const int mo0 = i + a.m_sy[0] * j, mo1 = i + a.m_sy[1] * j, mo2 = i + a.m_sy[2] * j;
     const int eo0 = i + a.e_sy[0] * j, eo1 = i + a.e_sy[1] * j, eo2 = i + a.e_sy[2] * j;
@@ -188,17 +202,14 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
     // eps: per reference box; the (i,j) part of the box index is fixed per thread
     const int nbt = a.g.nb[0] * a.g.nb[1] * a.g.nb[2];
     const int bij = nbt == 1 ? 0 : a.g.box1(0, i) + a.g.nb[0] * a.g.box1(1, j);
+    auto divh = [&](double x, int d) { return HP2 ? x * a.hinv[d] : div_h(x, a.g.h[d], a.hinv[d], a.hp2[d]); };
 
-    // ---- carried state ----
-    double s0[NC], sp1[NC], sp2[NC], sP[NC];          // s(k), s(k+1), s(k+2), s(k-1)
-    Parts pz0[NC];                                     // slope parts of cell k (z)
+    // ---- state carried in registers: the z window and the z slope parts; MAC data of plane k-1 ----
+    double s0[NC], sp1[NC], sp2[NC];                   // s(k), s(k+1), s(k+2)
+    PartsZ pz0[NC];                                    // slope parts of cell k (z)
     double frzm[NC];                                   // fromm_z(k-1)
-    double lxP[NC], rxP[NC], lyP[NC], ryP[NC];         // plane k-1: l at hi x/y face, r at lo x/y face (after BC)
-    double lzH[NC], lzxH[NC], lzyH[NC], LzH[NC];       // from cell k-1: L states of z-face k (1-D, corrected by x, by y, final)
-    double qzP[NC], XzxP[NC], XzyP[NC];                // z-face k-1: simh_z, s?zx, s?zy
-    double fP[NC];                                     // dt2*force(k-1)
     double umlP = 0, umhP = 0, vmlP = 0, vmhP = 0, wmlP = 0, wml = 0;
-    double epsP = 0;
+    FaceP PxP = { false, false }, PyP = { false, false };
 
     // prologue: z window around the first plane ka-1 and the slope parts that iteration needs
     {
@@ -208,28 +219,30 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             const double *sb = a.s[c] + so;
             const double sm3 = sb[(k - 2) * a.s_sz], sm2 = sb[(k - 1) * a.s_sz];
             s0[c] = sb[k * a.s_sz]; sp1[c] = sb[(k + 1) * a.s_sz]; sp2[c] = sb[(k + 2) * a.s_sz];
-            sP[c] = sm2;
-            pz0[c] = slope_parts3(sm2, s0[c], sp1[c]);
+            const Parts p0 = slope_parts3(sm2, s0[c], sp1[c]);
+            pz0[c].cen = p0.cen; pz0[c].lim = p0.lim; pz0[c].fromm = p0.fromm;
             frzm[c] = slope_parts3(sm3, sm2, s0[c]).fromm;
-            lxP[c] = rxP[c] = lyP[c] = ryP[c] = lzH[c] = lzxH[c] = lzyH[c] = LzH[c] = qzP[c] = XzxP[c] = XzyP[c] = fP[c] = ZERO;
+#pragma unroll
+            for (int q = 0; q < MK_NKEEP; ++q) Y.put(KB + q * NC + c, ZERO);
         }
         wml = a.mac[2][mo2 + k * a.m_sz[2]];
     }
 
     for (int k = ka - 1; k <= kb; ++k) {
         const bool zlo = bc_overrides(bcz0) && k == 0, zhi_c = bc_overrides(bcz1) && k == n2 - 1, zhi_f = bc_overrides(bcz1) && k == n2;
-        const bool bnd = tile_xy || zlo || zhi_c || zhi_f || k <= 1 || k >= n2 - 2;           // uniform: any BC work possible
+        // uniform: can this CTA meet any BC work in this iteration (overrides, one-sided slopes next to a physical face)?
+        const bool bnd = tile_xy || (bc_overrides(bcz0) && k <= 1) || (bc_overrides(bcz1) && k >= n2 - 2);
         const double eps = a.eps[nbt == 1 ? 0 : bij + a.g.nb[0] * a.g.nb[1] * a.g.box1(2, k)];
+        const int pc = 4 * (k & 1), pp = 4 - pc;                      // keep-slot sets of plane k / plane k-1
         // ---- MAC velocities of cell plane k ----
         const double uml = a.mac[0][mo0 + k * a.m_sz[0]], umh = a.mac[0][mo0 + k * a.m_sz[0] + 1];
         const double vml = a.mac[1][mo1 + k * a.m_sz[1]], vmh = a.mac[1][mo1 + k * a.m_sz[1] + a.m_sy[1]];
         const double wmh = a.mac[2][mo2 + (k + 1) * a.m_sz[2]];
         const FaceP Px = face_pred(uml, eps), Py = face_pred(vml, eps), Pz = face_pred(wml, eps);
-        const FaceP PxP = face_pred(umlP, epsP), PyP = face_pred(vmlP, epsP);
         // dt2*u/h at the lo and hi face of each direction
-        const double txl = div_h(a.dt2 * uml, a.g.h[0], a.hinv[0], a.hp2[0]), txh = div_h(a.dt2 * umh, a.g.h[0], a.hinv[0], a.hp2[0]);
-        const double tyl = div_h(a.dt2 * vml, a.g.h[1], a.hinv[1], a.hp2[1]), tyh = div_h(a.dt2 * vmh, a.g.h[1], a.hinv[1], a.hp2[1]);
-        const double tzl = div_h(a.dt2 * wml, a.g.h[2], a.hinv[2], a.hp2[2]), tzh = div_h(a.dt2 * wmh, a.g.h[2], a.hinv[2], a.hp2[2]);
+        const double txl = divh(a.dt2 * uml, 0), txh = divh(a.dt2 * umh, 0);
+        const double tyl = divh(a.dt2 * vml, 1), tyh = divh(a.dt2 * vmh, 1);
+        const double tzl = divh(a.dt2 * wml, 2), tzh = divh(a.dt2 * wmh, 2);
         // transverse factors of cell plane k (x, y) and k-1 (all)
         const double sux = umh + uml, suy = vmh + vml;
         const double suxP = umhP + umlP, suyP = vmhP + vmlP, suzP = wml + wmlP;
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                 if (byh && ty == TYT - 1 && j + 1 == n1 - 1) fry_e[c] = slope_onesided(sb[2 * a.s_sy], syp[c], s0[c], sym[c], true, order);
                 // z: pz1 belongs to cell k+1
                 if (bzl && k + 1 == 0)      pz1[c].fromm = slope_onesided(s0[c], sp1[c], sp2[c], snext[c], false, order);
-                if (bzh && k + 1 == n2 - 1) pz1[c].fromm = slope_onesided(sp2[c], sp1[c], s0[c], sP[c], true, order);
+                if (bzh && k + 1 == n2 - 1) pz1[c].fromm = slope_onesided(sp2[c], sp1[c], s0[c], sb[-a.s_sz], true, order);
             }
         }
         // exchange fromm_y (y) -- x by shuffle, z in registers
@@ -304,7 +317,8 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                 if (ty == TYT - 1) fyp = fry_e[c];
                 slx[c] = slope4_from(px[c], fxm, fxp);
                 sly[c] = slope4_from(py[c], fym, fyp);
-                slz[c] = slope4_from(pz0[c], frzm[c], pz1[c].fromm);
+                Parts pzc; pzc.cen = pz0[c].cen; pzc.lim = pz0[c].lim; pzc.flag = copysign(ONE, pz0[c].cen); pzc.fromm = pz0[c].fromm;
+                slz[c] = slope4_from(pzc, frzm[c], pz1[c].fromm);
             } else if (order == 2) {
                 slx[c] = px[c].fromm; sly[c] = py[c].fromm; slz[c] = pz0[c].fromm;
             } else { slx[c] = sly[c] = slz[c] = ZERO; }
@@ -338,7 +352,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                 if (xhi_c) lx[c] = mf_bc_hi(lx[c], sxp[c], 0, bcx1, a.is_vel, comp);
                 if (ylo) ry[c] = mf_bc_lo(ry[c], sym[c], 1, bcy0, a.is_vel, comp);
                 if (yhi_c) ly[c] = mf_bc_hi(ly[c], syp[c], 1, bcy1, a.is_vel, comp);
-                if (zlo) rz[c] = mf_bc_lo(rz[c], sP[c], 2, bcz0, a.is_vel, comp);
+                if (zlo) rz[c] = mf_bc_lo(rz[c], a.s[c][so + (k - 1) * a.s_sz], 2, bcz0, a.is_vel, comp);
                 if (zhi_c) lz[c] = mf_bc_hi(lz[c], sp1[c], 2, bcz1, a.is_vel, comp);
             }
             Y.put(NC + c, ly[c]);
@@ -346,7 +360,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
         __syncthreads();                                                                    // B2
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            double lxi = shfl_up1(lx[c]), lyi = Y.from_lo(NC + c), lzi = lzH[c];
+            double lxi = shfl_up1(lx[c]), lyi = Y.from_lo(NC + c), lzi = Y.get(KB + MK_LZH * NC + c);
             if (bnd) {
                 if (xlo) lxi = rx[c];
                 if (xhi_f) rx[c] = lxi;
@@ -361,29 +375,33 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
         __syncthreads();                                                                    // B3
         // ================= T: transverse terms and the six once-corrected states =================
         double Xxy[NC], Xyx[NC], Xzx[NC], Xzy[NC], Xxz[NC], Xyz[NC];
-        double lzxN[NC], lzyN[NC];
         double rxy[NC], ryx[NC], rzx[NC], rzy[NC], rxz[NC], ryz[NC], lxy[NC], lyx[NC], lxz[NC], lyz[NC];
+        double lzxi[NC], lzyi[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int comp = a.comp0 + c;
             const bool cons = (CONSMASK >> c) & 1;
             const double qxh = shfl_dn1(qx[c]), qyh = Y.from_hi(2 * NC + c);
+            const double qzP = Y.get(KB + MK_QZP * NC + c);
+            const double lxP = Y.get(KB + (pp + MK_LXP) * NC + c), rxP = Y.get(KB + (pp + MK_RXP) * NC + c);
+            const double lyP = Y.get(KB + (pp + MK_LYP) * NC + c), ryP = Y.get(KB + (pp + MK_RYP) * NC + c);
+            lzxi[c] = Y.get(KB + MK_LZXH * NC + c); lzyi[c] = Y.get(KB + MK_LZYH * NC + c);
             double ttx, tty, ttz;
             if (cons) {          // mkflux.f90:1620-1622
                 ttx = a.c3[0] * (qxh * umh - qx[c] * uml);
                 tty = a.c3[1] * (qyh * vmh - qy[c] * vml);
-                ttz = a.c3[2] * (qz[c] * wml - qzP[c] * wmlP);
+                ttz = a.c3[2] * (qz[c] * wml - qzP * wmlP);
             } else {             // :1624-1626
                 ttx = a.c6[0] * sux * (qxh - qx[c]);
                 tty = a.c6[1] * suy * (qyh - qy[c]);
-                ttz = a.c6[2] * suzP * (qz[c] - qzP[c]);
+                ttz = a.c6[2] * suzP * (qz[c] - qzP);
             }
             rxy[c] = rx[c] - tty; lxy[c] = lx[c] - tty;
             ryx[c] = ry[c] - ttx; lyx[c] = ly[c] - ttx;
-            rzx[c] = rz[c] - ttx; lzxN[c] = lz[c] - ttx;
-            rzy[c] = rz[c] - tty; lzyN[c] = lz[c] - tty;
-            rxz[c] = rxP[c] - ttz; lxz[c] = lxP[c] - ttz;
-            ryz[c] = ryP[c] - ttz; lyz[c] = lyP[c] - ttz;
+            rzx[c] = rz[c] - ttx; double lzxN = lz[c] - ttx;
+            rzy[c] = rz[c] - tty; double lzyN = lz[c] - tty;
+            rxz[c] = rxP - ttz; lxz[c] = lxP - ttz;
+            ryz[c] = ryP - ttz; lyz[c] = lyP - ttz;
             if (bnd) {
                 if (xlo || xhi_c) {
                     const double *sb = a.s[c] + so + k * a.s_sz;
@@ -397,9 +415,15 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                     if (ylo) { ryx[c] = mf_bc_lo(ryx[c], sym[c], 1, bcy0, a.is_vel, comp); ryz[c] = mf_bc_lo(ryz[c], sgP, 1, bcy0, a.is_vel, comp); }
                     else     { lyx[c] = mf_bc_hi(lyx[c], syp[c], 1, bcy1, a.is_vel, comp); lyz[c] = mf_bc_hi(lyz[c], sgP, 1, bcy1, a.is_vel, comp); }
                 }
-                if (zlo) { rzx[c] = mf_bc_lo(rzx[c], sP[c], 2, bcz0, a.is_vel, comp); rzy[c] = mf_bc_lo(rzy[c], sP[c], 2, bcz0, a.is_vel, comp); }
-                if (zhi_c) { lzxN[c] = mf_bc_hi(lzxN[c], sp1[c], 2, bcz1, a.is_vel, comp); lzyN[c] = mf_bc_hi(lzyN[c], sp1[c], 2, bcz1, a.is_vel, comp); }
+                if (zlo) { const double sg = a.s[c][so + (k - 1) * a.s_sz];
+                           rzx[c] = mf_bc_lo(rzx[c], sg, 2, bcz0, a.is_vel, comp); rzy[c] = mf_bc_lo(rzy[c], sg, 2, bcz0, a.is_vel, comp); }
+                if (zhi_c) { lzxN = mf_bc_hi(lzxN, sp1[c], 2, bcz1, a.is_vel, comp); lzyN = mf_bc_hi(lzyN, sp1[c], 2, bcz1, a.is_vel, comp); }
             }
+            // the L states this cell hands to z-face k+1, and the 1-D states the next iteration needs as "plane k-1"
+            Y.put(KB + MK_LZXH * NC + c, lzxN); Y.put(KB + MK_LZYH * NC + c, lzyN);
+            Y.put(KB + (pc + MK_LXP) * NC + c, lx[c]); Y.put(KB + (pc + MK_RXP) * NC + c, rx[c]);
+            Y.put(KB + (pc + MK_LYP) * NC + c, ly[c]); Y.put(KB + (pc + MK_RYP) * NC + c, ry[c]);
+            Y.put(KB + MK_LZH * NC + c, lz[c]); Y.put(KB + MK_QZP * NC + c, qz[c]);
             Y.put(3 * NC + c, lyx[c]); Y.put(c, lyz[c]);
         }
         __syncthreads();                                                                    // B4
@@ -407,17 +431,16 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
         for (int c = 0; c < NC; ++c) {
             double lxyi = shfl_up1(lxy[c]), lxzi = shfl_up1(lxz[c]);
             double lyxi = Y.from_lo(3 * NC + c), lyzi = Y.from_lo(c);
-            double lzxi = lzxH[c], lzyi = lzyH[c];
             if (bnd) {
                 if (xlo) { lxyi = rxy[c]; lxzi = rxz[c]; }
                 if (xhi_f) { rxy[c] = lxyi; rxz[c] = lxzi; }
                 if (ylo) { lyxi = ryx[c]; lyzi = ryz[c]; }
                 if (yhi_f) { ryx[c] = lyxi; ryz[c] = lyzi; }
-                if (zlo) { lzxi = rzx[c]; lzyi = rzy[c]; }
-                if (zhi_f) { rzx[c] = lzxi; rzy[c] = lzyi; }
+                if (zlo) { lzxi[c] = rzx[c]; lzyi[c] = rzy[c]; }
+                if (zhi_f) { rzx[c] = lzxi[c]; rzy[c] = lzyi[c]; }
             }
             Xxy[c] = upw_p(lxyi, rxy[c], Px); Xyx[c] = upw_p(lyxi, ryx[c], Py);
-            Xzx[c] = upw_p(lzxi, rzx[c], Pz); Xzy[c] = upw_p(lzyi, rzy[c], Pz);
+            Xzx[c] = upw_p(lzxi[c], rzx[c], Pz); Xzy[c] = upw_p(lzyi[c], rzy[c], Pz);
             Xxz[c] = upw_p(lxzi, rxz[c], PxP); Xyz[c] = upw_p(lyzi, ryz[c], PyP);
             Y.put(NC + c, Xyx[c]); Y.put(2 * NC + c, Xyz[c]);
         }
@@ -430,6 +453,8 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             const bool cons = (CONSMASK >> c) & 1;
             const double Xxyh = shfl_dn1(Xxy[c]), Xxzh = shfl_dn1(Xxz[c]);
             const double Xyxh = Y.from_hi(NC + c), Xyzh = Y.from_hi(2 * NC + c);
+            const double LzH = Y.get(KB + MK_LZF * NC + c), fP = Y.get(KB + MK_FP * NC + c);
+            const double XzxP = Y.get(KB + MK_XZXP * NC + c), XzyP = Y.get(KB + MK_XZYP * NC + c);
             // ---- sedge_z on face k: mkflux.f90:1870-1972 ----
             double Rz, LzN;
             if (cons) {
@@ -442,30 +467,35 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             }
             if (!minion) { Rz = Rz + fk[c]; LzN = LzN + fk[c]; }
             if (k >= ka && (k < kb || lastchunk)) {
-                double v = upw_p(LzH[c], Rz, Pz);
-                if (zlo) v = mf_bc_lo(Rz, sP[c], 2, bcz0, a.is_vel, comp);
-                if (zhi_f) v = mf_bc_hi(LzH[c], s0[c], 2, bcz1, a.is_vel, comp);
+                double v = upw_p(LzH, Rz, Pz);
+                if (zlo) v = mf_bc_lo(Rz, a.s[c][so + (k - 1) * a.s_sz], 2, bcz0, a.is_vel, comp);
+                if (zhi_f) v = mf_bc_hi(LzH, s0[c], 2, bcz1, a.is_vel, comp);
                 if (st_z) {
                     a.sedge[2][c][eo2 + k * a.e_sz[2]] = v;
                     if (cons) a.flux[2][c][eo2 + k * a.e_sz[2]] = v * wml;
                 }
             }
+            Y.put(KB + MK_LZF * NC + c, LzN); Y.put(KB + MK_FP * NC + c, fk[c]);
+            Y.put(KB + MK_XZXP * NC + c, Xzx[c]); Y.put(KB + MK_XZYP * NC + c, Xzy[c]);
             // ---- sedge_x, sedge_y on plane k-1: mkflux.f90:2310-2408, :2414-2512 ----
+            const double lxP = Y.get(KB + (pp + MK_LXP) * NC + c), rxP = Y.get(KB + (pp + MK_RXP) * NC + c);
+            const double lyP = Y.get(KB + (pp + MK_LYP) * NC + c), ryP = Y.get(KB + (pp + MK_RYP) * NC + c);
             double Rx, Lx;
             if (cons) {
-                const double A1 = a.c2[1] * (Xyzh * vmhP - Xyz[c] * vmlP), A2 = a.c2[2] * (Xzy[c] * wml - XzyP[c] * wmlP);
-                const double B1 = a.c2[1] * sP[c] * (vmhP - vmlP), B2 = a.c2[2] * sP[c] * (wml - wmlP);
-                Rx = rxP[c] - A1 - A2 + B1 + B2; Lx = lxP[c] - A1 - A2 + B1 + B2;
-                const double C1 = a.c2[0] * (Xxzh * umhP - Xxz[c] * umlP), C2 = a.c2[2] * (Xzx[c] * wml - XzxP[c] * wmlP);
-                const double D1 = a.c2[0] * sP[c] * (umhP - umlP), D2 = a.c2[2] * sP[c] * (wml - wmlP);
-                Ry[c] = ryP[c] - C1 - C2 + D1 + D2; Ly[c] = lyP[c] - C1 - C2 + D1 + D2;
+                const double sP = a.s[c][so + (k - 1) * a.s_sz];
+                const double A1 = a.c2[1] * (Xyzh * vmhP - Xyz[c] * vmlP), A2 = a.c2[2] * (Xzy[c] * wml - XzyP * wmlP);
+                const double B1 = a.c2[1] * sP * (vmhP - vmlP), B2 = a.c2[2] * sP * (wml - wmlP);
+                Rx = rxP - A1 - A2 + B1 + B2; Lx = lxP - A1 - A2 + B1 + B2;
+                const double C1 = a.c2[0] * (Xxzh * umhP - Xxz[c] * umlP), C2 = a.c2[2] * (Xzx[c] * wml - XzxP * wmlP);
+                const double D1 = a.c2[0] * sP * (umhP - umlP), D2 = a.c2[2] * sP * (wml - wmlP);
+                Ry[c] = ryP - C1 - C2 + D1 + D2; Ly[c] = lyP - C1 - C2 + D1 + D2;
             } else {
-                const double A1 = a.c4[1] * suyP * (Xyzh - Xyz[c]), A2 = a.c4[2] * suzP * (Xzy[c] - XzyP[c]);
-                Rx = rxP[c] - A1 - A2; Lx = lxP[c] - A1 - A2;
-                const double C1 = a.c4[0] * suxP * (Xxzh - Xxz[c]), C2 = a.c4[2] * suzP * (Xzx[c] - XzxP[c]);
-                Ry[c] = ryP[c] - C1 - C2; Ly[c] = lyP[c] - C1 - C2;
+                const double A1 = a.c4[1] * suyP * (Xyzh - Xyz[c]), A2 = a.c4[2] * suzP * (Xzy[c] - XzyP);
+                Rx = rxP - A1 - A2; Lx = lxP - A1 - A2;
+                const double C1 = a.c4[0] * suxP * (Xxzh - Xxz[c]), C2 = a.c4[2] * suzP * (Xzx[c] - XzxP);
+                Ry[c] = ryP - C1 - C2; Ly[c] = lyP - C1 - C2;
             }
-            if (!minion) { Rx = Rx + fP[c]; Lx = Lx + fP[c]; Ry[c] = Ry[c] + fP[c]; Ly[c] = Ly[c] + fP[c]; }
+            if (!minion) { Rx = Rx + fP; Lx = Lx + fP; Ry[c] = Ry[c] + fP; Ly[c] = Ly[c] + fP; }
             Y.put(3 * NC + c, Ly[c]);
             const double Lxi = shfl_up1(Lx);
             if (k > ka) {
@@ -473,14 +503,13 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                 if (bnd && (xlo || xhi_f)) {
                     const double *sb = a.s[c] + so + (k - 1) * a.s_sz;
                     if (xlo) v = mf_bc_lo(Rx, sb[-1], 0, bcx0, a.is_vel, comp);
-                    else     v = mf_bc_hi(Lxi, sP[c], 0, bcx1, a.is_vel, comp);
+                    else     v = mf_bc_hi(Lxi, sb[0], 0, bcx1, a.is_vel, comp);
                 }
                 if (st_x) {
                     a.sedge[0][c][eo0 + (k - 1) * a.e_sz[0]] = v;
                     if (cons) a.flux[0][c][eo0 + (k - 1) * a.e_sz[0]] = v * umlP;
                 }
             }
-            LzH[c] = LzN;
         }
         __syncthreads();                                                                    // B6
 #pragma unroll
@@ -493,25 +522,20 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                 if (bnd && (ylo || yhi_f)) {
                     const double *sb = a.s[c] + so + (k - 1) * a.s_sz;
                     if (ylo) v = mf_bc_lo(Ry[c], sb[-a.s_sy], 1, bcy0, a.is_vel, comp);
-                    else     v = mf_bc_hi(Lyi, sP[c], 1, bcy1, a.is_vel, comp);
+                    else     v = mf_bc_hi(Lyi, sb[0], 1, bcy1, a.is_vel, comp);
                 }
                 if (st_y) {
                     a.sedge[1][c][eo1 + (k - 1) * a.e_sz[1]] = v;
                     if (cons) a.flux[1][c][eo1 + (k - 1) * a.e_sz[1]] = v * vmlP;
                 }
             }
-            // ---- rotate the carried state ----
-            lxP[c] = lx[c]; rxP[c] = rx[c]; lyP[c] = ly[c]; ryP[c] = ry[c];
-            lzH[c] = lz[c]; lzxH[c] = lzxN[c]; lzyH[c] = lzyN[c];
-            qzP[c] = qz[c]; XzxP[c] = Xzx[c]; XzyP[c] = Xzy[c];
-            fP[c] = fk[c];
-            sP[c] = s0[c]; s0[c] = sp1[c]; sp1[c] = sp2[c]; sp2[c] = snext[c];
-            frzm[c] = pz0[c].fromm; pz0[c] = pz1[c];
+            // ---- rotate the register-carried state ----
+            s0[c] = sp1[c]; sp1[c] = sp2[c]; sp2[c] = snext[c];
+            frzm[c] = pz0[c].fromm; pz0[c].cen = pz1[c].cen; pz0[c].lim = pz1[c].lim; pz0[c].fromm = pz1[c].fromm;
         }
-        umlP = uml; umhP = umh; vmlP = vml; vmhP = vmh; wmlP = wml; wml = wmh; epsP = eps;
+        umlP = uml; umhP = umh; vmlP = vml; vmhP = vmh; wmlP = wml; wml = wmh; PxP = Px; PyP = Py;
     }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // velpred_3d.  Same march; the advecting velocity of a face is the Riemann value uimh_D(D) of the normal extrapolation, so the
@@ -528,7 +552,14 @@ struct VpmArgs {
     int zchunk;
     double dt2, c4[3], c6[3], hinv[3]; int hp2[3];
 };
-constexpr int vp_smem_slots() { return 6; }
+// keep slots (per-thread state across iterations, see YSlots): the 1-D states of plane k-1 (comps u, v; double-buffered by iteration parity)
+// and the z-face states of face k-1
+enum { VK_LX0 = 0, VK_LX1, VK_RX0, VK_RX1, VK_LY0, VK_LY1, VK_RY0, VK_RY1, VK_LZH0 = 16, VK_LZH1, VK_LZH2, VK_LZXH, VK_LZYH, VK_LZF,
+       VK_QZ0, VK_QZ1, VK_QZ2, VK_XZXP, VK_XZYP, VK_FPX, VK_FPY,
+       // the z window and z slope parts (7 per component): only the N stage touches them, so they are parked here during T and F
+       VK_ZP0, VK_NKEEP = VK_ZP0 + 21 };
+constexpr int VP_EX = 6;                                // exchange slots
+constexpr int vp_smem_slots() { return VP_EX + VK_NKEEP; }
 
 // velpred.f90:2044-2079 on the surviving state of a boundary face (normal extrapolation)
 __device__ __forceinline__ double vp_bcn_lo(double v, double ug, bool isn, int bc)
@@ -570,7 +601,7 @@ __device__ __forceinline__ double upt_p(double l, double r, TanP p)             
     return p.small ? uavg : v;
 }
 
-template <int TYT, bool GEN>
+template <int TYT, bool GEN, bool HP2>
 __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
 {
     VDN_DYN_SMEM(smem);
@@ -591,8 +622,8 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
     const int bcx0 = a.g.pbc[0][0], bcx1 = a.g.pbc[0][1], bcy0 = a.g.pbc[1][0], bcy1 = a.g.pbc[1][1], bcz0 = a.g.pbc[2][0], bcz1 = a.g.pbc[2][1];
     const bool xlo = bc_overrides(bcx0) && i == 0, xhi_c = bc_overrides(bcx1) && i == n0 - 1, xhi_f = bc_overrides(bcx1) && i == n0;
     const bool ylo = bc_overrides(bcy0) && j == 0, yhi_c = bc_overrides(bcy1) && j == n1 - 1, yhi_f = bc_overrides(bcy1) && j == n1;
-    const bool tile_x = (blockIdx.x == 0) || ((int)blockIdx.x * TXO + TXT >= n0);
-    const bool tile_y = (blockIdx.y == 0) || ((int)blockIdx.y * (TYT - 2) + TYT >= n1);
+    const bool tile_x = (bc_overrides(bcx0) && blockIdx.x == 0) || (bc_overrides(bcx1) && (int)blockIdx.x * TXO + TXT >= n0);
+    const bool tile_y = (bc_overrides(bcy0) && blockIdx.y == 0) || (bc_overrides(bcy1) && (int)blockIdx.y * (TYT - 2) + TYT >= n1);
     const bool tile_xy = tile_x || tile_y;
 
     const int uo = is + a.u_sy * js, fo = i + a.f_sy * j;
@@ -600,50 +631,76 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
     const int nbt = a.g.nb[0] * a.g.nb[1] * a.g.nb[2];
     const int bij = nbt == 1 ? 0 : a.g.box1(0, i) + a.g.nb[0] * a.g.box1(1, j);
 
-    // ---- carried state ----
-    double s0[3], sp1[3], sp2[3];                      // u(k), u(k+1), u(k+2)
-    Parts pz0[3]; double frzm[3];
-    double lxP[2], rxP[2], lyP[2], ryP[2];             // plane k-1: x faces comps (u, v), y faces comps (u, v)
-    double lzH[3], lzxH, lzyH, LzH;                    // from cell k-1: L states of z-face k
-    double qzP[3], XzxP, XzyP;                         // z-face k-1: uimh_z(3 comps), vimhzx, uimhzy
-    double fPx, fPy;                                   // dt2*force(k-1), comps u, v
-    double nsxP = 0, nsyP = 0, unxP = 0, unyP = 0, epsP = 0;
+    auto divh = [&](double x, int d) { return HP2 ? x * a.hinv[d] : div_h(x, a.g.h[d], a.hinv[d], a.hp2[d]); };
+    // ---- state carried in registers: the z window and the z slope parts; everything else of plane / face k-1 lives in the keep slots ----
+    double nsxP = 0, nsyP = 0, epsP = 0;
+    TanP tpxP = { false, false }, tpyP = { false, false };
+    auto KS = [&](int q) { return VP_EX + q; };
 
     {
         const int k = ka - 1;
+        double s0[3], sp1[3], sp2[3]; PartsZ pz0[3]; double frzm[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double *sb = a.u[c] + uo;
             const double sm3 = sb[(k - 2) * a.u_sz], sm2 = sb[(k - 1) * a.u_sz];
             s0[c] = sb[k * a.u_sz]; sp1[c] = sb[(k + 1) * a.u_sz]; sp2[c] = sb[(k + 2) * a.u_sz];
-            pz0[c] = slope_parts3(sm2, s0[c], sp1[c]);
+            const Parts p0 = slope_parts3(sm2, s0[c], sp1[c]);
+            pz0[c].cen = p0.cen; pz0[c].lim = p0.lim; pz0[c].fromm = p0.fromm;
             frzm[c] = slope_parts3(sm3, sm2, s0[c]).fromm;
-            lzH[c] = qzP[c] = ZERO;
         }
-        lxP[0] = lxP[1] = rxP[0] = rxP[1] = lyP[0] = lyP[1] = ryP[0] = ryP[1] = ZERO;
-        lzxH = lzyH = LzH = XzxP = XzyP = fPx = fPy = ZERO;
+#pragma unroll
+        for (int q = 0; q < VK_ZP0; ++q) Y.put(KS(q), ZERO);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Y.put(KS(VK_ZP0 + 7 * c), s0[c]); Y.put(KS(VK_ZP0 + 7 * c + 1), sp1[c]); Y.put(KS(VK_ZP0 + 7 * c + 2), sp2[c]);
+            Y.put(KS(VK_ZP0 + 7 * c + 3), pz0[c].cen); Y.put(KS(VK_ZP0 + 7 * c + 4), pz0[c].lim); Y.put(KS(VK_ZP0 + 7 * c + 5), pz0[c].fromm);
+            Y.put(KS(VK_ZP0 + 7 * c + 6), frzm[c]);
+        }
     }
 
     for (int k = ka - 1; k <= kb; ++k) {
         const bool zlo = bc_overrides(bcz0) && k == 0, zhi_c = bc_overrides(bcz1) && k == n2 - 1, zhi_f = bc_overrides(bcz1) && k == n2;
-        const bool bnd = tile_xy || zlo || zhi_c || zhi_f || k <= 1 || k >= n2 - 2;
+        const bool bnd = tile_xy || (bc_overrides(bcz0) && k <= 1) || (bc_overrides(bcz1) && k >= n2 - 2);
         const double eps = a.eps[nbt == 1 ? 0 : bij + a.g.nb[0] * a.g.nb[1] * a.g.box1(2, k)];
+        const int pc = 8 * (k & 1), pp = 8 - pc;                      // keep-slot sets of plane k / plane k-1
 
-        double snext[3], fk[3];
-        Parts px[3], py[3], pz1[3];
+        // ---- z direction first, one component at a time: un-park the z window / parts of cell k, finish the z slope, park the rotated
+        // state for the next iteration -- nothing of it stays in registers except u(k) itself ----
+        double s0[3], slz[3], fk[3];
+        Parts px[3], py[3];
         double sxm[3], sxp[3], sym[3], syp[3], frx_e[3], fry_e[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double *sb = a.u[c] + uo + k * a.u_sz;
             const int k3 = (k + 3 <= n2 + 2) ? 3 : 2;
-            snext[c] = sb[k3 * a.u_sz];
+            const double snext = sb[k3 * a.u_sz];
+            s0[c] = Y.get(KS(VK_ZP0 + 7 * c));
+            const double sp1 = Y.get(KS(VK_ZP0 + 7 * c + 1)), sp2 = Y.get(KS(VK_ZP0 + 7 * c + 2));
+            Parts pzc; pzc.cen = Y.get(KS(VK_ZP0 + 7 * c + 3)); pzc.lim = Y.get(KS(VK_ZP0 + 7 * c + 4)); pzc.fromm = Y.get(KS(VK_ZP0 + 7 * c + 5));
+            pzc.flag = copysign(ONE, pzc.cen);
+            const double frzm = Y.get(KS(VK_ZP0 + 7 * c + 6));
+            Parts pz1 = slope_parts3(s0[c], sp1, sp2);
+            const bool bzl = a.sbc[c][2][0] == BC_EXT_DIR || a.sbc[c][2][0] == BC_HOEXTRAP, bzh = a.sbc[c][2][1] == BC_EXT_DIR || a.sbc[c][2][1] == BC_HOEXTRAP;
+            if (bnd && order != 0) {       // one-sided slopes next to an EXT_DIR / HOEXTRAP z face (pz1 belongs to cell k+1)
+                if (bzl && k + 1 == 0)      pz1.fromm = slope_onesided(s0[c], sp1, sp2, snext, false, order);
+                if (bzh && k + 1 == n2 - 1) pz1.fromm = slope_onesided(sp2, sp1, s0[c], sb[-a.u_sz], true, order);
+            }
+            slz[c] = order == 4 ? slope4_from(pzc, frzm, pz1.fromm) : (order == 2 ? pzc.fromm : ZERO);
+            if (bnd && order != 0) {
+                if ((bzl && k == 0) || (bzh && k == n2 - 1)) slz[c] = pzc.fromm;
+                if ((bzl && k == -1) || (bzh && k == n2)) slz[c] = ZERO;
+            }
+            Y.put(KS(VK_ZP0 + 7 * c), sp1); Y.put(KS(VK_ZP0 + 7 * c + 1), sp2); Y.put(KS(VK_ZP0 + 7 * c + 2), snext);
+            Y.put(KS(VK_ZP0 + 7 * c + 3), pz1.cen); Y.put(KS(VK_ZP0 + 7 * c + 4), pz1.lim); Y.put(KS(VK_ZP0 + 7 * c + 5), pz1.fromm);
+            Y.put(KS(VK_ZP0 + 7 * c + 6), pzc.fromm);
+            // ---- x, y: parts of this cell; fromm of the neighbours comes by shuffle / shared memory after the barrier ----
             sxm[c] = sb[-1]; sxp[c] = sb[1]; sym[c] = sb[-a.u_sy]; syp[c] = sb[a.u_sy];
             fk[c] = a.dt2 * a.force[c][fo + k * a.f_sz];
             frx_e[c] = fry_e[c] = ZERO;
             if (order != 0) {
                 px[c] = slope_parts3(sxm[c], s0[c], sxp[c]);
                 py[c] = slope_parts3(sym[c], s0[c], syp[c]);
-                pz1[c] = slope_parts3(s0[c], sp1[c], sp2[c]);
                 if (order == 4) {
                     if (tx == 0 || tx == TXT - 1) {
                         const double s2 = sb[tx == 0 ? -2 : (it <= n0 ? 2 : 1)];
@@ -655,22 +712,15 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
                     }
                 }
             }
-        }
-        if (bnd && order != 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double *sb = a.u[c] + uo + k * a.u_sz;
+            if (bnd && order != 0) {
                 const bool bxl = a.sbc[c][0][0] == BC_EXT_DIR || a.sbc[c][0][0] == BC_HOEXTRAP, bxh = a.sbc[c][0][1] == BC_EXT_DIR || a.sbc[c][0][1] == BC_HOEXTRAP;
                 const bool byl = a.sbc[c][1][0] == BC_EXT_DIR || a.sbc[c][1][0] == BC_HOEXTRAP, byh = a.sbc[c][1][1] == BC_EXT_DIR || a.sbc[c][1][1] == BC_HOEXTRAP;
-                const bool bzl = a.sbc[c][2][0] == BC_EXT_DIR || a.sbc[c][2][0] == BC_HOEXTRAP, bzh = a.sbc[c][2][1] == BC_EXT_DIR || a.sbc[c][2][1] == BC_HOEXTRAP;
                 if (bxl && i == 0)      px[c].fromm = slope_onesided(sxm[c], s0[c], sxp[c], sb[2], false, order);
                 if (bxh && i == n0 - 1) px[c].fromm = slope_onesided(sxp[c], s0[c], sxm[c], sb[-2], true, order);
                 if (bxh && tx == TXT - 1 && i + 1 == n0 - 1) frx_e[c] = slope_onesided(sb[2], sxp[c], s0[c], sxm[c], true, order);
                 if (byl && j == 0)      py[c].fromm = slope_onesided(sym[c], s0[c], syp[c], sb[2 * a.u_sy], false, order);
                 if (byh && j == n1 - 1) py[c].fromm = slope_onesided(syp[c], s0[c], sym[c], sb[-2 * a.u_sy], true, order);
                 if (byh && ty == TYT - 1 && j + 1 == n1 - 1) fry_e[c] = slope_onesided(sb[2 * a.u_sy], syp[c], s0[c], sym[c], true, order);
-                if (bzl && k + 1 == 0)      pz1[c].fromm = slope_onesided(s0[c], sp1[c], sp2[c], snext[c], false, order);
-                if (bzh && k + 1 == n2 - 1) pz1[c].fromm = slope_onesided(sp2[c], sp1[c], s0[c], sb[-a.u_sz], true, order);
             }
         }
         if (order == 4) {
@@ -678,7 +728,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
             for (int c = 0; c < 3; ++c) Y.put(c, py[c].fromm);
         }
         __syncthreads();                                                                    // B1
-        double slx[3], sly[3], slz[3];
+        double slx[3], sly[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             if (order == 4) {
@@ -690,33 +740,29 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
                 if (ty == TYT - 1) fyp = fry_e[c];
                 slx[c] = slope4_from(px[c], fxm, fxp);
                 sly[c] = slope4_from(py[c], fym, fyp);
-                slz[c] = slope4_from(pz0[c], frzm[c], pz1[c].fromm);
             } else if (order == 2) {
-                slx[c] = px[c].fromm; sly[c] = py[c].fromm; slz[c] = pz0[c].fromm;
-            } else { slx[c] = sly[c] = slz[c] = ZERO; }
+                slx[c] = px[c].fromm; sly[c] = py[c].fromm;
+            } else { slx[c] = sly[c] = ZERO; }
         }
         if (bnd && order != 0) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const bool bxl = a.sbc[c][0][0] == BC_EXT_DIR || a.sbc[c][0][0] == BC_HOEXTRAP, bxh = a.sbc[c][0][1] == BC_EXT_DIR || a.sbc[c][0][1] == BC_HOEXTRAP;
                 const bool byl = a.sbc[c][1][0] == BC_EXT_DIR || a.sbc[c][1][0] == BC_HOEXTRAP, byh = a.sbc[c][1][1] == BC_EXT_DIR || a.sbc[c][1][1] == BC_HOEXTRAP;
-                const bool bzl = a.sbc[c][2][0] == BC_EXT_DIR || a.sbc[c][2][0] == BC_HOEXTRAP, bzh = a.sbc[c][2][1] == BC_EXT_DIR || a.sbc[c][2][1] == BC_HOEXTRAP;
                 if ((bxl && i == 0) || (bxh && i == n0 - 1)) slx[c] = px[c].fromm;
                 if ((bxl && i == -1) || (bxh && i == n0)) slx[c] = ZERO;
                 if ((byl && j == 0) || (byh && j == n1 - 1)) sly[c] = py[c].fromm;
                 if ((byl && j == -1) || (byh && j == n1)) sly[c] = ZERO;
-                if ((bzl && k == 0) || (bzh && k == n2 - 1)) slz[c] = pz0[c].fromm;
-                if ((bzl && k == -1) || (bzh && k == n2)) slz[c] = ZERO;
             }
         }
         // normal extrapolation of all comps to the six faces of the cell: velpred.f90:2022-2029 (x), :2108-2115 (y), :2286-2293 (z).
         // Operation-order quirks: x, z: dt2*max(0,u)/h ; y left state: dt2*max(0,u/h)
-        const double clx = HALF - div_h(a.dt2 * fmax(ZERO, s0[0]), a.g.h[0], a.hinv[0], a.hp2[0]);
-        const double crx = HALF + div_h(a.dt2 * fmin(ZERO, s0[0]), a.g.h[0], a.hinv[0], a.hp2[0]);
-        const double cly = HALF - a.dt2 * fmax(ZERO, div_h(s0[1], a.g.h[1], a.hinv[1], a.hp2[1]));
-        const double cry = HALF + div_h(a.dt2 * fmin(ZERO, s0[1]), a.g.h[1], a.hinv[1], a.hp2[1]);
-        const double clz = HALF - div_h(a.dt2 * fmax(ZERO, s0[2]), a.g.h[2], a.hinv[2], a.hp2[2]);
-        const double crz = HALF + div_h(a.dt2 * fmin(ZERO, s0[2]), a.g.h[2], a.hinv[2], a.hp2[2]);
+        const double clx = HALF - divh(a.dt2 * fmax(ZERO, s0[0]), 0);
+        const double crx = HALF + divh(a.dt2 * fmin(ZERO, s0[0]), 0);
+        const double cly = HALF - a.dt2 * fmax(ZERO, divh(s0[1], 1));
+        const double cry = HALF + divh(a.dt2 * fmin(ZERO, s0[1]), 1);
+        const double clz = HALF - divh(a.dt2 * fmax(ZERO, s0[2]), 2);
+        const double crz = HALF + divh(a.dt2 * fmin(ZERO, s0[2]), 2);
         double lx[3], rx[3], ly[3], ry[3], lz[3], rz[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -732,7 +778,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
                 if (ylo) ry[c] = vp_bcn_lo(ry[c], sym[c], c == 1, bcy0);
                 if (yhi_c) ly[c] = vp_bcn_hi(ly[c], syp[c], c == 1, bcy1, false);
                 if (zlo) rz[c] = vp_bcn_lo(rz[c], a.u[c][uo + (k - 1) * a.u_sz], c == 2, bcz0);
-                if (zhi_c) lz[c] = vp_bcn_hi(lz[c], sp1[c], c == 2, bcz1, false);
+                if (zhi_c) lz[c] = vp_bcn_hi(lz[c], a.u[c][uo + (k + 1) * a.u_sz], c == 2, bcz1, false);
             }
             Y.put(3 + c, ly[c]);
         }
@@ -742,7 +788,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
             double lxi[3], lyi[3], lzi[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                lxi[c] = shfl_up1(lx[c]); lyi[c] = Y.from_lo(3 + c); lzi[c] = lzH[c];
+                lxi[c] = shfl_up1(lx[c]); lyi[c] = Y.from_lo(3 + c); lzi[c] = Y.get(KS(VK_LZH0 + c));
                 if (bnd) {
                     if (xlo) lxi[c] = rx[c];
                     if (xhi_f) rx[c] = lxi[c];
@@ -765,6 +811,9 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
         double qxh[3], qyh[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { qxh[c] = shfl_dn1(qx[c]); qyh[c] = Y.from_hi(c); }
+        double qzP[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) qzP[c] = Y.get(KS(VK_QZ0 + c));
         const double nsx = qxh[0] + qx[0], nsy = qyh[1] + qy[1], nszP = qz[2] + qzP[2];
         const double ttx_y = a.c6[0] * nsx * (qxh[1] - qx[1]), ttx_z = a.c6[0] * nsx * (qxh[2] - qx[2]);
         const double tty_x = a.c6[1] * nsy * (qyh[0] - qy[0]), tty_z = a.c6[1] * nsy * (qyh[2] - qy[2]);
@@ -775,8 +824,8 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
         double ryx = ry[2] - ttx_z, lyx = ly[2] - ttx_z;
         double rzx = rz[1] - ttx_y, lzxN = lz[1] - ttx_y;
         double rzy = rz[0] - tty_x, lzyN = lz[0] - tty_x;
-        double rxz = rxP[1] - ttz_y, lxz = lxP[1] - ttz_y;
-        double ryz = ryP[0] - ttz_x, lyz = lyP[0] - ttz_x;
+        double rxz = Y.get(KS(pp + VK_RX1)) - ttz_y, lxz = Y.get(KS(pp + VK_LX1)) - ttz_y;
+        double ryz = Y.get(KS(pp + VK_RY0)) - ttz_x, lyz = Y.get(KS(pp + VK_LY0)) - ttz_x;
         if (bnd) {
             if (xlo || xhi_c) {
                 const int o = uo + k * a.u_sz + (xlo ? -1 : 1);
@@ -789,8 +838,15 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
                 else     { lyx = vp_bct(lyx, a.u[2][o], bcy1); lyz = vp_bct(lyz, a.u[0][o - a.u_sz], bcy1); }
             }
             if (zlo) { const int o = uo + (k - 1) * a.u_sz; rzx = vp_bct(rzx, a.u[1][o], bcz0); rzy = vp_bct(rzy, a.u[0][o], bcz0); }
-            if (zhi_c) { lzxN = vp_bct(lzxN, sp1[1], bcz1); lzyN = vp_bct(lzyN, sp1[0], bcz1); }
+            if (zhi_c) { const int o = uo + (k + 1) * a.u_sz; lzxN = vp_bct(lzxN, a.u[1][o], bcz1); lzyN = vp_bct(lzyN, a.u[0][o], bcz1); }
         }
+        const double lzxH = Y.get(KS(VK_LZXH)), lzyH = Y.get(KS(VK_LZYH));
+        // hand-over to the next iteration: the L states of z-face k+1 and the 1-D states of this plane (comps u, v)
+        Y.put(KS(VK_LZXH), lzxN); Y.put(KS(VK_LZYH), lzyN);
+        Y.put(KS(pc + VK_LX0), lx[0]); Y.put(KS(pc + VK_LX1), lx[1]); Y.put(KS(pc + VK_RX0), rx[0]); Y.put(KS(pc + VK_RX1), rx[1]);
+        Y.put(KS(pc + VK_LY0), ly[0]); Y.put(KS(pc + VK_LY1), ly[1]); Y.put(KS(pc + VK_RY0), ry[0]); Y.put(KS(pc + VK_RY1), ry[1]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { Y.put(KS(VK_LZH0 + c), lz[c]); Y.put(KS(VK_QZ0 + c), qz[c]); }
         Y.put(3, lyx); Y.put(4, lyz);
         __syncthreads();                                                                    // B4
         double Xxy, Xyx, Xzx, Xzy, Xxz, Xyz;
@@ -805,7 +861,6 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
                 if (zhi_f) { rzx = lzxi; rzy = lzyi; }
             }
             const TanP tpx = tan_pred(qx[0], eps), tpy = tan_pred(qy[1], eps), tpz = tan_pred(qz[2], eps);
-            const TanP tpxP = tan_pred(unxP, epsP), tpyP = tan_pred(unyP, epsP);
             Xxy = upt_p(lxyi, rxy, tpx); Xyx = upt_p(lyxi, ryx, tpy);
             Xzx = upt_p(lzxi, rzx, tpz); Xzy = upt_p(lzyi, rzy, tpz);
             Xxz = upt_p(lxzi, rxz, tpxP); Xyz = upt_p(lyzi, ryz, tpyP);
@@ -816,6 +871,8 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
         double Ly, Ry;
         {
             const double Xxyh = shfl_dn1(Xxy), Xxzh = shfl_dn1(Xxz), Xyxh = Y.from_hi(0), Xyzh = Y.from_hi(1);
+            const double LzH = Y.get(KS(VK_LZF)), XzxP = Y.get(KS(VK_XZXP)), XzyP = Y.get(KS(VK_XZYP));
+            const double fPx = Y.get(KS(VK_FPX)), fPy = Y.get(KS(VK_FPY));
             // wmac on face k: velpred.f90:2373-2419
             const double A1 = a.c4[0] * nsx * (Xxyh - Xxy), A2 = a.c4[1] * nsy * (Xyxh - Xyx);
             double Rz = rz[2] - A1 - A2, LzN = lz[2] - A1 - A2;
@@ -823,15 +880,15 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
             if (k >= ka && (k < kb || lastchunk)) {
                 double v = riemann_p(LzH, Rz, eps);
                 if (zlo)   v = (bcz0 == BC_INLET) ? a.u[2][uo + (k - 1) * a.u_sz] : (bcz0 == BC_OUTLET ? fmin(Rz, ZERO) : ZERO);
-                if (zhi_f) v = (bcz1 == BC_INLET) ? s0[2] : (bcz1 == BC_OUTLET ? fmax(LzH, ZERO) : ZERO);
+                if (zhi_f) v = (bcz1 == BC_INLET) ? a.u[2][uo + k * a.u_sz] : (bcz1 == BC_OUTLET ? fmax(LzH, ZERO) : ZERO);
                 if (st_z) a.out[2][oo2 + k * a.o_sz[2]] = v;
             }
-            LzH = LzN;
+            Y.put(KS(VK_LZF), LzN); Y.put(KS(VK_XZXP), Xzx); Y.put(KS(VK_XZYP), Xzy); Y.put(KS(VK_FPX), fk[0]); Y.put(KS(VK_FPY), fk[1]);
             // umac, vmac on plane k-1: velpred.f90:2617-2659, :2665-2707
             const double B1 = a.c4[1] * nsyP * (Xyzh - Xyz), B2 = a.c4[2] * nszP * (Xzy - XzyP);
-            double Rx = rxP[0] - B1 - B2, Lx = lxP[0] - B1 - B2;
+            double Rx = Y.get(KS(pp + VK_RX0)) - B1 - B2, Lx = Y.get(KS(pp + VK_LX0)) - B1 - B2;
             const double C1 = a.c4[0] * nsxP * (Xxzh - Xxz), C2 = a.c4[2] * nszP * (Xzx - XzxP);
-            Ry = ryP[1] - C1 - C2; Ly = lyP[1] - C1 - C2;
+            Ry = Y.get(KS(pp + VK_RY1)) - C1 - C2; Ly = Y.get(KS(pp + VK_LY1)) - C1 - C2;
             if (!minion) { Rx = Rx + fPx; Lx = Lx + fPx; Ry = Ry + fPy; Ly = Ly + fPy; }
             Y.put(3, Ly);
             const double Lxi = shfl_up1(Lx);
@@ -854,17 +911,9 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
             }
             if (st_y) a.out[1][oo1 + (k - 1) * a.o_sz[1]] = v;
         }
-        // ---- rotate ----
-        lxP[0] = lx[0]; lxP[1] = lx[1]; rxP[0] = rx[0]; rxP[1] = rx[1];
-        lyP[0] = ly[0]; lyP[1] = ly[1]; ryP[0] = ry[0]; ryP[1] = ry[1];
-        lzxH = lzxN; lzyH = lzyN; XzxP = Xzx; XzyP = Xzy;
-        fPx = fk[0]; fPy = fk[1]; nsxP = nsx; nsyP = nsy; unxP = qx[0]; unyP = qy[1]; epsP = eps;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            lzH[c] = lz[c]; qzP[c] = qz[c];
-            s0[c] = sp1[c]; sp1[c] = sp2[c]; sp2[c] = snext[c];
-            frzm[c] = pz0[c].fromm; pz0[c] = pz1[c];
-        }
+        // ---- rotate the register-carried state ----
+        nsxP = nsx; nsyP = nsy; epsP = eps; tpxP = tan_pred(qx[0], eps); tpyP = tan_pred(qy[1], eps);
+
     }
 }
 
@@ -929,8 +978,10 @@ void mkflux_march_group(L &launch, MfmArgs &a, int consmask, bool gen, int slots
     constexpr int TYT = MARCH_TYT;
     const size_t smem = sizeof(double) * TXT * TYT * mf_smem_slots<NC>();
     a.nc = NC;
-    if (consmask) { if (gen) march_launch<TYT>(launch, k_mkflux_march<NC, 1, TYT, true>, a, a.g, smem, slots); else march_launch<TYT>(launch, k_mkflux_march<NC, 1, TYT, false>, a, a.g, smem, slots); }
-    else          { if (gen) march_launch<TYT>(launch, k_mkflux_march<NC, 0, TYT, true>, a, a.g, smem, slots); else march_launch<TYT>(launch, k_mkflux_march<NC, 0, TYT, false>, a, a.g, smem, slots); }
+    const bool hp2 = a.hp2[0] && a.hp2[1] && a.hp2[2];
+    // the common case (slope_order 4, no Minion forcing, power-of-two spacings) is compiled in; everything else takes the general instantiation
+    if (consmask) { if (gen || !hp2) march_launch<TYT>(launch, k_mkflux_march<NC, 1, TYT, true, false>, a, a.g, smem, slots); else march_launch<TYT>(launch, k_mkflux_march<NC, 1, TYT, false, true>, a, a.g, smem, slots); }
+    else          { if (gen || !hp2) march_launch<TYT>(launch, k_mkflux_march<NC, 0, TYT, true, false>, a, a.g, smem, slots); else march_launch<TYT>(launch, k_mkflux_march<NC, 0, TYT, false, true>, a, a.g, smem, slots); }
 }
 
 // mkflux.f90:16 for ncomp components of s.  adv_bc: [comp][3][2] of these components.  Conservative: comp 0 of the scalars.
@@ -990,8 +1041,8 @@ void velpred_march(L &launch, const Geo &g, const View &u, const View &force, co
     const size_t smem = sizeof(double) * TXT * TYT * vp_smem_slots();
     // SURVEY 8(a) a2 bytes: R u 24 + force 24, W three face arrays 24
     auto ls = launch.scope("velpred", (double)g.n[0] * g.n[1] * g.n[2] * 72.0, 1);
-    if (order == 4 && !use_minion) march_launch<TYT>(launch, k_velpred_march<TYT, false>, a, g, smem, slots);
-    else                           march_launch<TYT>(launch, k_velpred_march<TYT, true>, a, g, smem, slots);
+    if (order == 4 && !use_minion && a.hp2[0] && a.hp2[1] && a.hp2[2]) march_launch<TYT>(launch, k_velpred_march<TYT, false, true>, a, g, smem, slots);
+    else                                                                march_launch<TYT>(launch, k_velpred_march<TYT, true, false>, a, g, smem, slots);
 }
 
 } // namespace march
