@@ -227,12 +227,13 @@ __global__ void __launch_bounds__(PULL_NT) k_halo_pull(PullArgs a)
     const long per = (long)s.n[0] * s.n[1] * s.n[2];
     const long tot = per * a.nc;
     const long t0 = (long)((int)blockIdx.x - s.blk0) * (PULL_NT * PULL_UNR) + threadIdx.x;
-    double v[PULL_UNR]; long dix[PULL_UNR];
+    double v[PULL_UNR]; long dix[PULL_UNR]; bool ok[PULL_UNR];        // (ghost cells have negative offsets: validity is a flag of its own)
 #pragma unroll
     for (int u = 0; u < PULL_UNR; ++u) {
         const long t = t0 + (long)u * PULL_NT;
-        dix[u] = -1;
-        if (t < tot) {
+        dix[u] = 0; v[u] = 0.0;
+        ok[u] = t < tot;
+        if (ok[u]) {
             const int c = (int)(t / per); const long r = t - (long)c * per;
             const int i = s.lo[0] + (int)(r % s.n[0]), j = s.lo[1] + (int)((r / s.n[0]) % s.n[1]), k = s.lo[2] + (int)(r / ((long)s.n[0] * s.n[1]));
             dix[u] = i + (long)a.sy * j + (long)a.sz * k + (long)a.cs * c;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(PULL_NT) k_halo_pull(PullArgs a)
         }
     }
 #pragma unroll
-    for (int u = 0; u < PULL_UNR; ++u) if (dix[u] >= 0) dst[dix[u]] = v[u];
+    for (int u = 0; u < PULL_UNR; ++u) if (ok[u]) dst[dix[u]] = v[u];
 }
 
 static bool in_heap(const Comm *cm, const void *p)

@@ -43,6 +43,33 @@ constexpr int TXO = TXT - 2;        // output columns per tile row
 #define VDN_DYN_SMEM(name) extern __shared__ double name[]
 #endif
 
+// Synchronisation of the y exchange.  A row of the thread tile is one warp and only exchanges with the rows above and below it, so a
+// CTA-wide barrier is more than the data flow needs: with MARCH_PAIRBAR every pair of adjacent rows owns one named barrier (ids 1..TYT-1);
+// even rows meet their upper neighbour first, odd rows their lower one, so an exchange costs two 64-thread barriers per warp and the warps of
+// a CTA may drift apart by a phase per row instead of all waiting for the slowest one.
+#ifndef MARCH_PAIRBAR
+#define MARCH_PAIRBAR 0
+#endif
+#ifndef MARCH_MINB
+#define MARCH_MINB 1         // resident CTAs per SM the register allocation aims for
+#endif
+template <int TYT> __device__ __forceinline__ void row_sync(int ty)
+{
+#if MARCH_PAIRBAR && !defined(VDN_EMU)
+    static_assert(TYT <= 16, "one hardware barrier per pair of rows");
+    const int up = ty + 1, dn = ty;                       // barrier ids of the pairs (ty, ty+1) and (ty-1, ty)
+    if ((ty & 1) == 0) {
+        if (ty < TYT - 1) asm volatile("bar.sync %0, 64;" :: "r"(up) : "memory");
+        if (ty > 0)       asm volatile("bar.sync %0, 64;" :: "r"(dn) : "memory");
+    } else {
+        asm volatile("bar.sync %0, 64;" :: "r"(dn) : "memory");
+        if (ty < TYT - 1) asm volatile("bar.sync %0, 64;" :: "r"(up) : "memory");
+    }
+#else
+    (void)ty; __syncthreads();
+#endif
+}
+
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
@@ -166,7 +193,7 @@ struct PartsZ { double cen, lim, fromm; };
 // grid = (tiles_x, tiles_y, z chunks), block = (32, TYT).
 // ------------------------------------------------------------------------------------------
 template <int NC, int CONSMASK, int TYT, bool GEN, bool HP2>
-__global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
+__global__ void __launch_bounds__(TXT * TYT, MARCH_MINB) k_mkflux_march(const MfmArgs a)
 {
     VDN_DYN_SMEM(smem);
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -304,7 +331,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
 #pragma unroll
             for (int c = 0; c < NC; ++c) Y.put(c, py[c].fromm);
         }
-        __syncthreads();                                                                    // B1
+        row_sync<TYT>(ty);                                                                  // B1
         double slx[NC], sly[NC], slz[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -357,7 +384,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             }
             Y.put(NC + c, ly[c]);
         }
-        __syncthreads();                                                                    // B2
+        row_sync<TYT>(ty);                                                                  // B2
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             double lxi = shfl_up1(lx[c]), lyi = Y.from_lo(NC + c), lzi = Y.get(KB + MK_LZH * NC + c);
@@ -372,7 +399,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             qx[c] = upw_p(lxi, rx[c], Px); qy[c] = upw_p(lyi, ry[c], Py); qz[c] = upw_p(lzi, rz[c], Pz);
             Y.put(2 * NC + c, qy[c]);
         }
-        __syncthreads();                                                                    // B3
+        row_sync<TYT>(ty);                                                                  // B3
         // ================= T: transverse terms and the six once-corrected states =================
         double Xxy[NC], Xyx[NC], Xzx[NC], Xzy[NC], Xxz[NC], Xyz[NC];
         double rxy[NC], ryx[NC], rzx[NC], rzy[NC], rxz[NC], ryz[NC], lxy[NC], lyx[NC], lxz[NC], lyz[NC];
@@ -426,7 +453,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             Y.put(KB + MK_LZH * NC + c, lz[c]); Y.put(KB + MK_QZP * NC + c, qz[c]);
             Y.put(3 * NC + c, lyx[c]); Y.put(c, lyz[c]);
         }
-        __syncthreads();                                                                    // B4
+        row_sync<TYT>(ty);                                                                  // B4
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             double lxyi = shfl_up1(lxy[c]), lxzi = shfl_up1(lxz[c]);
@@ -444,7 +471,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
             Xxz[c] = upw_p(lxzi, rxz[c], PxP); Xyz[c] = upw_p(lyzi, ryz[c], PyP);
             Y.put(NC + c, Xyx[c]); Y.put(2 * NC + c, Xyz[c]);
         }
-        __syncthreads();                                                                    // B5
+        row_sync<TYT>(ty);                                                                  // B5
         // ================= F: final edge states =================
         double Ly[NC], Ry[NC];
 #pragma unroll
@@ -511,7 +538,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_mkflux_march(const MfmArgs a)
                 }
             }
         }
-        __syncthreads();                                                                    // B6
+        row_sync<TYT>(ty);                                                                  // B6
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int comp = a.comp0 + c;
@@ -602,7 +629,7 @@ __device__ __forceinline__ double upt_p(double l, double r, TanP p)             
 }
 
 template <int TYT, bool GEN, bool HP2>
-__global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
+__global__ void __launch_bounds__(TXT * TYT, MARCH_MINB) k_velpred_march(const VpmArgs a)
 {
     VDN_DYN_SMEM(smem);
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -727,7 +754,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
 #pragma unroll
             for (int c = 0; c < 3; ++c) Y.put(c, py[c].fromm);
         }
-        __syncthreads();                                                                    // B1
+        row_sync<TYT>(ty);                                                                  // B1
         double slx[3], sly[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -782,7 +809,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
             }
             Y.put(3 + c, ly[c]);
         }
-        __syncthreads();                                                                    // B2
+        row_sync<TYT>(ty);                                                                  // B2
         double qx[3], qy[3], qz[3];                      // uimh at the lo faces
         {
             double lxi[3], lyi[3], lzi[3];
@@ -806,7 +833,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) Y.put(c, qy[c]);
-        __syncthreads();                                                                    // B3
+        row_sync<TYT>(ty);                                                                  // B3
         // ================= T =================
         double qxh[3], qyh[3];
 #pragma unroll
@@ -848,7 +875,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
 #pragma unroll
         for (int c = 0; c < 3; ++c) { Y.put(KS(VK_LZH0 + c), lz[c]); Y.put(KS(VK_QZ0 + c), qz[c]); }
         Y.put(3, lyx); Y.put(4, lyz);
-        __syncthreads();                                                                    // B4
+        row_sync<TYT>(ty);                                                                  // B4
         double Xxy, Xyx, Xzx, Xzy, Xxz, Xyz;
         {
             double lxyi = shfl_up1(lxy), lxzi = shfl_up1(lxz), lyxi = Y.from_lo(3), lyzi = Y.from_lo(4), lzxi = lzxH, lzyi = lzyH;
@@ -866,7 +893,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
             Xxz = upt_p(lxzi, rxz, tpxP); Xyz = upt_p(lyzi, ryz, tpyP);
         }
         Y.put(0, Xyx); Y.put(1, Xyz);
-        __syncthreads();                                                                    // B5
+        row_sync<TYT>(ty);                                                                  // B5
         // ================= F =================
         double Ly, Ry;
         {
@@ -901,7 +928,7 @@ __global__ void __launch_bounds__(TXT * TYT) k_velpred_march(const VpmArgs a)
                 if (st_x) a.out[0][oo0 + (k - 1) * a.o_sz[0]] = v;
             }
         }
-        __syncthreads();                                                                    // B6
+        row_sync<TYT>(ty);                                                                  // B6
         if (k > ka) {
             const double Lyi = Y.from_lo(3);
             double v = riemann_p(Lyi, Ry, epsP);
