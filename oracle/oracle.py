@@ -180,6 +180,18 @@ def rt_state(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, seeded_velocity=
     return geom, params, st, dt
 
 
+def bubble_state(n=64, max_grid_size=32, params=None):
+    """bubble_problem (BASELINE config 1: exec/test/inputs_2d-regt, max_levs = 1) + the path-boundary ghost fill of varden.f90:291-300."""
+    from varden_b200.problems import bubble_problem
+    if params is None:
+        params = Params(dim=2, nscal=2)
+    geom, st, dt = bubble_problem(n, max_grid_size=max_grid_size, nscal=params.nscal)
+    fill_and_physbc(geom, params, st["uold"], 3, 2, 0, 0, 2)
+    fill_and_physbc(geom, params, st["sold"], 3, params.nscal, 0, 2, params.nscal)
+    fill_boundary(geom, st["gp"], 1, 2)
+    return geom, params, st, dt
+
+
 def random_state(n, dim=3, max_grid_size=256, phys_bc=None, seed=0, params=None, umag=1.0, prob_hi=None):
     """Randomised but smooth-ish state exercising all selects; any phys_bc combination."""
     rng = np.random.default_rng(seed)

@@ -321,10 +321,10 @@ static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles,
         // macproject (macproject.f90:20-133)
         LaunchScope ph(c, "phase:MAC_Project", 0.0, 0);
         if (c->hio && c->hio->mac_rhs) io_need(c, VDN_MAC_RHS);
-        st_divumac(c, false);
+        const double bn = st_divumac(c, true);          // rh and |rh|_inf in one pass
         st_mk_mac_coeffs(c);
         st_setval(c, VDN_PHI, 0.0);
-        rc = st_mac_solve(c, mac_rel_eps > 0 ? mac_rel_eps : 1.0e-10, -1.0, cycles, resnorm);
+        rc = st_mac_solve(c, mac_rel_eps > 0 ? mac_rel_eps : 1.0e-10, -1.0, cycles, resnorm, true, bn);
         st_mkumac(c);
     }
     {
@@ -346,7 +346,8 @@ static void advance_impl(vdn_ctx *c, double dt, double mac_rel_eps, int *cycles,
     {
         // velocity_advance (velocity_advance.f90:70-93)
         LaunchScope ph(c, "phase:Velocity_update", 0.0, 0);
-        st_mkvelforce(c, VDN_SOLD, 1.0);
+        // velocity_advance.f90:70 evaluates mkvelforce(rho^n, visc_fac = 1) again; VEL_FORCE still holds exactly that from advance_premac
+        // (same ext_vel_force, gp, sold, lapu; nothing in between writes it), so the fused path does not recompute it
         st_mkflux(c, 1, dt);
         st_mkvelforce(c, VDN_RHOHALF, 0.0);
         st_update(c, 1, dt);
@@ -432,10 +433,10 @@ int vdn_macproject(vdn_ctx *ctx, double rel_eps, double abs_eps, int *ncycles, d
     try {
         VDN_CUDA(cudaSetDevice(ctx->device));
         // macproject.f90:60-67 computes umac_norm only for the (overridden) abs tolerance; skipped like the reference's "HACK"
-        st_divumac(ctx, false);
+        const double bn = st_divumac(ctx, true);
         st_mk_mac_coeffs(ctx);
         st_setval(ctx, VDN_PHI, 0.0);
-        int rc = st_mac_solve(ctx, rel_eps > 0 ? rel_eps : 1.0e-10, abs_eps, ncycles, resnorm);
+        int rc = st_mac_solve(ctx, rel_eps > 0 ? rel_eps : 1.0e-10, abs_eps, ncycles, resnorm, true, bn);
         st_mkumac(ctx);
         if (rc) { ctx->err = "MAC multigrid did not converge within mg_max_cycles"; return 2; }
         return 0;

@@ -77,7 +77,7 @@ void st_make_at_halftime(vdn_ctx *c);
 double st_divumac(vdn_ctx *c, bool want_norm);
 void st_mk_mac_coeffs(vdn_ctx *c);
 void st_mkumac(vdn_ctx *c);
-int  st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm);
+int  st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm, bool phi_zero = false, double bnorm_known = -1.0);
 void st_setval(vdn_ctx *c, int field, double val);
 double st_absmax_valid(vdn_ctx *c, int field);           // norm_inf over valid cells/faces, all comps
 void mg_destroy(MG *mg);

@@ -47,6 +47,7 @@ struct MG {
     // fused smoother (k_sweep3): levels 0..nfused-1 of a 3-D hierarchy
     int nfused = 0;                             // number of leading levels that run the fused kernel
     int tile_force = -1;                        // test hook (vdn_mg_tune): force one tile shape
+    int tail_from = -1;                         // first level of the single-CTA tail (k_tail); -1: none
     int sm_count = 148;
 };
 
@@ -176,9 +177,8 @@ __device__ double block_sum(double v, double *sm)
 struct BotVec { double *r, *rh, *p, *v, *s, *t; };
 
 template <int DIM>
-__global__ void __launch_bounds__(1024) k_bottom(Lev L, BotVec w, int maxit, double eps, int singular)
+__device__ void bottom_solve(const Lev &L, const BotVec &w, int maxit, double eps, int singular, double *sm)
 {
-    __shared__ double sm[32];
     const long nc = (long)L.n[0] * L.n[1] * L.n[2];
     const int nt = blockDim.x, tid = threadIdx.x;
 #define CELL(q, c, ix) const int ix##0 = (int)((q) % L.n[0]), ix##1 = (int)(((q) / L.n[0]) % L.n[1]), ix##2 = (int)((q) / ((long)L.n[0] * L.n[1])); \
@@ -234,6 +234,79 @@ __global__ void __launch_bounds__(1024) k_bottom(Lev L, BotVec w, int maxit, dou
         for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] -= s; }
     }
 #undef CELL
+}
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_bottom(Lev L, BotVec w, int maxit, double eps, int singular)
+{
+    __shared__ double sm[32];
+    bottom_solve<DIM>(L, w, maxit, eps, singular, sm);
+}
+
+// ---- the tail of a V-cycle in ONE CTA: every level of at most TAIL_CELLS cells (16^3) -- smoothing, residual, restriction, the BiCGStab
+// bottom solve, prolongation, smoothing -- with __syncthreads between the stages instead of a kernel launch per stage (44 launches of a few
+// microseconds each per V-cycle at 256^3).  The level arrays stay in global memory (L1/L2-resident at these sizes). ----
+constexpr long TAIL_CELLS = 4096;
+constexpr int TAIL_MAXLEV = 6;
+struct TailArgs { int nl; Lev L[TAIL_MAXLEV]; BotVec w; int nu1, nu2, maxit, singular; double eps; };
+template <int DIM>
+__device__ __forceinline__ void tail_cell(const Lev &L, long q, long &c, int (&ix)[3])
+{
+    ix[0] = (int)(q % L.n[0]); ix[1] = (int)((q / L.n[0]) % L.n[1]); ix[2] = (int)(q / ((long)L.n[0] * L.n[1]));
+    c = L.off + ix[0] + L.s[1] * ix[1] + L.s[2] * ix[2];
+}
+template <int DIM>
+__device__ void tail_smooth(const Lev &L, int sweeps)
+{
+    const long nc = (long)L.n[0] * L.n[1] * L.n[2];
+    for (int s = 0; s < sweeps; ++s)
+        for (int color = 0; color < 2; ++color) {
+            for (long q = threadIdx.x; q < nc; q += blockDim.x) {
+                long c; int ix[3]; tail_cell<DIM>(L, q, c, ix);
+                if (((ix[0] + ix[1] + ix[2] + color + L.par0) & 1) != 0) continue;
+                double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+                if (dg != 0.0) L.phi[c] += (L.rhs[c] - Ax) / dg;
+            }
+            __syncthreads();
+        }
+}
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_tail(TailArgs a)
+{
+    __shared__ double sm[32];
+    for (int l = 0; l + 1 < a.nl; ++l) {
+        const Lev &F = a.L[l], &C = a.L[l + 1];
+        tail_smooth<DIM>(F, a.nu1);
+        const long nf = (long)F.n[0] * F.n[1] * F.n[2];
+        for (long q = threadIdx.x; q < nf; q += blockDim.x) {
+            long c; int ix[3]; tail_cell<DIM>(F, q, c, ix);
+            double Ax, dg; cell_op<DIM>(F, F.phi, c, ix, Ax, dg);
+            F.res[c] = F.rhs[c] - Ax;
+        }
+        __syncthreads();
+        const long ncc = (long)C.n[0] * C.n[1] * C.n[2];
+        for (long q = threadIdx.x; q < ncc; q += blockDim.x) {
+            long cc; int ix[3]; tail_cell<DIM>(C, q, cc, ix);
+            const long cf = F.off + 2 * ix[0] + F.s[1] * (2 * ix[1]) + F.s[2] * (DIM == 3 ? 2 * ix[2] : 0);
+            double s = F.res[cf] + F.res[cf + 1] + F.res[cf + F.s[1]] + F.res[cf + F.s[1] + 1];
+            if (DIM == 3) s += F.res[cf + F.s[2]] + F.res[cf + F.s[2] + 1] + F.res[cf + F.s[2] + F.s[1]] + F.res[cf + F.s[2] + F.s[1] + 1];
+            C.rhs[cc] = s * (DIM == 3 ? 0.125 : 0.25);
+            C.phi[cc] = 0.0;
+        }
+        __syncthreads();
+    }
+    bottom_solve<DIM>(a.L[a.nl - 1], a.w, a.maxit, a.eps, a.singular, sm);
+    __syncthreads();
+    for (int l = a.nl - 2; l >= 0; --l) {
+        const Lev &F = a.L[l], &C = a.L[l + 1];
+        const long nf = (long)F.n[0] * F.n[1] * F.n[2];
+        for (long q = threadIdx.x; q < nf; q += blockDim.x) {
+            long c; int ix[3]; tail_cell<DIM>(F, q, c, ix);
+            const long cc = C.off + (ix[0] >> 1) + C.s[1] * (ix[1] >> 1) + C.s[2] * (DIM == 3 ? (ix[2] >> 1) : 0);
+            F.phi[c] += C.phi[cc];
+        }
+        __syncthreads();
+        tail_smooth<DIM>(F, a.nu2);
+    }
 }
 
 template <class F> void for_dim(int dim, F f) { if (dim == 3) f(std::integral_constant<int, 3>()); else f(std::integral_constant<int, 2>()); }
@@ -321,6 +394,11 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         L.res = dalloc(L.ntot);
         for (int d = 0; d < c->dim; ++d) { n[d] /= 2; h[d] *= 2.0; glo[d] /= 2; }
     }
+    if (!m->distributed)
+        for (int l = 1; l < nlev; ++l) {
+            const Lev &L = m->L[l];
+            if ((long)L.n[0] * L.n[1] * L.n[2] <= TAIL_CELLS && nlev - l <= TAIL_MAXLEV) { m->tail_from = l; break; }
+        }
     for (int q = 0; q < 6; ++q) { VDN_CUDA(cudaMalloc(&m->bot[q], sizeof(double) * m->L[nlev - 1].ntot)); VDN_CUDA(cudaMemsetAsync(m->bot[q], 0, sizeof(double) * m->L[nlev - 1].ntot, c->stream)); }
     VDN_CUDA(cudaMalloc(&m->d_norm, 64));
     return m;
@@ -574,6 +652,15 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         k_blk_extract<<<(int)std::min<long>(592, (tot + 255) / 256), 256, 0, c->stream>>>(e);
         return;
     }
+    if (l == m->tail_from) {
+        LaunchScope ls(c, "mg_tail", 0.0);
+        TailArgs a; a.nl = m->nlev - l;
+        for (int q = 0; q < a.nl; ++q) a.L[q] = m->L[l + q];
+        a.w = { m->bot[0], m->bot[1], m->bot[2], m->bot[3], m->bot[4], m->bot[5] };
+        a.nu1 = c->prm.mg_nu1; a.nu2 = c->prm.mg_nu2; a.maxit = c->prm.mg_max_bottom_iter; a.eps = c->prm.mg_bottom_eps; a.singular = m->singular ? 1 : 0;
+        for_dim(m->dim, [&](auto D) { k_tail<decltype(D)::value><<<1, 1024, 0, c->stream>>>(a); });
+        return;
+    }
     if (l == m->nlev - 1) {
         LaunchScope ls(c, "mg_bottom", 0.0);
         BotVec w = { m->bot[0], m->bot[1], m->bot[2], m->bot[3], m->bot[4], m->bot[5] };
@@ -664,7 +751,9 @@ void mg_destroy(MG *m)
 }
 
 // Solve with RH / BETA_* as right-hand side / coefficients and PHI as initial guess and result.
-int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm)
+// phi_zero: the caller has just set PHI = 0, so the initial residual IS the right-hand side (no residual pass); bnorm_known >= 0: |rh|_inf as
+// reduced by divumac in the pass that wrote rh (no separate norm pass).
+int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm, bool phi_zero, double bnorm_known)
 {
     if (!c->mg) {
         mg_build(c);
@@ -684,14 +773,14 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
             if (l == 0) mg_halo_deep(c, m, m->L[0], m->L[0].rhs, MG_PAD);
         }
     VDN_CUDA(cudaGetLastError());
-    const double bnorm = st_absmax_valid(c, VDN_RH);
+    const double bnorm = bnorm_known >= 0.0 ? bnorm_known : st_absmax_valid(c, VDN_RH);
     auto res_norm = [&]() {
         residual(c, m, 0, m->d_norm);
         VDN_CUDA(cudaMemcpyAsync(c->h_pin, m->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
         VDN_CUDA(cudaStreamSynchronize(c->stream));
         return comm_allreduce_max(c, c->h_pin[0]);
     };
-    double rn = res_norm();
+    double rn = phi_zero ? bnorm : res_norm();
     int cyc = 0;
     const bool talk = c->prm.mg_verbose && comm_rank(c) == 0;
     if (talk) printf("vdn_mg: levels %d%s  |rh| = %.6e  initial |r| = %.6e\n", m->nlev, m->tail ? " (+ agglomerated tail)" : "", bnorm, rn);

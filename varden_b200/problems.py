@@ -134,3 +134,30 @@ def rt_problem(n, dim=3, max_grid_size=256, ratio=2.0, grav=-9.8, nscal=2, seede
         st["ext_vel_force"][ib][..., dim - 1] = grav      # varden.f90:428-429
     dt = 0.45 * geom.dx[0] / 0.1                           # fixed_dt: CFL ~ 0.45 on |u| = 0.1
     return geom, st, dt
+
+
+def bubble_problem(n=64, max_grid_size=32, grav=-9.8, nscal=2, densfact=2.0, cflfac=0.9, init_shrink=0.1, box_ids=None):
+    """
+    BASELINE config 1: the reference's own CPU-runnable case exec/test/inputs_2d-regt with max_levs = 1 -- 2-D 64^2, max_grid_size 32
+    (4 boxes), prob_type = 1 (initdata.f90:136-160): u = 0, rho = 1 + (densfact-1)/2 (1 - tanh(30 (r - 0.1))) around (0.5, 0.5),
+    tracer = rho; no-slip walls on every side (bcx/bcy = 15); grav = -9.8.  The deck is viscous (visc_coef = 0.001): visc_solve stays the
+    reference's and the path is compared inviscid.  dt as the first step takes it: init_shrink * cflfac * the forcing bound
+    sqrt(2 dx / |F|) of estdt.f90:165-172 (u = 0, gp = 0).  VALID cells only; ghost cells are the caller's job (varden.f90:291-300).
+    """
+    dim = 2
+    phys_bc = [[NO_SLIP_WALL, NO_SLIP_WALL], [NO_SLIP_WALL, NO_SLIP_WALL]]
+    geom = Geom(dim, [n, n], phys_bc, prob_hi=(1., 1., 1.), max_grid_size=max_grid_size)
+    if box_ids is not None:
+        geom = geom.subset(box_ids)
+    st = dict(uold=mf_alloc(geom, 3, dim), sold=mf_alloc(geom, 3, nscal), gp=mf_alloc(geom, 1, dim),
+              ext_vel_force=mf_alloc(geom, 1, dim), ext_scal_force=mf_alloc(geom, 1, nscal))
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        ax = [(np.arange(lo[d], hi[d] + 1) + 0.5) * geom.dx[d] if d < dim else np.zeros(1) for d in range(3)]
+        X, Y, Z = np.meshgrid(ax[0], ax[1], ax[2], indexing='ij', sparse=True)
+        dist = np.sqrt((X - 0.5) ** 2 + (Y - 0.5) ** 2) + 0.0 * Z
+        rho = 1.0 + 0.5 * (densfact - 1.0) * (1.0 - np.tanh(30.0 * (dist - 0.1)))
+        valid(geom, st["sold"][ib], ib, 3)[..., 0] = rho
+        valid(geom, st["sold"][ib], ib, 3)[..., 1] = rho
+        st["ext_vel_force"][ib][..., dim - 1] = grav
+    dt = init_shrink * cflfac * np.sqrt(2.0 * geom.dx[1] / abs(grav))
+    return geom, st, dt
