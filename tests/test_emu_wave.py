@@ -18,12 +18,13 @@ PAD = 4          # MG_PAD in vdn_ctx.h
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU, "libemu_wave.so")
+    dev = os.environ.get("VDN_FUSED_HEADER")                     # development: test a working copy of the kernel header
+    so = os.path.join(EMU, "libemu_wave%s.so" % ("_dev" if dev else ""))
     src = [os.path.join(EMU, "emu_wave.cpp"), os.path.join(EMU, "cuda_emu.h"),
-           os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_fused.cuh")]
+           dev or os.path.join(HERE, "..", "varden_b200", "csrc", "vdn_mg_fused.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
-        subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off",
-                               src[0], "-o", so])
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-ffp-contract=off"] +
+                              (['-DFUSED_HEADER="%s"' % dev] if dev else []) + [src[0], "-o", so])
     return C.CDLL(so)
 
 
@@ -142,12 +143,15 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
             assert np.all(czero[CV] == 0.0)
 
 
+@pytest.mark.parametrize("p2p", [0, 1])
 @pytest.mark.parametrize("cfg", [5, 2])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
 @pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
-def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, kern="sweep3"):
-    """a level split across ranks: the kernel relaxes the neighbour ranks' cells held in its MG_PAD ghost layers (M_GHOST)
-    redundantly; the block of every 'rank' must equal the same block of the whole-domain sweep"""
+def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, p2p, kern="sweep3"):
+    """a level split across ranks: the kernel relaxes the neighbour ranks' cells redundantly; the block of every 'rank' must equal the same
+    block of the whole-domain sweep.  p2p = 0: the neighbours' phi (and coarse phi) sit in the rank's MG_PAD ghost layers (M_GHOST), filled by an
+    exchange beforehand; p2p = 1: the peer-memory mode -- the ghost layers of phi / coarse phi hold NaN and the kernel reads those cells from the
+    owning rank's own array through the 27-entry pointer table (the operator data stays in the ghost layers: exchanged once per solve)"""
     rng = np.random.default_rng(77 + pre + 5 * post + len(split))
     N = (32, 32, 16)                      # whole periodic domain, halved along the directions in `split`
     n = tuple(N[d] // 2 if d in split else N[d] for d in range(3))
@@ -177,16 +181,36 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, kern="sweep3"):
     Pp = lambda a: a.ctypes.data_as(C.c_void_p)
     mode = tuple((M_GHOST, M_GHOST) if d in split else (M_WRAP, M_WRAP) for d in range(3))
     nrm_all = 0.0
-    for corner in np.ndindex(*[2 if d in split else 1 for d in range(3)]):
+    def cut(a, nn, oo):                                # the block with its ghost layers, as the rank stores it
+        return np.ascontiguousarray(a[oo[2]:oo[2] + nn[2] + 2 * PAD, oo[1]:oo[1] + nn[1] + 2 * PAD, oo[0]:oo[0] + nn[0] + 2 * PAD])
+    def nanghost(a, nn):                               # peer-memory mode: a rank holds its own cells only (and index n of unsplit directions)
+        m = np.full(a.shape, True)
+        m[tuple(slice(PAD, PAD + nn[d] + (0 if d in split else 1)) if d in split else slice(None) for d in (2, 1, 0))] = False
+        out = a.copy(); out[m] = np.nan
+        return out
+    corners = list(np.ndindex(*[2 if d in split else 1 for d in range(3)]))
+    pgrid = [2 if d in split else 1 for d in range(3)]
+    rank_phi = {c_: (nanghost(cut(phi, n, [c_[d] * n[d] for d in range(3)]), n) if p2p else None) for c_ in corners}
+    rank_c = {c_: (nanghost(cut(cphi, cn, [c_[d] * cn[d] for d in range(3)]), cn) if p2p else None) for c_ in corners}
+    for corner in corners:
         o = [corner[d] * n[d] for d in range(3)]          # block origin (x, y, z)
-        def cut(a, nn, oo):                                # the block with its ghost layers, as the rank stores it
-            return np.ascontiguousarray(a[oo[2]:oo[2] + nn[2] + 2 * PAD, oo[1]:oo[1] + nn[1] + 2 * PAD, oo[0]:oo[0] + nn[0] + 2 * PAD])
-        lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o); lphi = cut(phi, n, o)
-        lc = cut(cphi, cn, [x // 2 for x in o])
+        lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o)
+        lphi = rank_phi[corner] if p2p else cut(phi, n, o)
+        lc = rank_c[corner] if p2p else cut(cphi, cn, [x // 2 for x in o])
+        peers = peersc = None
+        if p2p:
+            PT = C.c_void_p * 27
+            peers, peersc = PT(), PT()
+            for q in range(27):
+                off = (q % 3 - 1, (q // 3) % 3 - 1, q // 9 - 1)
+                if any(off[d] != 0 and d not in split for d in range(3)):
+                    continue                              # no rank there (that direction wraps by index inside the rank)
+                pc = tuple((corner[d] + off[d]) % pgrid[d] for d in range(3))
+                peers[q] = rank_phi[pc].ctypes.data; peersc[q] = rank_c[pc].ctypes.data
         out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
-        fn = getattr(emu, "emu_" + kern)
+        fn = emu.emu_sweep3_p2p
         rc = fn(1, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
-                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD)
+                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD, peers, peersc)
         assert rc == 0
         V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
         want = ref[o[2] + PAD:o[2] + PAD + n[2], o[1] + PAD:o[1] + PAD + n[1], o[0] + PAD:o[0] + PAD + n[0]]

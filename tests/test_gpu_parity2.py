@@ -49,10 +49,12 @@ def test_one_step_production_kernels(n):
     a, b = _demean(geom, phi, 1), _demean(geom, ref["phi"], 1)
     e_phi = max(np.abs(x - y).max() for x, y in zip(a, b)) / max(np.abs(y).max() for y in b)
     assert e_phi <= TOL_MAC, ("phi", e_phi)
-    # the whole step, both solves at 1e-13 (SURVEY Q10 mode b)
-    ref2 = O.advance(geom, P, st, dt, mac_rel_eps=1e-13)
+    # the whole step, both solves converged as far as FP64 allows at this size (SURVEY Q10 mode b): 1e-13 at 128^3; at 256^3 the relative
+    # residual stalls above 1e-13 (round-off of a 1.7e7-cell operator), so 1e-12 there
+    eps = 1e-13 if n <= 128 else 1e-12
+    ref2 = O.advance(geom, P, st, dt, mac_rel_eps=eps)
     upload_state(ctx, geom, P, st)
-    ctx.advance(dt, mac_rel_eps=1e-13)
+    ctx.advance(dt, mac_rel_eps=eps)
     e_s = relerr(geom, download_like(ctx, geom, "SNEW", ref2["snew"], 3, P.nscal), ref2["snew"], 3)
     e_u = relerr(geom, download_like(ctx, geom, "UNEW", ref2["unew"], 3, 3), ref2["unew"], 3)
     ctx.close()

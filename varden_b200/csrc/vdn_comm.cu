@@ -305,6 +305,52 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int no
     launch_pack(c, pu);
 }
 
+long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask)
+{
+    Comm *cm = c->comm;
+    if (!cm) return 0;
+    int ns = 0, nr = 0, speer[26], rpeer[26], slo[78], sn[78], rlo[78], rn[78], rsh[78], per[3];
+    for (int d = 0; d < 3; ++d) per[d] = c->dom_bc[d][0] == BC_PERIODIC ? 1 : 0;
+    if (vdn_halo_plan_ex(dim, cm->pgrid, cm->pcoord, per, cm->coord2rank.data(), n, ng, dmask, -1, 1, &ns, speer, slo, sn, &nr, rpeer, rlo, rn, rsh)) return 0;
+    long v = 0;
+    for (int q = 0; q < nr; ++q) v += (long)rn[3 * q] * rn[3 * q + 1] * rn[3 * q + 2];
+    return v;
+}
+
+// Tables for a kernel that reads its neighbours' cells itself (the fused smoother in peer-memory mode): base pointer of arr / arr2 (both in the
+// symmetric heap; arr2 may be null) on the rank at every process-grid offset (ox, oy, oz) -> index (ox+1) + 3 (oy+1) + 9 (oz+1), the neighbours'
+// flag words, this rank's flag word and the epoch of this launch (one epoch per exchange-like event, the same sequence on every rank).
+// dmask: split directions of the array.  Returns false when the peer-memory transport is not available for these arrays.
+bool comm_peer_tables(vdn_ctx *c, const double *arr, const double *arr2, int dmask, const double **p27, const double **p27b,
+                      const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch)
+{
+    Comm *cm = c->comm;
+    if (!cm || !in_heap(cm, arr) || (arr2 && !in_heap(cm, arr2))) return false;
+    const long off = (long)((const char *)arr - cm->heap), off2 = arr2 ? (long)((const char *)arr2 - cm->heap) : 0;
+    for (int q = 0; q < 27; ++q) {
+        p27[q] = nullptr; p27b[q] = nullptr; f27[q] = nullptr;
+        const int o[3] = { q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1 };
+        int pc[3]; bool ok = true;
+        for (int d = 0; d < 3; ++d) {
+            pc[d] = cm->pcoord[d] + o[d];
+            if (o[d] == 0) continue;
+            if (d >= c->dim || !((dmask >> d) & 1) || cm->pgrid[d] == 1) { ok = false; break; }
+            if (pc[d] < 0 || pc[d] >= cm->pgrid[d]) {
+                if (c->dom_bc[d][0] != BC_PERIODIC) { ok = false; break; }
+                pc[d] = (pc[d] + cm->pgrid[d]) % cm->pgrid[d];
+            }
+        }
+        if (!ok) continue;
+        const int r = cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])];
+        p27[q] = (const double *)(cm->peer_base[r] + off);
+        if (arr2) p27b[q] = (const double *)(cm->peer_base[r] + off2);
+        if (r != cm->rank) f27[q] = (const unsigned long long *)cm->peer_base[r];
+    }
+    *mine = (unsigned long long *)cm->heap;
+    *epoch = ++cm->epoch;
+    return true;
+}
+
 // multifab_fill_boundary between ranks for a field: every split direction at once (vdn_stream.cu then wraps the periodic directions this
 // rank owns alone over the ghosted range, which completes the edge and corner ghosts)
 void comm_exchange_field(vdn_ctx *c, int field)

@@ -15,3 +15,7 @@ const int *comm_pcoord(const vdn_ctx *c);
 bool comm_has_neighbor(const vdn_ctx *c, int d, int s);
 void comm_allgather(vdn_ctx *c, const double *send, double *recv, size_t count);
 void comm_coord_of(const vdn_ctx *c, int r, int *pc);
+// peer-memory tables for kernels that read neighbour ranks' arrays themselves (see vdn_comm.cu); false: not available (NCCL transport)
+bool comm_peer_tables(vdn_ctx *c, const double *arr, const double *arr2, int dmask, const double **p27, const double **p27b,
+                      const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch);
+long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask);      // cells an exchange of depth ng would move (accounting)

@@ -242,10 +242,10 @@ __global__ void __launch_bounds__(1024) k_bottom(Lev L, BotVec w, int maxit, dou
     bottom_solve<DIM>(L, w, maxit, eps, singular, sm);
 }
 
-// ---- the tail of a V-cycle in ONE CTA: every level of at most TAIL_CELLS cells (16^3) -- smoothing, residual, restriction, the BiCGStab
+// ---- the tail of a V-cycle in ONE CTA: every level of at most TAIL_CELLS cells (8^3) -- smoothing, residual, restriction, the BiCGStab
 // bottom solve, prolongation, smoothing -- with __syncthreads between the stages instead of a kernel launch per stage (44 launches of a few
 // microseconds each per V-cycle at 256^3).  The level arrays stay in global memory (L1/L2-resident at these sizes). ----
-constexpr long TAIL_CELLS = 4096;
+constexpr long TAIL_CELLS = 512;       // 8^3: measured (r2 call 5) -- a 16^3 stage in one CTA costs as much as the launch it replaces
 constexpr int TAIL_MAXLEV = 6;
 struct TailArgs { int nl; Lev L[TAIL_MAXLEV]; BotVec w; int nu1, nu2, maxit, singular; double eps; };
 template <int DIM>
@@ -544,12 +544,12 @@ struct WaveVariant { const void *fn = nullptr; size_t smem = 0; int occ = 0; int
 constexpr int SWEEP_NCFG = 5;
 
 // k_sweep3 variants (one column of cell pairs per thread, register-pipelined operator data): [tile cfg][pre][post index]
-template <int PRE, int POST, int TX, int TY>
+template <int PRE, int POST, int TX, int TY, bool P2P>
 WaveVariant sweep3_variant()
 {
     using C = Sweep3Cfg<PRE, POST, TX, TY>;
     WaveVariant v;
-    v.fn = (const void *)k_sweep3<PRE, POST, TX, TY>;
+    v.fn = (const void *)k_sweep3<PRE, POST, TX, TY, P2P>;
     v.smem = C::SMEM;
     v.H = C::H; v.W = C::X; v.HH = C::Y; v.TX = TX; v.TY = TY; v.NT = C::NT;
     VDN_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
@@ -557,23 +557,26 @@ WaveVariant sweep3_variant()
     VDN_REQUIRE(v.occ >= 1, "k_sweep3 variant does not fit on an SM");
     return v;
 }
-WaveVariant &sweep3_get(int cfg, int pre, int post)
+// p2p: the instantiation that reads neighbour ranks' cells from peer memory (levels split across ranks, peer-memory transport up)
+WaveVariant &sweep3_get(int cfg, int pre, int post, bool p2p)
 {
-    static WaveVariant tab[SWEEP_NCFG][2][3];
+    static WaveVariant tab[2][SWEEP_NCFG][2][3];
     const int pi = post == 0 ? 0 : post == 2 ? 1 : 2;
-    WaveVariant &v = tab[cfg][pre][pi];
+    WaveVariant &v = tab[p2p ? 1 : 0][cfg][pre][pi];
     if (v.fn) return v;
-#define SV3(C, TX, TY) \
-    if (cfg == C) { \
-        if (pre == 0 && post == 0) v = sweep3_variant<0, 0, TX, TY>(); \
-        if (pre == 0 && post == 2) v = sweep3_variant<0, 2, TX, TY>(); \
-        if (pre == 0 && post == 3) v = sweep3_variant<0, 3, TX, TY>(); \
-        if (pre == 1 && post == 0) v = sweep3_variant<1, 0, TX, TY>(); \
-        if (pre == 1 && post == 2) v = sweep3_variant<1, 2, TX, TY>(); \
-        if (pre == 1 && post == 3) v = sweep3_variant<1, 3, TX, TY>(); \
+#define SV3P(C, TX, TY, P) \
+    if (cfg == C && p2p == P) { \
+        if (pre == 0 && post == 0) v = sweep3_variant<0, 0, TX, TY, P>(); \
+        if (pre == 0 && post == 2) v = sweep3_variant<0, 2, TX, TY, P>(); \
+        if (pre == 0 && post == 3) v = sweep3_variant<0, 3, TX, TY, P>(); \
+        if (pre == 1 && post == 0) v = sweep3_variant<1, 0, TX, TY, P>(); \
+        if (pre == 1 && post == 2) v = sweep3_variant<1, 2, TX, TY, P>(); \
+        if (pre == 1 && post == 3) v = sweep3_variant<1, 3, TX, TY, P>(); \
     }
+#define SV3(C, TX, TY) SV3P(C, TX, TY, false) SV3P(C, TX, TY, true)
     SV3(0, 32, 32) SV3(1, 64, 16) SV3(2, 32, 16) SV3(3, 64, 14) SV3(4, 32, 24)     // 3, 4: 640-thread CTAs (20 warps: 96 registers, no spills)
 #undef SV3
+#undef SV3P
     VDN_REQUIRE(v.fn != nullptr, "no such k_sweep3 variant");
     return v;
 }
@@ -585,7 +588,17 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     const int nsw = 1;
     // pick tile shape and z-chunking: cost ~ waves * CTAs sharing an SM * iterations * plane cells
     int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
-    auto variant = [&](int cfg) -> const WaveVariant & { return sweep3_get(cfg, pre, post); };
+    // peer-memory mode: the kernel reads the neighbour ranks' cells (phi, and the coarse correction under them) straight from their arrays
+    WaveArgs a;
+    a.p2p = 0; a.my_flag = nullptr; a.epoch = 0;
+    bool peer_mode = false;
+    int dmask = 0;
+    if (m->distributed) {
+        for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
+        peer_mode = comm_peer_tables(c, L.phi, pre ? m->L[l + 1].phi : nullptr, dmask, a.peer_in, a.peer_cphi, a.peer_flag, &a.my_flag, &a.epoch);
+        a.p2p = peer_mode ? 1 : 0;
+    }
+    auto variant = [&](int cfg) -> const WaveVariant & { return sweep3_get(cfg, pre, post, peer_mode); };
     for (int cfg = 0; cfg < SWEEP_NCFG; ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
         // measured defaults (profiles/r01_bench_256_v5_*): 32x24 (640 threads, 96 registers) for the plain / prolongating sweeps of the finest
@@ -605,7 +618,6 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
         }
     }
     const WaveVariant &v = variant(best_cfg);
-    WaveArgs a;
     for (int d = 0; d < 3; ++d) { a.n[d] = L.n[d]; a.h2[d] = L.h2inv[d]; a.mode[d][0] = L.mode[d][0]; a.mode[d][1] = L.mode[d][1]; }
     a.s1 = L.s[1]; a.s2 = L.s[2]; a.off = L.off; a.par0 = L.par0;
     a.rhs = L.rhs; a.b0 = L.b[0]; a.b1 = L.b[1]; a.b2 = L.b[2];
@@ -616,7 +628,14 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
         a.cphi = C.phi; a.crhs = C.rhs; a.czero = C.phi; a.cs1 = C.s[1]; a.cs2 = C.s[2]; a.coff = C.off;
     }
     a.nrm = m->d_norm; a.zchunk = best_ch;
-    mg_halo_deep(c, m, L, L.phi, v.H);          // neighbour-rank cells the tiles relax redundantly
+    if (peer_mode) {
+        c->comm_bytes += 8 * comm_halo_volume(c, L.n, m->dim, v.H, dmask);
+        if (pre) c->comm_bytes += 8 * comm_halo_volume(c, m->L[l + 1].n, m->dim, 2, dmask);
+    }
+    if (!peer_mode) {
+        if (pre) mg_halo_deep(c, m, m->L[l + 1], m->L[l + 1].phi, 2);   // the prolongation under 3 fine ghost layers reads 2 coarse ones
+        mg_halo_deep(c, m, L, L.phi, v.H);      // neighbour-rank cells the tiles relax redundantly
+    }
     if (post == 3) VDN_CUDA(cudaMemsetAsync(m->d_norm, 0, 8, c->stream));
     const double cells = (double)L.n[0] * L.n[1] * L.n[2];
     // SURVEY 8(a) a8 per stage: colour half-sweep 40, residual 48, restriction 9, prolongation 17 B/cell
@@ -682,7 +701,6 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         int rem = c->prm.mg_nu1;
         while (rem > 0) { --rem; wave_launch(c, m, l, 0, rem == 0 ? 2 : 0); }
         coarse();
-        mg_halo_deep(c, m, C, C.phi, 2);                        // the prolongation under 3 fine ghost layers reads 2 coarse ones
         rem = c->prm.mg_nu2;
         bool first = true;
         while (rem > 0) { --rem; wave_launch(c, m, l, first ? 1 : 0, (rem == 0 && l == 0) ? 3 : 0); first = false; }

@@ -34,6 +34,14 @@ struct WaveArgs {
     const double *cphi; double *crhs, *czero; long cs1, cs2, coff;   // coarse level (PRE / POST == 2)
     double *nrm;
     int zchunk;
+    // peer-memory mode (levels split across ranks, all arrays in the symmetric heap): the phi planes -- and the coarse correction under them --
+    // of cells that belong to a neighbour rank are read STRAIGHT from that rank's array instead of from a ghost layer filled by a separate
+    // exchange.  peer_in / peer_cphi: base of the same array on the rank at process-grid offset (ox, oy, oz), index (ox+1) + 3 (oy+1) + 9 (oz+1)
+    // ([13] = this rank).  The kernel publishes "my stream has reached launch `epoch`" in its own flag word and the CTAs whose footprint leaves
+    // the rank's region wait for the flags of the neighbours -- interior CTAs start at once, so the wait overlaps with their work.
+    int p2p;
+    const double *peer_in[27], *peer_cphi[27];
+    const unsigned long long *peer_flag[27]; unsigned long long *my_flag; unsigned long long epoch;
 };
 
 
@@ -71,6 +79,8 @@ __device__ __forceinline__ void sweep_load(SweepCoef &c, const WaveArgs &a, long
 }
 
 #ifdef VDN_EMU
+template <class T> inline T __ldcv(const T *p) { return *p; }
+inline void __threadfence_system() { }
 inline double emu_xor_buf[2048];
 inline double __shfl_xor_sync(unsigned, double v, int m)
 {
@@ -93,7 +103,7 @@ struct Sweep3Cfg {
     static_assert(TX % 2 == 0 && TY % 2 == 0, "even tiles");
 };
 
-template <int PRE, int POST, int TX, int TY>
+template <int PRE, int POST, int TX, int TY, bool P2P = false>
 __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(const WaveArgs a)
 {
     using C = Sweep3Cfg<PRE, POST, TX, TY>;
@@ -125,7 +135,17 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     }
     const int wyb = ld[0] ? wy[0] : wy[1] - 1;                  // rows of a pair exist together except on the masked outer ring
     const long gofs = a.off + (okx ? wx : 0) + a.s1 * (long)wyb;  // + s1 * row + s2 * plane
-    const long cofs = PRE ? a.coff + ((okx ? wx : 0) >> 1) + a.cs1 * (long)(wyb >> 1) : 0;
+    // peer-memory mode: which rank owns this column (process-grid offset ox, oy) and where it sits in THAT rank's local numbering (the level
+    // sizes are even, so a row pair never straddles a rank boundary)
+    int ox = 0, oy = 0;
+    if (P2P) {
+        if (gx < 0 && mx0 == M_GHOST) ox = -1; else if (gx >= n0 && mx1 == M_GHOST) ox = 1;
+        if (gy0 < 0 && my0 == M_GHOST) oy = -1; else if (gy0 >= n1 && my1 == M_GHOST) oy = 1;
+    }
+    const int wxl = (okx ? wx : 0) - ox * n0, wyl = wyb - oy * n1;
+    const long pofs = a.off + wxl + a.s1 * (long)wyl;
+    const int oxy = (ox + 1) + 3 * (oy + 1);
+    const long cofs = PRE ? a.coff + (wxl >> 1) + a.cs1 * (long)(wyl >> 1) : 0;
     const bool anyld = ld[0] || ld[1];
     const bool bndx = (gx == 0 && (mx0 == M_NEU || mx0 == M_DIR)) || (gx == n0 - 1 && (mx1 == M_NEU || mx1 == M_DIR));
     bool bndy[2];
@@ -142,10 +162,26 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     auto fetch = [&](int wz) {
         pf[0] = 0.0; pf[1] = 0.0; pc = 0.0;
         if (wz != WAVE_NONE && anyld) {
-            const double *src = a.in + gofs + a.s2 * (long)wz;
-            if (ld[0]) pf[0] = src[0];
-            if (ld[1]) pf[1] = src[a.s1];
-            if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wz >> 1));
+            if (!P2P) {
+                const double *src = a.in + gofs + a.s2 * (long)wz;
+                if (ld[0]) pf[0] = src[0];
+                if (ld[1]) pf[1] = src[a.s1];
+                if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wz >> 1));
+            } else {
+                int oz = 0;
+                if (wz < 0 && mz0 == M_GHOST) oz = -1; else if (wz >= n2 && mz1 == M_GHOST) oz = 1;
+                const int wzl = wz - oz * n2, who = oxy + 9 * (oz + 1);
+                const double *src = a.peer_in[who] + pofs + a.s2 * (long)wzl;
+                if (who == 13) {
+                    if (ld[0]) pf[0] = src[0];
+                    if (ld[1]) pf[1] = src[a.s1];
+                    if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wzl >> 1));
+                } else {                                   // another rank's memory: never through a stale L1 line
+                    if (ld[0]) pf[0] = __ldcv(src);
+                    if (ld[1]) pf[1] = __ldcv(src + a.s1);
+                    if (PRE) pc = __ldcv(a.peer_cphi[who] + cofs + a.cs2 * (long)(wzl >> 1));
+                }
+            }
         }
     };
     auto stash = [&](int o) {
@@ -184,6 +220,19 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     for (int k = 0; k < NPL; ++k) oP[k] = ring(tfirst - k);             // state "step tfirst-1", rotated at the top of the loop
 #pragma unroll
     for (int k = 0; k < S + 3 + E; ++k) wzq[k] = zidx(tfirst + 1 - k);
+    if (P2P && a.my_flag) {
+        // everything this rank's stream produced before this launch is complete: publish it; CTAs that read a neighbour's cells wait until
+        // the neighbours have published the same launch (their producing kernels are complete as well)
+        if (tid == 0) { __threadfence_system(); *(volatile unsigned long long *)a.my_flag = a.epoch; }
+        const bool edge = (x0 - H < 0 && mx0 == M_GHOST) || (x0 + TX + H > n0 && mx1 == M_GHOST) || (y0 - H < 0 && my0 == M_GHOST) ||
+                          (y0 + TY + H > n1 && my1 == M_GHOST) || (z0 - H < 0 && mz0 == M_GHOST) || (z1 + H > n2 && mz1 == M_GHOST);
+        if (edge && tid < 27 && a.peer_flag[tid]) {
+            const volatile unsigned long long *f = (const volatile unsigned long long *)a.peer_flag[tid];
+            while (*f < a.epoch) { }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     fetch(wzq[1]); stash(oP[0]); fetch(wzq[0]);                        // planes tfirst (into the ring) and tfirst+1 (registers)
     // operator data of stage 0 of the first step
     SweepCoef c0n;
