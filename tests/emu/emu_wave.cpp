@@ -13,7 +13,7 @@ double sm[1 << 17];
 extern "C" int emu_sweep3_p2p(int nsw, int pre, int post, int cfg, const int *n, const int *mode, int par0, const double *h2,
                               const double *rhs, const double *b0, const double *b1, const double *b2,
                               const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk, int pad,
-                              const double *const *peer_in, const double *const *peer_c)
+                              const double *const *peer_in, const double *const *peer_c, const double *dinv)
 {
     if (nsw != 1) return 1;
     WaveArgs a;
@@ -21,7 +21,7 @@ extern "C" int emu_sweep3_p2p(int nsw, int pre, int post, int cfg, const int *n,
     if (peer_in) { a.p2p = 1; for (int q = 0; q < 27; ++q) { a.peer_in[q] = peer_in[q]; a.peer_cphi[q] = peer_c ? peer_c[q] : nullptr; } }
     for (int d = 0; d < 3; ++d) { a.n[d] = n[d]; a.h2[d] = h2[d]; a.mode[d][0] = mode[2 * d]; a.mode[d][1] = mode[2 * d + 1]; }
     a.s1 = n[0] + 2 * pad; a.s2 = (long)(n[0] + 2 * pad) * (n[1] + 2 * pad); a.off = pad * (1 + a.s1 + a.s2); a.par0 = par0;
-    a.rhs = rhs; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.in = in; a.out = out;
+    a.rhs = rhs; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.dinv = dinv; a.in = in; a.out = out;
     a.cphi = cphi; a.crhs = crhs; a.czero = czero;
     a.cs1 = n[0] / 2 + 2 * pad; a.cs2 = (long)(n[0] / 2 + 2 * pad) * (n[1] / 2 + 2 * pad); a.coff = pad * (1 + a.cs1 + a.cs2);
     a.nrm = nrm; a.zchunk = zchunk;
@@ -36,7 +36,7 @@ extern "C" int emu_sweep3_p2p(int nsw, int pre, int post, int cfg, const int *n,
 }
 extern "C" int emu_sweep3(int nsw, int pre, int post, int cfg, const int *n, const int *mode, int par0, const double *h2,
                           const double *rhs, const double *b0, const double *b1, const double *b2,
-                          const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk, int pad)
+                          const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk, int pad, const double *dinv)
 {
-    return emu_sweep3_p2p(nsw, pre, post, cfg, n, mode, par0, h2, rhs, b0, b1, b2, in, out, cphi, crhs, czero, nrm, zchunk, pad, nullptr, nullptr);
+    return emu_sweep3_p2p(nsw, pre, post, cfg, n, mode, par0, h2, rhs, b0, b1, b2, in, out, cphi, crhs, czero, nrm, zchunk, pad, nullptr, nullptr, dinv);
 }

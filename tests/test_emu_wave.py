@@ -120,8 +120,10 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
     nrm = np.zeros(1)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
     fn = getattr(emu, "emu_" + kern)
+    _, dg0 = apply_A(phi, b, h2, mode, n)                     # the kernel takes 1 / diagonal (k_diag_inv in vdn_mg.cu computes it per solve)
+    dinv = np.zeros(shp); dinv[V] = np.where(dg0 != 0.0, 1.0 / np.where(dg0 != 0.0, dg0, 1.0), 0.0)
     rc = fn(nsw, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), par0, P(h2),
-            P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk, PAD)
+            P(rhs), P(b[0]), P(b[1]), P(b[2]), P(phi), P(out), P(cphi), P(crhs), P(czero), P(nrm), zchunk, PAD, P(dinv))
     assert rc == 0
     # reference
     start = phi.copy()
@@ -176,6 +178,9 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, p2p, kern="sweep3"):
     if pre:
         start[VN] += np.repeat(np.repeat(np.repeat(cphi[CVN], 2, axis=0), 2, axis=1), 2, axis=2)
     ref = gsrb(start, rhs, b, h2, gmode, N, 0, 1)
+    _, dgN = apply_A(phi, b, h2, gmode, N)
+    dinvN = np.zeros(shpN); dinvN[VN] = 1.0 / dgN
+    periodic_fill(dinvN, N)
     ax, _ = apply_A(ref, b, h2, gmode, N)
     res = rhs[VN] - ax
     Pp = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -194,7 +199,7 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, p2p, kern="sweep3"):
     rank_c = {c_: (nanghost(cut(cphi, cn, [c_[d] * cn[d] for d in range(3)]), cn) if p2p else None) for c_ in corners}
     for corner in corners:
         o = [corner[d] * n[d] for d in range(3)]          # block origin (x, y, z)
-        lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o)
+        lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o); ldinv = cut(dinvN, n, o)
         lphi = rank_phi[corner] if p2p else cut(phi, n, o)
         lc = rank_c[corner] if p2p else cut(cphi, cn, [x // 2 for x in o])
         peers = peersc = None
@@ -210,7 +215,7 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, p2p, kern="sweep3"):
         out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
         fn = emu.emu_sweep3_p2p
         rc = fn(1, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
-                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD, peers, peersc)
+                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD, peers, peersc, Pp(ldinv))
         assert rc == 0
         V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
         want = ref[o[2] + PAD:o[2] + PAD + n[2], o[1] + PAD:o[1] + PAD + n[1], o[0] + PAD:o[0] + PAD + n[0]]

@@ -444,7 +444,7 @@ static void p2p_setup(vdn_ctx *c)
 {
     Comm *cm = c->comm;
     if (c->comm_force_nccl) return;
-    // size: the fields + the multigrid arrays that are not aliases of fields (level 0: 1 array; coarser distributed levels: 6 each)
+    // size: the fields + the multigrid arrays that are not aliases of fields (level 0: 2 arrays; coarser distributed levels: 7 each)
     size_t need = HEAP_RESERVED;
     for (int i = 0; i < VDN_NFIELDS; ++i) {
         if (i >= VDN_SEDGE_X && i <= VDN_SEDGE_Z) continue;
@@ -455,7 +455,7 @@ static void p2p_setup(vdn_ctx *c)
         for (int l = 0; l < 32; ++l) {
             size_t tot = 1;
             for (int d = 0; d < c->dim; ++d) tot *= (size_t)(nn[d] + 2 * MG_PAD);
-            need += (l == 0 ? 1 : 6) * ((tot * 8 + 255) & ~(size_t)255);
+            need += (l == 0 ? 2 : 7) * ((tot * 8 + 255) & ~(size_t)255);
             bool ok = true;
             for (int d = 0; d < c->dim; ++d) if (nn[d] % 2 != 0 || nn[d] / 2 < 2) ok = false;
             if (!ok) break;

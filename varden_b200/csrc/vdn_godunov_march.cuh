@@ -1035,8 +1035,10 @@ void mkflux_march(L &launch, const Geo &g, const View &s, const View &force, con
                 for (int sd = 0; sd < 2; ++sd) a.sbc[c][d][sd] = adv_bc[c0 + c][d][sd];
             }
         }
-        // SURVEY 8(a) a3 bytes: R s + force per comp, the three MAC velocities per launch; W three edge states per comp (+ fluxes)
-        const double bytes = cells * 8.0 * (nc * (1 + 1 + 3) + 3 + ((consmask & 1) ? 3 : 0));
+        // the whole phase moves 136 B/cell (scalars: R s 2 + umac 3 + force 2 + mac_rhs 1, W sedge 6 + flux 3) resp. 152 B/cell
+        // (velocity: R 3 + 3 + 3 + 1, W 9) of compulsory traffic; a launch is charged its share of the components (the MAC velocities are in fact
+        // re-read by every launch, which the figure does not credit)
+        const double bytes = cells * (is_vel ? 152.0 : 136.0) * (double)nc / (double)ncomp;
         auto ls = launch.scope(is_vel ? "mkflux_vel" : "mkflux_scal", bytes, 1);
         if (nc == 1) mkflux_march_group<1>(launch, a, consmask, gen, slots);
 #if MARCH_NCG >= 2

@@ -25,6 +25,7 @@ struct Lev {
     int mode[3][2];
     int par0;               // parity of the global index of local cell (0,0,0)
     double *phi, *rhs, *res, *b[3];
+    double *dinv;           // 1 / diagonal (fused smoother levels), recomputed with the coefficients at every solve
 };
 
 struct MG {
@@ -139,6 +140,29 @@ __global__ void k_prolong(Lev F, Lev C)
     const long cf = F.off + i + F.s[1] * j + F.s[2] * k;
     const long cc = C.off + (i >> 1) + C.s[1] * (j >> 1) + C.s[2] * (DIM == 3 ? (k >> 1) : 0);
     F.phi[cf] += C.phi[cc];
+}
+
+// dinv = 1 / diagonal of the operator (boundary conditions included, 0 where the diagonal vanishes) on the cells lo..hi of every direction:
+// the level's own cells, plus the ghost layers that the fused smoother relaxes redundantly on levels split across ranks
+template <int DIM>
+__global__ void k_diag_inv(Lev L, int lo0, int lo1, int lo2, int hi0, int hi1, int hi2)
+{
+    const int i = lo0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = lo1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = lo2 + blockIdx.z;
+    if (i > hi0 || j > hi1 || k > hi2) return;
+    const long c = L.off + i + L.s[1] * j + L.s[2] * k;
+    const int ix[3] = { i, j, k };
+    double g = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double h2 = L.h2inv[d], blo = L.b[d][c], bhi = L.b[d][c + L.s[d]];
+        const bool at_lo = ix[d] == 0, at_hi = ix[d] == L.n[d] - 1;
+        const int mlo = L.mode[d][0], mhi = L.mode[d][1];
+        if (at_lo && mlo == M_NEU) { } else if (at_lo && mlo == M_DIR) g += 3.0 * blo * h2; else g += blo * h2;
+        if (at_hi && mhi == M_NEU) { } else if (at_hi && mhi == M_DIR) g += 3.0 * bhi * h2; else g += bhi * h2;
+    }
+    L.dinv[c] = g != 0.0 ? 1.0 / g : 0.0;
 }
 
 // coarse face coefficient = arithmetic mean of the fine faces it covers
@@ -392,6 +416,7 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         }
         for (int d = c->dim; d < 3; ++d) L.b[d] = nullptr;
         L.res = dalloc(L.ntot);
+        L.dinv = c->dim == 3 ? dalloc(L.ntot) : nullptr;
         for (int d = 0; d < c->dim; ++d) { n[d] /= 2; h[d] *= 2.0; glo[d] /= 2; }
     }
     if (!m->distributed)
@@ -620,7 +645,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     const WaveVariant &v = variant(best_cfg);
     for (int d = 0; d < 3; ++d) { a.n[d] = L.n[d]; a.h2[d] = L.h2inv[d]; a.mode[d][0] = L.mode[d][0]; a.mode[d][1] = L.mode[d][1]; }
     a.s1 = L.s[1]; a.s2 = L.s[2]; a.off = L.off; a.par0 = L.par0;
-    a.rhs = L.rhs; a.b0 = L.b[0]; a.b1 = L.b[1]; a.b2 = L.b[2];
+    a.rhs = L.rhs; a.b0 = L.b[0]; a.b1 = L.b[1]; a.b2 = L.b[2]; a.dinv = L.dinv;
     a.in = L.phi; a.out = L.res;
     a.cphi = nullptr; a.crhs = nullptr; a.czero = nullptr; a.cs1 = a.cs2 = a.coff = 0;
     if (pre || post == 2) {
@@ -790,6 +815,18 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
             for (int d = 0; d < m->dim; ++d) mg_halo_deep(c, m, m->L[l], m->L[l].b[d], MG_PAD);
             if (l == 0) mg_halo_deep(c, m, m->L[0], m->L[0].rhs, MG_PAD);
         }
+    // inverse diagonal of the fused levels (after the coefficient ghost layers are in place: ghost cells are relaxed redundantly)
+    for (int l = 0; l < m->nfused; ++l) {
+        Lev &L = m->L[l];
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+            const int g = (d < m->dim && (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST)) ? MG_PAD - 1 : 0;
+            lo[d] = (d < m->dim && L.mode[d][0] == M_GHOST) ? -g : 0;
+            hi[d] = L.n[d] - 1 + ((d < m->dim && L.mode[d][1] == M_GHOST) ? g : 0);
+        }
+        LaunchScope ls(c, "mg_diag_inv", (double)L.n[0] * L.n[1] * L.n[2] * 32.0);
+        k_diag_inv<3><<<cgrid(hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1), BLK, 0, c->stream>>>(L, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+    }
     VDN_CUDA(cudaGetLastError());
     const double bnorm = bnorm_known >= 0.0 ? bnorm_known : st_absmax_valid(c, VDN_RH);
     auto res_norm = [&]() {
