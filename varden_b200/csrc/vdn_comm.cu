@@ -397,6 +397,13 @@ static double allreduce(vdn_ctx *c, double v, ncclRedOp_t op)
     return c->h_pin[9];
 }
 double comm_allreduce_max(vdn_ctx *c, double v) { return allreduce(c, v, ncclMax); }
+// the same on a DEVICE scalar, in place and asynchronous on the context's stream (no host round trip)
+void comm_allreduce_max_dev(vdn_ctx *c, double *d_v)
+{
+    Comm *cm = c->comm;
+    if (!cm || cm->nranks == 1) return;
+    VDN_NCCL(ncclAllReduce(d_v, d_v, 1, ncclDouble, ncclMax, cm->nccl, c->stream));
+}
 double comm_allreduce_sum(vdn_ctx *c, double v) { return allreduce(c, v, ncclSum); }
 
 int comm_rank(const vdn_ctx *c) { return c->comm ? c->comm->rank : 0; }

@@ -19,3 +19,4 @@ void comm_coord_of(const vdn_ctx *c, int r, int *pc);
 bool comm_peer_tables(vdn_ctx *c, const double *arr, const double *arr2, int dmask, const double **p27, const double **p27b,
                       const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch);
 long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask);      // cells an exchange of depth ng would move (accounting)
+void comm_allreduce_max_dev(vdn_ctx *c, double *d_v);       // ncclAllReduce(MAX) of one device double, in place, asynchronous

@@ -49,6 +49,8 @@ struct MG {
     int nfused = 0;                             // number of leading levels that run the fused kernel
     int tile_force = -1;                        // test hook (vdn_mg_tune): force one tile shape
     int tail_from = -1;                         // first level of the single-CTA tail (k_tail); -1: none
+    bool first_sweep_done = false;              // the first smoothing sweep of level 0 of the coming V-cycle has been launched already
+    cudaEvent_t ev_norm = nullptr;              // the residual norm of the last V-cycle has reached the pinned host word
     int sm_count = 148;
 };
 
@@ -440,7 +442,11 @@ void mg_pick_fused(vdn_ctx *c, MG *m)
     const int last = m->tail ? m->agg_level : m->nlev - 1;      // the agglomerated / bottom level is never fused
     while (m->nfused < last) {
         const Lev &L = m->L[m->nfused];
-        if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(c->mg_fuse_min, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
+        // rank-local hierarchies: the plain kernels inside the CUDA graph beat the fused one below 128^3 (round 1, b15_min64); levels split
+        // across ranks: every plain colour half-sweep needs its own ghost exchange, so the fused kernel (which reads its neighbours' cells
+        // itself) pays off down to 64^3
+        const int fmin_ = (m->distributed && c->mg_fuse_min == 128) ? 64 : c->mg_fuse_min;
+        if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
         ++m->nfused;
     }
 }
@@ -724,6 +730,7 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         };
         if (l > 0) mg_halo_deep(c, m, L, L.rhs, MG_PAD);        // restricted by the level above: valid cells only
         int rem = c->prm.mg_nu1;
+        if (l == 0 && m->first_sweep_done) { --rem; m->first_sweep_done = false; }      // launched ahead by the solve loop
         while (rem > 0) { --rem; wave_launch(c, m, l, 0, rem == 0 ? 2 : 0); }
         coarse();
         rem = c->prm.mg_nu2;
@@ -784,6 +791,7 @@ void mg_destroy(MG *m)
     if (!m) return;
     if (m->tail) mg_destroy(m->tail);
     if (m->coarse_graph) cudaGraphExecDestroy(m->coarse_graph);
+    if (m->ev_norm) cudaEventDestroy(m->ev_norm);
     for (double *p : m->owned) cudaFree(p);
     for (int q = 0; q < 6; ++q) if (m->bot[q]) cudaFree(m->bot[q]);
     if (m->d_norm) cudaFree(m->d_norm);
@@ -840,17 +848,26 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
     const bool talk = c->prm.mg_verbose && comm_rank(c) == 0;
     if (talk) printf("vdn_mg: levels %d%s  |rh| = %.6e  initial |r| = %.6e\n", m->nlev, m->tail ? " (+ agglomerated tail)" : "", bnorm, rn);
     auto converged = [&](double r) { return r <= rel_eps * bnorm || r <= abs_eps; };
+    if (!m->ev_norm) VDN_CUDA(cudaEventCreateWithFlags(&m->ev_norm, cudaEventDisableTiming));
     while (bnorm > 0.0 && !converged(rn) && cyc < c->prm.mg_max_cycles) {
         vcycle(c, m, 0);
         VDN_CUDA(cudaGetLastError());
-        if (m->nfused > 0) {            // the up-leg kernel of level 0 already reduced |rhs - A phi|_inf
-            VDN_CUDA(cudaMemcpyAsync(c->h_pin, m->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
-            VDN_CUDA(cudaStreamSynchronize(c->stream));
-            rn = comm_allreduce_max(c, c->h_pin[0]);
-        } else rn = res_norm();
         ++cyc;
+        if (m->nfused > 0) {
+            // the up-leg kernel of level 0 already reduced |rhs - A phi|_inf: all-reduce it on the device and bring it to the host
+            // asynchronously.  The convergence test costs a host round trip per V-cycle (and, between ranks, whatever their host threads
+            // drift apart while they wait); it is hidden behind the FIRST smoothing sweep of the next cycle, which is launched before the
+            // host looks at the norm.  If the solve turns out to be converged, that sweep has smoothed the solution once more -- harmless.
+            comm_allreduce_max_dev(c, m->d_norm);
+            VDN_CUDA(cudaMemcpyAsync(c->h_pin, m->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
+            VDN_CUDA(cudaEventRecord(m->ev_norm, c->stream));
+            if (c->prm.mg_nu1 >= 2 && cyc < c->prm.mg_max_cycles) { wave_launch(c, m, 0, 0, 0); m->first_sweep_done = true; }
+            VDN_CUDA(cudaEventSynchronize(m->ev_norm));
+            rn = c->h_pin[0];
+        } else rn = res_norm();
         if (talk) printf("vdn_mg: cycle %2d  |r|/|rh| = %.6e\n", cyc, rn / bnorm);
     }
+    m->first_sweep_done = false;
     if (m->nfused > 0 && m->L[0].phi != c->f[VDN_PHI].base) {       // odd number of ping-pong launches: result sits in the spare buffer
         VDN_CUDA(cudaMemcpyAsync(c->f[VDN_PHI].base, m->L[0].phi, sizeof(double) * m->L[0].ntot, cudaMemcpyDeviceToDevice, c->stream));
         std::swap(m->L[0].phi, m->L[0].res);
