@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--ratio", type=float, default=0.0, help="density ratio (default 2, config 5: 1000)")
     ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU sample (256^3 = one reference box: a few seconds per pass)")
     ap.add_argument("--force-nccl", action="store_true", help="A/B: ghost exchanges through NCCL send/recv instead of the peer-memory transport")
+    ap.add_argument("--xchg", default="push", choices=["push", "nccl", "pull", "pushk"],
+                    help="A/B: ghost exchange of the fused multigrid levels -- push: stored by the sweep kernel itself (default); nccl; pull / pushk: a pull kernel "
+                         "before / a push kernel after every sweep")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--global-n", type=int, default=0, help="configs 3/5: global cells per direction (default 2 x --n)")
@@ -214,7 +217,8 @@ def main():
     ctx = V.Context(3, geom.boxes, gfull.dlo, gfull.dhi, gfull.phys_bc, gfull.dx, params=prm, device=local)
     if world > 1:
         if args.force_nccl:
-            ctx.comm_tune(True)
+            args.xchg = "nccl"
+        ctx.comm_tune({"push": 0, "nccl": 1, "pull": 2, "pushk": 3}[args.xchg])
         PAR.init_comm(ctx, rank, world, rlo, rhi)
 
     # ---- pinned host buffers = what the Fortran driver would hand over (ghosts filled as varden.f90:291-300) ----
@@ -260,6 +264,8 @@ def main():
         cyc, res = step_resident()
     ctx.sync()
     ctx.prof_enable(True)
+    if world > 1:
+        ctx.debug_counters()                                 # switch the flag-wait accounting of the fused smoother on
     l0 = ctx.launch_count()
     cb0 = ctx.comm_bytes()
     sampler = ClockSampler(local); sampler.start()
@@ -291,6 +297,14 @@ def main():
     launches = ctx.launch_count() - l0
     prof = ctx.prof_report()
     ctx.prof_enable(False)
+    waits, by_rank = None, None
+    if world > 1:
+        # per rank: time per kernel family (the table below is rank 0's) and what the boundary CTAs of the fused sweeps spent waiting for a neighbour
+        mine = {"ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["ms"] > 0 and not k.startswith("phase:")},
+                "flag_wait": {k: {"ms_summed_over_ctas_per_step": v[0] / args.steps, "longest_us": v[1], "waits_per_step": v[2] / args.steps}
+                              for k, v in ctx.debug_counters().items() if v[2]}}
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, mine)
     phases = {k[6:]: v["ms"] / args.steps for k, v in prof.items() if k.startswith("phase:")}
     prof = {k: v for k, v in prof.items() if not k.startswith("phase:")}
     dev_ms = sum(p["ms"] for p in prof.values())
@@ -374,13 +388,13 @@ def main():
             "config": {"workload": label + "; variable-density RT (ratio %g:1), periodic x,y / no-slip z, nscal=2, slope_order=4, MAC rel tol 1e-10, "
                                    "%d reference box(es) of %d^3 per GPU, global %dx%dx%d; the same input state every step" % (args.ratio, geom.nboxes, n, nglob[0], nglob[1], nglob[2]),
                        "parallelism": ("1 region per GPU, process grid %s, %s ghost exchanges, NCCL allreduce, coarse MG levels agglomerated"
-                                       % (pgrid, "NCCL send/recv" if args.force_nccl else "peer-memory (CUDA-IPC)")) if world > 1 else "single GPU",
+                                       % (pgrid, {"nccl": "NCCL send/recv", "push": "peer-memory (CUDA-IPC; fused MG sweeps push their boundary results)", "pull": "peer-memory (pull kernel per exchange)", "pushk": "peer-memory (push kernel per MG sweep)"}[args.xchg])) if world > 1 else "single GPU",
                        "l2_policy": "inputs (%.1f GB of fields per GPU) exceed the 126 MB L2; no explicit flush" % (45 * 8 * geom.nboxes * (n + 6) ** 3 / 1e9),
                        "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
                        "host_wall_ms_per_step": 1e3 * wall_host / args.steps},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "phases_ms_per_step": phases, "nvlink": nvlink,
-            "kernels": fam}
+            "kernels": fam, "by_rank": by_rank}
     if rank == 0:
         print(json.dumps(line))
     ctx.close()

@@ -179,9 +179,18 @@ int vdn_mkumac(vdn_ctx *ctx);                     /* macproject.f90:403 */
  * multigrid hierarchy; takes effect at the next solve. */
 int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile);
 
-/* test / measurement hook, before vdn_ctx_set_comm: force_nccl != 0 keeps the NCCL transport (pack + grouped send/recv + unpack) for the ghost
- * exchanges instead of the peer-memory transport (CUDA-IPC mapped symmetric heap, one pull kernel per exchange) */
+/* test / measurement hook, before vdn_ctx_set_comm: transport of the ghost exchanges between ranks.
+ *   0 (default) peer memory (CUDA-IPC mapped symmetric heap): one pull kernel per field exchange; the fused multigrid sweeps store their
+ *               boundary results straight into the neighbours' ghost layers (no exchange launches inside a V-cycle)
+ *   1           NCCL (pack + grouped send/recv + unpack)
+ *   2           peer memory, one pull kernel before every fused sweep
+ *   3           peer memory, one push kernel after every fused sweep */
 int vdn_comm_tune(vdn_ctx *ctx, int force_nccl);
+
+/* measurement hook: 32 device counters -- per fused-smoother kernel family f (0 smooth, 1 down, 2 pro, 3 up of level 0, 4 coarser levels):
+ * out32[4f] = ns its boundary CTAs spent waiting for a neighbour rank's flag, [4f+1] = longest wait, [4f+2] = number of waits.  The first call
+ * switches the accounting on; every call returns the counters and resets them. */
+int vdn_debug_counters(vdn_ctx *ctx, unsigned long long *out32);
 
 /* ---- measurement: per-kernel-family CUDA-event timing on the launching stream ---- */
 int vdn_prof_enable(vdn_ctx *ctx, int on);        /* resets counters */

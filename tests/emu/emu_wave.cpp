@@ -8,17 +8,18 @@ double sm[1 << 17];
 #endif
 #include FUSED_HEADER
 
-// peer_in / peer_c: null, or 27 base pointers (process-grid offset (ox,oy,oz) at (ox+1)+3(oy+1)+9(oz+1)) of the phi / coarse-phi arrays of
-// the neighbour "ranks": the peer-memory mode, in which ghost cells of phi are read from the owner's array
+// peer_delta: null, or 27 byte distances (process-grid offset (ox,oy,oz) at (ox+1)+3(oy+1)+9(oz+1)) from this "rank's" out / crhs / czero
+// arrays to the same arrays of the neighbour "ranks" (the test lays the three arrays of every rank out in one buffer, like the symmetric heap):
+// the peer-memory mode, in which the kernel also stores what it writes near a shared face into the neighbours' ghost layers
 extern "C" int emu_sweep3_p2p(int nsw, int pre, int post, int cfg, const int *n, const int *mode, int par0, const double *h2,
                               const double *rhs, const double *b0, const double *b1, const double *b2,
                               const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk, int pad,
-                              const double *const *peer_in, const double *const *peer_c, const double *dinv)
+                              const long *peer_delta, const double *dinv)
 {
     if (nsw != 1) return 1;
     WaveArgs a;
     memset(&a, 0, sizeof a);
-    if (peer_in) { a.p2p = 1; for (int q = 0; q < 27; ++q) { a.peer_in[q] = peer_in[q]; a.peer_cphi[q] = peer_c ? peer_c[q] : nullptr; } }
+    if (peer_delta) { a.p2p = 1; for (int q = 0; q < 27; ++q) a.peer_delta[q] = peer_delta[q]; }
     for (int d = 0; d < 3; ++d) { a.n[d] = n[d]; a.h2[d] = h2[d]; a.mode[d][0] = mode[2 * d]; a.mode[d][1] = mode[2 * d + 1]; }
     a.s1 = n[0] + 2 * pad; a.s2 = (long)(n[0] + 2 * pad) * (n[1] + 2 * pad); a.off = pad * (1 + a.s1 + a.s2); a.par0 = par0;
     a.rhs = rhs; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.dinv = dinv; a.in = in; a.out = out;
@@ -38,5 +39,5 @@ extern "C" int emu_sweep3(int nsw, int pre, int post, int cfg, const int *n, con
                           const double *rhs, const double *b0, const double *b1, const double *b2,
                           const double *in, double *out, const double *cphi, double *crhs, double *czero, double *nrm, int zchunk, int pad, const double *dinv)
 {
-    return emu_sweep3_p2p(nsw, pre, post, cfg, n, mode, par0, h2, rhs, b0, b1, b2, in, out, cphi, crhs, czero, nrm, zchunk, pad, nullptr, nullptr, dinv);
+    return emu_sweep3_p2p(nsw, pre, post, cfg, n, mode, par0, h2, rhs, b0, b1, b2, in, out, cphi, crhs, czero, nrm, zchunk, pad, nullptr, dinv);
 }

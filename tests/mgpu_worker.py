@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--case", default="rt3d")
     ap.add_argument("--size", dest="n", type=int, default=64)
     ap.add_argument("--tol", type=float, default=1e-10)
-    ap.add_argument("--force-nccl", type=int, default=0, help="1: NCCL transport instead of the peer-memory transport")
+    ap.add_argument("--comm-mode", type=int, default=0, help="vdn_comm_tune: 0 peer memory (fused sweeps push), 1 NCCL, 2 pull kernels, 3 push kernels")
     ap.add_argument("--fuse-min", type=int, default=128, help="smallest level the fused smoother runs on (16 forces it onto these small grids)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -51,8 +51,7 @@ def main():
     sub = geom.subset(mine)
     prm = V.default_params(nscal=nscal, bc_val=P.bcval)
     ctx = V.Context(dim, sub.boxes, geom.dlo, geom.dhi, geom.phys_bc, geom.dx, params=prm, device=local)
-    if args.force_nccl:
-        ctx.comm_tune(True)
+    ctx.comm_tune(args.comm_mode)
     PAR.init_comm(ctx, rank, world, rlo, rhi)
     ctx.mg_tune(args.fuse_min, -1)
     pick = lambda mf: [mf[i] for i in mine]
@@ -82,4 +81,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:                      # make the failing rank's reason visible in the test log (torchrun only reports exit codes)
+        import traceback
+        print("mgpu_worker rank %s FAILED:\n%s" % (os.environ.get("RANK"), traceback.format_exc()), flush=True)
+        os._exit(3)                            # do not wait for the other ranks in a collective
+

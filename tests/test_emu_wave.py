@@ -145,30 +145,36 @@ def test_wave_matches_plain_gsrb(emu, n, cfg, zchunk, mode, par0, kern, nsw, pre
             assert np.all(czero[CV] == 0.0)
 
 
+GM_PER = ((M_WRAP, M_WRAP),) * 3
+GM_MIX = ((M_NEU, M_DIR), (M_WRAP, M_WRAP), (M_NEU, M_NEU))        # inflow / outflow x, periodic y, walls z (the rand3d multi-GPU case)
+
+
 @pytest.mark.parametrize("p2p", [0, 1])
 @pytest.mark.parametrize("cfg", [5, 2])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
-@pytest.mark.parametrize("split", [(0,), (1, 2), (0, 1, 2)])
-def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, p2p, kern="sweep3"):
-    """a level split across ranks: the kernel relaxes the neighbour ranks' cells redundantly; the block of every 'rank' must equal the same
-    block of the whole-domain sweep.  p2p = 0: the neighbours' phi (and coarse phi) sit in the rank's MG_PAD ghost layers (M_GHOST), filled by an
-    exchange beforehand; p2p = 1: the peer-memory mode -- the ghost layers of phi / coarse phi hold NaN and the kernel reads those cells from the
-    owning rank's own array through the 27-entry pointer table (the operator data stays in the ghost layers: exchanged once per solve)"""
+@pytest.mark.parametrize("split,gmode,N", [((0,), GM_PER, (32, 32, 16)), ((1, 2), GM_PER, (32, 32, 32)), ((0, 1, 2), GM_PER, (32, 32, 32)),
+                                           ((0, 1, 2), GM_MIX, (32, 32, 32)), ((0, 2), GM_MIX, (32, 16, 32))])
+def test_wave_rank_ghost_layers(emu, pre, post, split, gmode, N, cfg, p2p, kern="sweep3"):
+    """a level split across ranks: the kernel relaxes the neighbour ranks' cells redundantly (they sit in the rank's MG_PAD ghost layers,
+    M_GHOST); the block of every 'rank' must equal the same block of the whole-domain sweep.  p2p = 1: the peer-memory mode -- every rank's
+    out / coarse rhs / coarse phi arrays live in one buffer (the symmetric heap) and the kernel also stores what it writes near a shared face into
+    the ghost layers of the neighbours' arrays: after all ranks have run, the PUSH_DEPTH = 3 ghost layers of those arrays (faces, edges, corners)
+    must hold the whole-domain result as well -- the next launch reads them instead of waiting for an exchange"""
     rng = np.random.default_rng(77 + pre + 5 * post + len(split))
-    N = (32, 32, 16)                      # whole periodic domain, halved along the directions in `split`
     n = tuple(N[d] // 2 if d in split else N[d] for d in range(3))
     cN = tuple(x // 2 for x in N); cn = tuple(x // 2 for x in n)
-    gmode = ((M_WRAP, M_WRAP),) * 3
+    per = [gmode[d][0] == M_WRAP for d in range(3)]
     h2 = np.array([1.0e4, 0.8e4, 1.3e4])
     shpN = pad(N)
     b = [np.ascontiguousarray(0.5 + rng.random(shpN)) for _ in range(3)]
     rhs = np.ascontiguousarray(rng.standard_normal(shpN)); phi = np.ascontiguousarray(rng.standard_normal(shpN))
     cphi = np.ascontiguousarray(rng.standard_normal(pad(cN)))
 
-    def periodic_fill(a, nn):             # all PAD ghost layers of a whole-domain array
+    def periodic_fill(a, nn):             # all PAD ghost layers of a whole-domain array along the periodic directions
         for ax, d in ((2, 0), (1, 1), (0, 2)):
-            idx = (np.arange(-PAD, nn[d] + PAD) % nn[d]) + PAD
-            a[...] = np.take(a, idx, axis=ax)
+            if per[d]:
+                idx = (np.arange(-PAD, nn[d] + PAD) % nn[d]) + PAD
+                a[...] = np.take(a, idx, axis=ax)
     for a in b + [rhs, phi]:
         periodic_fill(a, N)
     periodic_fill(cphi, cN)
@@ -183,48 +189,68 @@ def test_wave_rank_ghost_layers(emu, pre, post, split, cfg, p2p, kern="sweep3"):
     periodic_fill(dinvN, N)
     ax, _ = apply_A(ref, b, h2, gmode, N)
     res = rhs[VN] - ax
+    cres = np.zeros(pad(cN)); cres[CVN] = res.reshape(cN[2], 2, cN[1], 2, cN[0], 2).mean(axis=(1, 3, 5))
+    refg = ref.copy()
+    periodic_fill(refg, N); periodic_fill(cres, cN)
     Pp = lambda a: a.ctypes.data_as(C.c_void_p)
-    mode = tuple((M_GHOST, M_GHOST) if d in split else (M_WRAP, M_WRAP) for d in range(3))
-    nrm_all = 0.0
+    pgrid = [2 if d in split else 1 for d in range(3)]
+    corners = list(np.ndindex(*pgrid))
+    def rank_mode(corner):
+        return tuple(((M_GHOST if (corner[d] > 0 or per[d]) else gmode[d][0]), (M_GHOST if (corner[d] < pgrid[d] - 1 or per[d]) else gmode[d][1]))
+                     if d in split else gmode[d] for d in range(3))
     def cut(a, nn, oo):                                # the block with its ghost layers, as the rank stores it
         return np.ascontiguousarray(a[oo[2]:oo[2] + nn[2] + 2 * PAD, oo[1]:oo[1] + nn[1] + 2 * PAD, oo[0]:oo[0] + nn[0] + 2 * PAD])
-    def nanghost(a, nn):                               # peer-memory mode: a rank holds its own cells only (and index n of unsplit directions)
-        m = np.full(a.shape, True)
-        m[tuple(slice(PAD, PAD + nn[d] + (0 if d in split else 1)) if d in split else slice(None) for d in (2, 1, 0))] = False
-        out = a.copy(); out[m] = np.nan
-        return out
-    corners = list(np.ndindex(*[2 if d in split else 1 for d in range(3)]))
-    pgrid = [2 if d in split else 1 for d in range(3)]
-    rank_phi = {c_: (nanghost(cut(phi, n, [c_[d] * n[d] for d in range(3)]), n) if p2p else None) for c_ in corners}
-    rank_c = {c_: (nanghost(cut(cphi, cn, [c_[d] * cn[d] for d in range(3)]), cn) if p2p else None) for c_ in corners}
+    # "symmetric heap" of every rank: out | crhs | czero
+    szf, szc = int(np.prod(pad(n))), int(np.prod(pad(cn)))
+    heap = {c_: np.full(szf + 2 * szc, np.nan) for c_ in corners}
+    view = lambda c_: (heap[c_][:szf].reshape(pad(n)), heap[c_][szf:szf + szc].reshape(pad(cn)), heap[c_][szf + szc:].reshape(pad(cn)))
+    nrm_all = 0.0
     for corner in corners:
         o = [corner[d] * n[d] for d in range(3)]          # block origin (x, y, z)
+        mode = rank_mode(corner)
         lb = [cut(x, n, o) for x in b]; lrhs = cut(rhs, n, o); ldinv = cut(dinvN, n, o)
-        lphi = rank_phi[corner] if p2p else cut(phi, n, o)
-        lc = rank_c[corner] if p2p else cut(cphi, cn, [x // 2 for x in o])
-        peers = peersc = None
+        lphi = cut(phi, n, o); lc = cut(cphi, cn, [x // 2 for x in o])
+        out, crhs, czero = view(corner)
+        delta = None
         if p2p:
-            PT = C.c_void_p * 27
-            peers, peersc = PT(), PT()
+            delta = (C.c_long * 27)()
             for q in range(27):
                 off = (q % 3 - 1, (q // 3) % 3 - 1, q // 9 - 1)
-                if any(off[d] != 0 and d not in split for d in range(3)):
-                    continue                              # no rank there (that direction wraps by index inside the rank)
-                pc = tuple((corner[d] + off[d]) % pgrid[d] for d in range(3))
-                peers[q] = rank_phi[pc].ctypes.data; peersc[q] = rank_c[pc].ctypes.data
-        out = np.full(pad(n), np.nan); crhs = np.full(pad(cn), np.nan); czero = np.full(pad(cn), np.nan); nrm = np.zeros(1)
+                pc = [corner[d] + off[d] for d in range(3)]
+                ok = True
+                for d in range(3):
+                    if off[d] == 0:
+                        continue
+                    if d not in split:
+                        ok = False
+                    elif pc[d] < 0 or pc[d] >= pgrid[d]:
+                        if per[d]:
+                            pc[d] %= pgrid[d]
+                        else:
+                            ok = False
+                if ok:
+                    delta[q] = heap[tuple(pc)].ctypes.data - heap[corner].ctypes.data
+        nrm = np.zeros(1)
         fn = emu.emu_sweep3_p2p
         rc = fn(1, pre, post, cfg, (C.c_int * 3)(*n), (C.c_int * 6)(*[m for d in mode for m in d]), sum(o) & 1, Pp(h2),
-                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD, peers, peersc, Pp(ldinv))
+                Pp(lrhs), Pp(lb[0]), Pp(lb[1]), Pp(lb[2]), Pp(lphi), Pp(out), Pp(lc), Pp(crhs), Pp(czero), Pp(nrm), 8, PAD, delta, Pp(ldinv))
         assert rc == 0
-        V = (slice(PAD, n[2] + PAD), slice(PAD, n[1] + PAD), slice(PAD, n[0] + PAD))
-        want = ref[o[2] + PAD:o[2] + PAD + n[2], o[1] + PAD:o[1] + PAD + n[1], o[0] + PAD:o[0] + PAD + n[0]]
-        assert np.abs(out[V] - want).max() <= 1e-12 * np.abs(want).max(), corner
-        if post == 2:
-            cr = res.reshape(cN[2], 2, cN[1], 2, cN[0], 2).mean(axis=(1, 3, 5))
-            co = [x // 2 for x in o]
-            CV = (slice(PAD, cn[2] + PAD), slice(PAD, cn[1] + PAD), slice(PAD, cn[0] + PAD))
-            assert np.abs(crhs[CV] - cr[co[2]:co[2] + cn[2], co[1]:co[1] + cn[1], co[0]:co[0] + cn[0]]).max() <= 1e-10 * np.abs(res).max()
         nrm_all = max(nrm_all, nrm[0])
+    for corner in corners:
+        o = [corner[d] * n[d] for d in range(3)]
+        mode = rank_mode(corner)
+        out, crhs, czero = view(corner)
+        # own cells, and in peer-memory mode the 3 ghost layers on the sides shared with another rank
+        g = [[(3 if (p2p and mode[d][s] == M_GHOST) else 0) for s in range(2)] for d in range(3)]
+        R = tuple(slice(PAD - g[d][0], PAD + n[d] + g[d][1]) for d in (2, 1, 0))
+        RN = tuple(slice(o[d] + PAD - g[d][0], o[d] + PAD + n[d] + g[d][1]) for d in (2, 1, 0))
+        want = refg[RN]
+        assert np.abs(out[R] - want).max() <= 1e-12 * np.abs(want).max(), corner
+        if post == 2:
+            co = [x // 2 for x in o]
+            CR = tuple(slice(PAD - g[d][0], PAD + cn[d] + g[d][1]) for d in (2, 1, 0))
+            CRN = tuple(slice(co[d] + PAD - g[d][0], co[d] + PAD + cn[d] + g[d][1]) for d in (2, 1, 0))
+            assert np.abs(crhs[CR] - cres[CRN]).max() <= 1e-10 * np.abs(res).max(), corner
+            assert np.all(czero[CR] == 0.0), corner
     if post == 3:
         assert abs(nrm_all - np.abs(res).max()) <= 1e-10 * np.abs(res).max()

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
     "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune", "vdn_device_count", "vdn_comm_bytes",
+    "vdn_debug_counters",
 ]
 
 
@@ -212,9 +213,18 @@ class Context:
         self._chk(self.lib.vdn_mac_solve(self.h, C.c_double(rel_eps), C.c_double(abs_eps), C.byref(n), C.byref(r)))
         return n.value, r.value
 
-    def comm_tune(self, force_nccl):
-        """measurement hook, before set_comm: keep the NCCL transport for the ghost exchanges"""
-        self._chk(self.lib.vdn_comm_tune(self.h, int(force_nccl)))
+    def comm_tune(self, mode):
+        """measurement hook, before set_comm: transport of the ghost exchanges -- 0 peer memory with the fused sweeps pushing their boundary results
+        (default), 1 NCCL, 2 peer memory with a pull kernel before every sweep, 3 peer memory with a push kernel after every sweep"""
+        self._chk(self.lib.vdn_comm_tune(self.h, int(mode)))
+
+    def debug_counters(self):
+        """measurement hook: flag-wait accounting of the fused smoother per kernel family {name: (ms waited, longest wait in us, waits)};
+        the first call switches it on, every call resets it"""
+        buf = (C.c_ulonglong * 32)()
+        self._chk(self.lib.vdn_debug_counters(self.h, buf))
+        names = ["mg_wave_smooth_l0", "mg_wave_down_l0", "mg_wave_pro_l0", "mg_wave_up_l0", "mg_wave_coarse"]
+        return {n: (buf[4 * i] / 1e6, buf[4 * i + 1] / 1e3, int(buf[4 * i + 2])) for i, n in enumerate(names)}
 
     def mg_tune(self, fuse_min=128, tile=-1):
         """test hook: smallest level the fused smoother runs on, forced tile shape (-1: measured defaults)"""

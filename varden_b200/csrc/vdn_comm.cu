@@ -36,8 +36,10 @@ struct Comm {
     std::vector<char *> peer_base;                                  // base of rank r's heap in MY address space (own rank: heap)
     char **d_peer_base = nullptr;
     unsigned long long epoch = 0;                                   // exchanges issued so far (the same sequence on every rank)
+    unsigned int *d_push_ctr = nullptr;                             // block counter of k_halo_push
+    int mg_xchg = 0;                                                // how the fused multigrid levels exchange (vdn_comm_tune): 0 push inside the sweep, 2 pull kernels, 3 push kernels
 };
-constexpr size_t HEAP_RESERVED = 256;                               // flag word (+ padding) at the start of every heap
+constexpr size_t HEAP_RESERVED = 1024;                              // header of every heap: word 0 = "my stream has reached exchange e", words 1 + r = "the data rank r pushed for exchange e has arrived"
 
 // ---- host-only planning (testable without a GPU) ----
 extern "C" int vdn_comm_plan(int dim, int rank, int nranks, const int *region_lo, const int *region_hi,
@@ -139,9 +141,10 @@ static void ensure_buf(vdn_ctx *c, size_t doubles)
 // receives in the reverse order -- the message a peer sent for its offset o' is the one I receive for my offset -o', and negation reverses
 // the order -- so the pairing also holds when one peer is my neighbour for several offsets (two ranks along a periodic direction).
 // ------------------------------------------------------------------------------------------
-extern "C" int vdn_halo_plan_ex(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng,
-                                int dmask, int nodal, int carry_n,
-                                int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n, int *recv_shift)
+static int halo_plan_core(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng,
+                          int dmask, int nodal, int carry_n,
+                          int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n, int *recv_shift,
+                          int *send_shift)
 {
     *nsend = 0; *nrecv = 0;
     auto peer_of = [&](const int *o) -> int {          // rank at my process-grid coordinates + o, or -1
@@ -174,17 +177,25 @@ extern "C" int vdn_halo_plan_ex(int dim, const int *pgrid, const int *pcoord, co
                 const int nod = (d == nodal) ? 1 : 0;
                 const bool split = ((dmask >> d) & 1) && pgrid[d] > 1;
                 if (o[d] == 0) { lo[d] = 0; ext[d] = n[d] + nod + ((carry_n && !split) ? 1 : 0); }
-                else if (pass == 0) { lo[d] = o[d] < 0 ? nod : n[d] - ng; ext[d] = ng; }               // my cells / faces next to that neighbour
+                else if (pass == 0) { lo[d] = o[d] < 0 ? nod : n[d] - ng; ext[d] = ng; sh[d] = -o[d] * n[d]; }   // my cells / faces next to that neighbour (its ghosts)
                 else                { lo[d] = o[d] < 0 ? -ng : n[d] + nod; ext[d] = ng; sh[d] = -o[d] * n[d]; }   // my ghosts on that side
             }
             int &cnt = pass == 0 ? *nsend : *nrecv;
             if (cnt >= 26) return 1;
             int *pp = pass == 0 ? send_peer : recv_peer, *pl = pass == 0 ? send_lo : recv_lo, *pn = pass == 0 ? send_n : recv_n;
             pp[cnt] = peer;
-            for (int d = 0; d < 3; ++d) { pl[3 * cnt + d] = lo[d]; pn[3 * cnt + d] = ext[d]; if (pass == 1 && recv_shift) recv_shift[3 * cnt + d] = sh[d]; }
+            for (int d = 0; d < 3; ++d) { pl[3 * cnt + d] = lo[d]; pn[3 * cnt + d] = ext[d]; if (pass == 1 && recv_shift) recv_shift[3 * cnt + d] = sh[d];
+                                          if (pass == 0 && send_shift) send_shift[3 * cnt + d] = sh[d]; }
             ++cnt;
         }
     return 0;
+}
+extern "C" int vdn_halo_plan_ex(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng,
+                                int dmask, int nodal, int carry_n,
+                                int *nsend, int *send_peer, int *send_lo, int *send_n, int *nrecv, int *recv_peer, int *recv_lo, int *recv_n, int *recv_shift)
+{
+    return halo_plan_core(dim, pgrid, pcoord, periodic, coord2rank, n, ng, dmask, nodal, carry_n, nsend, send_peer, send_lo, send_n,
+                          nrecv, recv_peer, recv_lo, recv_n, recv_shift, nullptr);
 }
 // the multigrid form (cell-centred level arrays): kept as the entry point the round-1 tests bind
 extern "C" int vdn_halo_plan(int dim, const int *pgrid, const int *pcoord, const int *periodic, const int *coord2rank, const int *n, int ng, int dmask,
@@ -250,6 +261,66 @@ static bool in_heap(const Comm *cm, const void *p)
     return cm->p2p && (const char *)p >= cm->heap && (const char *)p < cm->heap + cm->heap_bytes;
 }
 
+// ---- peer-memory transport, push form: one kernel stores this rank's boundary layers of up to 3 arrays of one level straight into the ghost
+// layers of the neighbours' arrays (local reads, posted NVLink writes), then tells every neighbour "my data of exchange e has arrived" in the
+// neighbour's own heap header (word 1 + my rank) and waits until the neighbours have told it the same.  Used for the ping-pong arrays of the
+// fused multigrid levels, where the receiver is never still reading the ghost layers that are being overwritten (it read the OTHER buffer in the
+// sweep it may still be running), so no "ready to receive" handshake is needed and the exchange costs one flag latency. ----
+struct PushSeg { int peer; int lo[3], n[3], shift[3]; int blk0; };
+struct PushArgs {
+    long arr_off[3]; int narr;      // byte offsets, inside the symmetric heap, of each array's local element (0,0,0)
+    int sy, sz;
+    int nseg; PushSeg seg[26];
+    int npeer; int peers[26];       // distinct neighbour ranks
+    char *const *peer_base; int me;
+    unsigned long long epoch;
+    unsigned int *ctr; int nblk;    // blocks that have stored (and fenced) their part
+};
+constexpr int PUSH_NT = 256, PUSH_UNR = 4;
+__global__ void __launch_bounds__(PUSH_NT) k_halo_push(PushArgs a)
+{
+    int q = 0;
+#pragma unroll 1
+    for (int t = 1; t < a.nseg; ++t) if ((int)blockIdx.x >= a.seg[t].blk0) q = t;
+    const PushSeg &s = a.seg[q];
+    const long per = (long)s.n[0] * s.n[1] * s.n[2];
+    const long t0 = (long)((int)blockIdx.x - s.blk0) * (PUSH_NT * PUSH_UNR) + threadIdx.x;
+    for (int ar = 0; ar < a.narr; ++ar) {
+        const double *src = (const double *)(a.peer_base[a.me] + a.arr_off[ar]);
+        double *dst = (double *)(a.peer_base[s.peer] + a.arr_off[ar]);
+        double v[PUSH_UNR]; long dix[PUSH_UNR]; bool ok[PUSH_UNR];
+#pragma unroll
+        for (int u = 0; u < PUSH_UNR; ++u) {
+            const long t = t0 + (long)u * PUSH_NT;
+            dix[u] = 0; v[u] = 0.0;
+            ok[u] = t < per;
+            if (ok[u]) {
+                const int i = s.lo[0] + (int)(t % s.n[0]), j = s.lo[1] + (int)((t / s.n[0]) % s.n[1]), k = s.lo[2] + (int)(t / ((long)s.n[0] * s.n[1]));
+                v[u] = src[i + (long)a.sy * j + (long)a.sz * k];
+                dix[u] = (i + s.shift[0]) + (long)a.sy * (j + s.shift[1]) + (long)a.sz * (k + s.shift[2]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PUSH_UNR; ++u) if (ok[u]) dst[dix[u]] = v[u];
+    }
+    // the last block to finish signals the neighbours and waits for their signals
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = (atomicAdd(a.ctr, 1u) == (unsigned)(a.nblk - 1));
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *a.ctr = 0;                       // for the next exchange (stream-ordered after this kernel)
+    if ((int)threadIdx.x < a.npeer) {
+        const int p = a.peers[threadIdx.x];
+        __threadfence_system();
+        *(volatile unsigned long long *)(a.peer_base[p] + 8 * (1 + a.me)) = a.epoch;
+        const volatile unsigned long long *f = (const volatile unsigned long long *)(a.peer_base[a.me] + 8 * (1 + p));
+        while (*f < a.epoch) { }
+        __threadfence_system();
+    }
+}
+
 // Fill ng ghost layers of an array along the split directions in dmask (faces, edges and corners in one phase).
 // nodal: face-centred direction of the array or -1; carry_n: multigrid level arrays (see vdn_halo_plan_ex).
 void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int nodal, int dmask, bool carry_n)
@@ -305,6 +376,40 @@ void comm_halo(vdn_ctx *c, View v, const int *n, int dim, int ng, int nc, int no
     launch_pack(c, pu);
 }
 
+// push form of comm_halo for up to 3 multigrid level arrays of one level (all in the symmetric heap): see k_halo_push
+void comm_push(vdn_ctx *c, double *const *arrs, int narr, long off, int sy, int sz, const int *n, int dim, int ng, int dmask)
+{
+    Comm *cm = c->comm;
+    if (!cm || ng == 0 || narr == 0) return;
+    VDN_REQUIRE(cm->p2p && narr <= 3, "comm_push needs the peer-memory transport");
+    int ns = 0, nr = 0, speer[26], rpeer[26], slo[78], sn[78], rlo[78], rn[78], rsh[78], ssh[78], per[3];
+    for (int d = 0; d < 3; ++d) per[d] = c->dom_bc[d][0] == BC_PERIODIC ? 1 : 0;
+    VDN_REQUIRE(halo_plan_core(dim, cm->pgrid, cm->pcoord, per, cm->coord2rank.data(), n, ng, dmask, -1, 1,
+                               &ns, speer, slo, sn, &nr, rpeer, rlo, rn, rsh, ssh) == 0, "too many halo segments");
+    if (ns == 0) return;
+    PushArgs a;
+    a.narr = narr;
+    for (int q = 0; q < narr; ++q) { VDN_REQUIRE(in_heap(cm, arrs[q]), "comm_push: array outside the symmetric heap"); a.arr_off[q] = (long)((const char *)(arrs[q] + off) - cm->heap); }
+    a.sy = sy; a.sz = sz; a.nseg = ns; a.peer_base = cm->d_peer_base; a.me = cm->rank; a.epoch = ++cm->epoch;
+    a.npeer = 0;
+    long bytes = 0; int nblk = 0;
+    for (int q = 0; q < ns; ++q) {
+        a.seg[q].peer = speer[q];
+        long cnt = 1;
+        for (int d = 0; d < 3; ++d) { a.seg[q].lo[d] = slo[3 * q + d]; a.seg[q].n[d] = sn[3 * q + d]; a.seg[q].shift[d] = ssh[3 * q + d]; cnt *= sn[3 * q + d]; }
+        a.seg[q].blk0 = nblk;
+        nblk += (int)((cnt + PUSH_NT * PUSH_UNR - 1) / (PUSH_NT * PUSH_UNR));
+        bytes += 8 * cnt * narr;
+        bool seen = false;
+        for (int t = 0; t < a.npeer; ++t) if (a.peers[t] == speer[q]) seen = true;
+        if (!seen) a.peers[a.npeer++] = speer[q];
+    }
+    a.ctr = cm->d_push_ctr; a.nblk = nblk;
+    c->comm_bytes += bytes;
+    k_halo_push<<<nblk, PUSH_NT, 0, c->stream>>>(a);
+    VDN_CUDA(cudaGetLastError());
+}
+
 long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask)
 {
     Comm *cm = c->comm;
@@ -317,18 +422,19 @@ long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask)
     return v;
 }
 
-// Tables for a kernel that reads its neighbours' cells itself (the fused smoother in peer-memory mode): base pointer of arr / arr2 (both in the
-// symmetric heap; arr2 may be null) on the rank at every process-grid offset (ox, oy, oz) -> index (ox+1) + 3 (oy+1) + 9 (oz+1), the neighbours'
-// flag words, this rank's flag word and the epoch of this launch (one epoch per exchange-like event, the same sequence on every rank).
-// dmask: split directions of the array.  Returns false when the peer-memory transport is not available for these arrays.
-bool comm_peer_tables(vdn_ctx *c, const double *arr, const double *arr2, int dmask, const double **p27, const double **p27b,
+// Tables for a kernel that stores into its neighbours' ghost layers itself (the fused smoother in peer-memory mode): for the rank at every
+// process-grid offset (ox, oy, oz) -> index (ox+1) + 3 (oy+1) + 9 (oz+1) -- the byte distance from this rank's symmetric heap to that rank's
+// (one layout on every rank: local pointer + distance = the same array there) and its flag word; this rank's flag word and the epoch of this
+// launch (one epoch per exchange-like event, the same sequence on every rank).  arrs: the arrays the kernel will push (all must live in the heap).
+// dmask: split directions of the level.  Returns false when the peer-memory transport is not available for these arrays.
+bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask, long *delta27,
                       const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch)
 {
     Comm *cm = c->comm;
-    if (!cm || !in_heap(cm, arr) || (arr2 && !in_heap(cm, arr2))) return false;
-    const long off = (long)((const char *)arr - cm->heap), off2 = arr2 ? (long)((const char *)arr2 - cm->heap) : 0;
+    if (!cm) return false;
+    for (int q = 0; q < narr; ++q) if (arrs[q] && !in_heap(cm, arrs[q])) return false;
     for (int q = 0; q < 27; ++q) {
-        p27[q] = nullptr; p27b[q] = nullptr; f27[q] = nullptr;
+        delta27[q] = 0; f27[q] = nullptr;
         const int o[3] = { q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1 };
         int pc[3]; bool ok = true;
         for (int d = 0; d < 3; ++d) {
@@ -342,8 +448,7 @@ bool comm_peer_tables(vdn_ctx *c, const double *arr, const double *arr2, int dma
         }
         if (!ok) continue;
         const int r = cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])];
-        p27[q] = (const double *)(cm->peer_base[r] + off);
-        if (arr2) p27b[q] = (const double *)(cm->peer_base[r] + off2);
+        delta27[q] = (long)(cm->peer_base[r] - cm->heap);
         if (r != cm->rank) f27[q] = (const unsigned long long *)cm->peer_base[r];
     }
     *mine = (unsigned long long *)cm->heap;
@@ -406,6 +511,8 @@ void comm_allreduce_max_dev(vdn_ctx *c, double *d_v)
 }
 double comm_allreduce_sum(vdn_ctx *c, double v) { return allreduce(c, v, ncclSum); }
 
+bool comm_peer_mode(const vdn_ctx *c) { return c->comm && c->comm->p2p; }
+int comm_mg_xchg(const vdn_ctx *c) { return c->comm ? c->comm->mg_xchg : 0; }
 int comm_rank(const vdn_ctx *c) { return c->comm ? c->comm->rank : 0; }
 int comm_nranks(const vdn_ctx *c) { return c->comm ? c->comm->nranks : 1; }
 const int *comm_pgrid(const vdn_ctx *c) { return c->comm->pgrid; }
@@ -439,6 +546,7 @@ void comm_destroy(Comm *cm)
     if (cm->d_scal) cudaFree(cm->d_scal);
     for (int r = 0; r < (int)cm->peer_base.size(); ++r) if (r != cm->rank && cm->peer_base[r]) cudaIpcCloseMemHandle(cm->peer_base[r]);
     if (cm->d_peer_base) cudaFree(cm->d_peer_base);
+    if (cm->d_push_ctr) cudaFree(cm->d_push_ctr);
     if (cm->heap) cudaFree(cm->heap);
     delete cm;
 }
@@ -450,7 +558,8 @@ void ctx_rebuild_bc(vdn_ctx *c);      // vdn_ctx.cu
 static void p2p_setup(vdn_ctx *c)
 {
     Comm *cm = c->comm;
-    if (c->comm_force_nccl) return;
+    if (c->comm_mode == 1) return;
+    cm->mg_xchg = c->comm_mode;
     // size: the fields + the multigrid arrays that are not aliases of fields (level 0: 2 arrays; coarser distributed levels: 7 each)
     size_t need = HEAP_RESERVED;
     for (int i = 0; i < VDN_NFIELDS; ++i) {
@@ -512,6 +621,8 @@ static void p2p_setup(vdn_ctx *c)
     }
     cm->heap = heap; cm->heap_bytes = need; cm->heap_used = HEAP_RESERVED; cm->peer_base = peer; cm->p2p = true;
     VDN_CUDA(cudaMemsetAsync(heap, 0, HEAP_RESERVED, c->stream));
+    VDN_REQUIRE(8 * (size_t)(1 + cm->nranks) <= HEAP_RESERVED, "too many ranks for the heap header");
+    VDN_CUDA(cudaMalloc(&cm->d_push_ctr, 64)); VDN_CUDA(cudaMemsetAsync(cm->d_push_ctr, 0, 64, c->stream));
     VDN_CUDA(cudaMalloc(&cm->d_peer_base, sizeof(char *) * cm->nranks));
     VDN_CUDA(cudaMemcpyAsync(cm->d_peer_base, peer.data(), sizeof(char *) * cm->nranks, cudaMemcpyHostToDevice, c->stream));
     // move the fields into the heap (nothing has been uploaded yet: contents = the initial values of vdn_ctx_create)

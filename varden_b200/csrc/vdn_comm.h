@@ -15,8 +15,12 @@ const int *comm_pcoord(const vdn_ctx *c);
 bool comm_has_neighbor(const vdn_ctx *c, int d, int s);
 void comm_allgather(vdn_ctx *c, const double *send, double *recv, size_t count);
 void comm_coord_of(const vdn_ctx *c, int r, int *pc);
-// peer-memory tables for kernels that read neighbour ranks' arrays themselves (see vdn_comm.cu); false: not available (NCCL transport)
-bool comm_peer_tables(vdn_ctx *c, const double *arr, const double *arr2, int dmask, const double **p27, const double **p27b,
+// peer-memory tables for kernels that write into neighbour ranks' arrays themselves (see vdn_comm.cu); false: not available (NCCL transport)
+bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask, long *delta27,
                       const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch);
+int comm_mg_xchg(const vdn_ctx *c);                         // exchange style of the fused multigrid levels (vdn_ctx.h: comm_mode)
+// push form of comm_halo for up to 3 level arrays of one level (peer-memory transport): boundary layers stored into the neighbours' ghost layers
+void comm_push(vdn_ctx *c, double *const *arrs, int narr, long off, int sy, int sz, const int *n, int dim, int ng, int dmask);
+bool comm_peer_mode(const vdn_ctx *c);                     // the peer-memory transport is up (symmetric heap mapped by every rank)
 long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask);      // cells an exchange of depth ng would move (accounting)
 void comm_allreduce_max_dev(vdn_ctx *c, double *d_v);       // ncclAllReduce(MAX) of one device double, in place, asynchronous

@@ -215,6 +215,8 @@ static void ctx_free(vdn_ctx *c)
     if (c->scratch) cudaFree(c->scratch);
     if (c->d_eps) cudaFree(c->d_eps);
     if (c->d_red) cudaFree(c->d_red);
+    if (c->d_dbg) cudaFree(c->d_dbg);
+    for (int q = 0; q < 4; ++q) if (c->xstage[q]) cudaFree(c->xstage[q]);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage) cudaFreeHost(c->stage);
     for (auto &p : c->prof) for (auto &pr : p.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -258,22 +260,43 @@ static void box_copy(vdn_ctx *c, int field, int ibox, double *host, int ng, int 
         if (!upload && wait) VDN_CUDA(cudaStreamSynchronize(stream));
         return;
     }
-    cudaMemcpy3DParms p; memset(&p, 0, sizeof p);
-    const size_t hplane = (size_t)hext[0] * hext[1], dplane = (size_t)f.ext[0] * f.ext[1];
-    for (int comp = 0; comp < ncomp; ++comp) {
-        double *hp = host + (size_t)comp * hplane * hext[2];
-        double *dp = f.base + (size_t)comp * f.cs;
-        cudaPitchedPtr hptr = make_cudaPitchedPtr(hp, sizeof(double) * hext[0], hext[0], hext[1]);
-        cudaPitchedPtr dptr = make_cudaPitchedPtr(dp, sizeof(double) * f.ext[0], f.ext[0], f.ext[1]);
-        cudaPos hpos = make_cudaPos(sizeof(double) * (clo[0] - hlo[0]), clo[1] - hlo[1], clo[2] - hlo[2]);
-        cudaPos dpos = make_cudaPos(sizeof(double) * (clo[0] - c->rlo[0] + f.ngd[0]), clo[1] - c->rlo[1] + f.ngd[1], clo[2] - c->rlo[2] + f.ngd[2]);
-        p.extent = make_cudaExtent(sizeof(double) * (chi[0] - clo[0] + 1), chi[1] - clo[1] + 1, chi[2] - clo[2] + 1);
-        if (upload) { p.srcPtr = hptr; p.srcPos = hpos; p.dstPtr = dptr; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
-        else        { p.srcPtr = dptr; p.srcPos = dpos; p.dstPtr = hptr; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
-        VDN_CUDA(cudaMemcpy3DAsync(&p, stream));
-        (void)hplane; (void)dplane;
+    // several boxes per region (or a different ghost width): the host box travels as ONE flat copy through a device staging buffer and a
+    // kernel scatters / gathers its rows into / out of the region array.  (cudaMemcpy3DAsync moves 2 KB rows at ~21 GB/s; a flat copy of
+    // pinned memory runs at the PCIe rate, ~55 GB/s, and the device-side pass costs ~2 % of it.)
+    const size_t hcount = (size_t)hext[0] * hext[1] * hext[2] * ncomp;
+    const int slot = (upload ? 0 : 2) + (stream == c->stream ? 0 : 1);       // one staging buffer per (direction, stream): stream order protects it
+    if (c->xstage_bytes[slot] < hcount * sizeof(double)) {
+        VDN_CUDA(cudaStreamSynchronize(stream));
+        if (c->xstage[slot]) VDN_CUDA(cudaFree(c->xstage[slot]));
+        // sized at once for the largest box of any field (widest ghost zone, most components, face-centred): no regrowth from field to field
+        int ngmax = 0, ncmax = 1;
+        for (int i = 0; i < VDN_NFIELDS; ++i) if (c->f[i].base) { ngmax = std::max(ngmax, c->f[i].ng); ncmax = std::max(ncmax, c->f[i].nc); }
+        size_t big = 0;
+        for (int b = 0; b < c->nboxes; ++b) {
+            size_t v = sizeof(double) * ncmax;
+            for (int d = 0; d < c->dim; ++d) v *= (size_t)(c->box_hi[b][d] - c->box_lo[b][d] + 2 + 2 * ngmax);
+            big = std::max(big, v);
+        }
+        const size_t want = std::max(hcount * sizeof(double), big);
+        VDN_CUDA(cudaMalloc(&c->xstage[slot], want));
+        c->xstage_bytes[slot] = want;
     }
-    if (!upload && wait) VDN_CUDA(cudaStreamSynchronize(stream));
+    double *stg = c->xstage[slot];
+    BoxCopyArgs a;
+    a.stage = stg; a.base = f.base; a.cs = f.cs; a.ncomp = ncomp; a.upload = upload ? 1 : 0;
+    for (int d = 0; d < 3; ++d) {
+        a.hext[d] = hext[d]; a.hofs[d] = clo[d] - hlo[d]; a.n[d] = chi[d] - clo[d] + 1;
+        a.dofs[d] = d < c->dim ? clo[d] - c->rlo[d] + f.ngd[d] : 0;
+    }
+    a.dext0 = f.ext[0]; a.dext1 = f.ext[1];
+    if (upload) {
+        VDN_CUDA(cudaMemcpyAsync(stg, host, hcount * sizeof(double), cudaMemcpyHostToDevice, stream));
+        st_box_copy(a, stream);
+    } else {
+        st_box_copy(a, stream);
+        VDN_CUDA(cudaMemcpyAsync(host, stg, hcount * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (wait) VDN_CUDA(cudaStreamSynchronize(stream));
+    }
 }
 
 // one pass of the hot path, advance_timestep.f90:95-124
@@ -489,7 +512,16 @@ int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile)
                  ctx->mg_fuse_min = fuse_min; ctx->mg_tile_force = tile; }) }
 
 int vdn_comm_tune(vdn_ctx *ctx, int force_nccl)
-{ VDN_TRY(ctx, { VDN_REQUIRE(!ctx->comm, "vdn_comm_tune must be called before vdn_ctx_set_comm"); ctx->comm_force_nccl = force_nccl != 0; }) }
+{ VDN_TRY(ctx, { VDN_REQUIRE(!ctx->comm, "vdn_comm_tune must be called before vdn_ctx_set_comm"); VDN_REQUIRE(force_nccl >= 0 && force_nccl <= 3, "transport mode out of range"); ctx->comm_mode = force_nccl; }) }
+
+// measurement hook: 32 device counters (the fused smoother's flag-wait accounting: 4 per kernel family -- ns waited, max ns, waits, unused);
+// the first call allocates them (so the kernels start counting), every call returns and resets them
+int vdn_debug_counters(vdn_ctx *ctx, unsigned long long *out32)
+{ VDN_TRY(ctx, {
+      VDN_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (!ctx->d_dbg) { VDN_CUDA(cudaMalloc(&ctx->d_dbg, 32 * 8)); VDN_CUDA(cudaMemset(ctx->d_dbg, 0, 32 * 8)); }
+      if (out32) VDN_CUDA(cudaMemcpy(out32, ctx->d_dbg, 32 * 8, cudaMemcpyDeviceToHost));
+      VDN_CUDA(cudaMemset(ctx->d_dbg, 0, 32 * 8)); }) }
 
 int vdn_prof_enable(vdn_ctx *ctx, int on)
 { VDN_TRY(ctx, { prof_collect(ctx); ctx->prof.clear(); ctx->prof_idx.clear(); ctx->prof_on = on != 0; }) }

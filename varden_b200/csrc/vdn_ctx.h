@@ -32,8 +32,10 @@ struct vdn_ctx {
     double *scratch = nullptr; int nscr = 0; long s_sy = 0, s_sz = 0, s_n = 0, s_off = 0;
     double *d_eps = nullptr;                            // per-box eps
     double *d_red = nullptr;                            // reduction scratch (device)
+    unsigned long long *d_dbg = nullptr;                // measurement hook (vdn_debug_counters): 32 counters, allocated on first use
     double *h_pin = nullptr;                            // pinned host scalars
     double *stage = nullptr; size_t stage_bytes = 0;    // pinned staging buffer for pageable uploads
+    double *xstage[4] = {}; size_t xstage_bytes[4] = {}; // device staging of host boxes (multi-box regions): [upload, upload on a copy stream, download, download on a copy stream]
     std::string err;
     long long launches = 0;
     long long comm_bytes = 0;                           // bytes this rank sent to other ranks (halo exchanges, all-gathers) since creation
@@ -49,7 +51,8 @@ struct vdn_ctx {
     cudaEvent_t ev_up[VDN_NFIELDS] = {}, ev_fin[VDN_NFIELDS] = {};
     const vdn_host_state *hio = nullptr;
     int mg_fuse_min = 128, mg_tile_force = -1;          // fused smoother: smallest level it runs on; test hook (vdn_mg_tune)
-    bool comm_force_nccl = false;                       // test / measurement hook (vdn_comm_tune): keep the NCCL transport
+    int comm_mode = 0;                                  // test / measurement hook (vdn_comm_tune): 0 peer memory, fused levels push inside the sweep (default);
+                                                        // 1 NCCL transport; 2 peer memory, pull kernel before every sweep; 3 peer memory, push kernel after every sweep
     bool lapu_set = false;                              // LAPU has been uploaded (required when visc_coef > 0)
 
     View S(int q) const { View v; v.sy = (int)s_sy; v.sz = (int)s_sz; v.cs = (int)s_n; v.p = scratch + (long)q * s_n + s_off; return v; }
@@ -79,6 +82,9 @@ void st_mk_mac_coeffs(vdn_ctx *c);
 void st_mkumac(vdn_ctx *c);
 int  st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, double *resnorm, bool phi_zero = false, double bnorm_known = -1.0);
 void st_setval(vdn_ctx *c, int field, double val);
+// rows of a host box (staged flat on the device) <-> the region array
+struct BoxCopyArgs { double *stage, *base; long cs; int hext[3], hofs[3], n[3], dofs[3], dext0, dext1, ncomp, upload; };
+void st_box_copy(const BoxCopyArgs &a, cudaStream_t stream);
 double st_absmax_valid(vdn_ctx *c, int field);           // norm_inf over valid cells/faces, all comps
 void mg_destroy(MG *mg);
 void comm_destroy(Comm *cm);

@@ -40,6 +40,8 @@ struct MG {
     int coarse_graph_launches = 0;
     int graph_level = 1;                        // first level executed by the captured graph
     bool distributed = false;                   // levels exchange halos with neighbour ranks
+    bool push = false;                          // the fused levels fill their neighbours' ghost layers themselves (peer-memory transport)
+    bool pushk = false;                         // ... by a push kernel after every sweep instead of stores inside the sweep (A/B hook)
     // agglomeration (multi-rank): local level agg_level is solved on `tail`, a whole-domain hierarchy every rank holds
     int agg_level = -1;
     MG *tail = nullptr;
@@ -449,6 +451,8 @@ void mg_pick_fused(vdn_ctx *c, MG *m)
         if (std::min(L.n[0], std::min(L.n[1], L.n[2])) < std::max(fmin_, 16) || (L.n[0] | L.n[1] | L.n[2]) & 1) break;
         ++m->nfused;
     }
+    m->push = m->distributed && m->nfused > 0 && comm_peer_mode(c) && comm_mg_xchg(c) == 0;
+    m->pushk = m->distributed && m->nfused > 0 && comm_peer_mode(c) && comm_mg_xchg(c) == 3;
 }
 
 void mg_build(vdn_ctx *c)
@@ -619,16 +623,23 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     const int nsw = 1;
     // pick tile shape and z-chunking: cost ~ waves * CTAs sharing an SM * iterations * plane cells
     int best_cfg = 0, best_ch = L.n[2]; double best = 1e300;
-    // peer-memory mode: the kernel reads the neighbour ranks' cells (phi, and the coarse correction under them) straight from their arrays
+    // peer-memory mode: the kernel stores what it writes near a face shared with another rank into that rank's ghost layers as well (phi, and
+    // under post == 2 the coarse right-hand side and the zeroed coarse phi), so the fused levels need no exchange launches inside a V-cycle
     WaveArgs a;
     a.p2p = 0; a.my_flag = nullptr; a.epoch = 0;
     bool peer_mode = false;
     int dmask = 0;
-    if (m->distributed) {
-        for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
-        peer_mode = comm_peer_tables(c, L.phi, pre ? m->L[l + 1].phi : nullptr, dmask, a.peer_in, a.peer_cphi, a.peer_flag, &a.my_flag, &a.epoch);
+    // the coarse correction under the fine ghost layers: pushed by the last sweep of the level below if that level is fused, exchanged otherwise
+    // (before this launch takes its epoch: epochs are numbered in launch order)
+    if ((m->push || m->pushk) && pre && l + 1 >= m->nfused) mg_halo_deep(c, m, m->L[l + 1], m->L[l + 1].phi, 2);
+    if (m->distributed) for (int d = 0; d < m->dim; ++d) if (L.mode[d][0] == M_GHOST || L.mode[d][1] == M_GHOST) dmask |= 1 << d;
+    a.wait_ns = nullptr;
+    if (m->push) {
+        const double *arrs[4] = { L.phi, L.res, post == 2 ? m->L[l + 1].rhs : nullptr, post == 2 ? m->L[l + 1].phi : nullptr };
+        peer_mode = comm_peer_tables(c, arrs, 4, dmask, a.peer_delta, a.peer_flag, &a.my_flag, &a.epoch);
         a.p2p = peer_mode ? 1 : 0;
     }
+    VDN_REQUIRE(!m->distributed || peer_mode == m->push, "peer-memory mode of the fused smoother changed between launches");
     auto variant = [&](int cfg) -> const WaveVariant & { return sweep3_get(cfg, pre, post, peer_mode); };
     for (int cfg = 0; cfg < SWEEP_NCFG; ++cfg) {
         if (m->tile_force >= 0 && cfg != m->tile_force) continue;
@@ -660,10 +671,9 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     }
     a.nrm = m->d_norm; a.zchunk = best_ch;
     if (peer_mode) {
-        c->comm_bytes += 8 * comm_halo_volume(c, L.n, m->dim, v.H, dmask);
-        if (pre) c->comm_bytes += 8 * comm_halo_volume(c, m->L[l + 1].n, m->dim, 2, dmask);
-    }
-    if (!peer_mode) {
+        c->comm_bytes += 8 * comm_halo_volume(c, L.n, m->dim, PUSH_DEPTH, dmask);
+        if (post == 2) c->comm_bytes += 2 * 8 * comm_halo_volume(c, m->L[l + 1].n, m->dim, PUSH_DEPTH, dmask);
+    } else if (!m->pushk) {
         if (pre) mg_halo_deep(c, m, m->L[l + 1], m->L[l + 1].phi, 2);   // the prolongation under 3 fine ghost layers reads 2 coarse ones
         mg_halo_deep(c, m, L, L.phi, v.H);      // neighbour-rank cells the tiles relax redundantly
     }
@@ -672,11 +682,23 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     // SURVEY 8(a) a8 per stage: colour half-sweep 40, residual 48, restriction 9, prolongation 17 B/cell
     const double alg = cells * (nsw * 2 * 40.0 + (pre ? 17.0 : 0.0) + (post == 2 ? 48.0 + 9.0 : post == 3 ? 48.0 : 0.0));
     const char *name = l == 0 ? (post == 2 ? "mg_wave_down_l0" : post == 3 ? "mg_wave_up_l0" : pre ? "mg_wave_pro_l0" : "mg_wave_smooth_l0") : "mg_wave_coarse";
+    if (peer_mode && c->d_dbg) a.wait_ns = c->d_dbg + 4 * (l == 0 ? (post == 2 ? 1 : post == 3 ? 3 : pre ? 2 : 0) : 4);
     LaunchScope ls(c, name, alg);
     dim3 grid(cdiv(L.n[0], v.TX), cdiv(L.n[1], v.TY), cdiv(L.n[2], best_ch));
     void *args[] = { (void *)&a };
     VDN_CUDA(cudaLaunchKernel(v.fn, grid, dim3(v.NT), args, v.smem, c->stream));
     std::swap(L.phi, L.res);
+    if (m->pushk) {
+        // A/B hook: the same ghost layers filled by a push kernel after the sweep
+        LaunchScope lp(c, "mg_halo_exchange", 0.0, post == 2 ? 2 : 1);
+        double *a1[1] = { L.phi };
+        comm_push(c, a1, 1, L.off, (int)L.s[1], (int)L.s[2], L.n, m->dim, PUSH_DEPTH, dmask);
+        if (post == 2) {
+            Lev &C = m->L[l + 1];
+            double *a2[2] = { C.rhs, C.phi };
+            comm_push(c, a2, 2, C.off, (int)C.s[1], (int)C.s[2], C.n, m->dim, PUSH_DEPTH, dmask);
+        }
+    }
 }
 
 void mg_capture_coarse(vdn_ctx *c, MG *m, int from_level);
@@ -728,7 +750,7 @@ void vcycle(vdn_ctx *c, MG *m, int l)
                 VDN_CUDA(cudaGraphLaunch(m->coarse_graph, c->stream));
             } else vcycle(c, m, l + 1);
         };
-        if (l > 0) mg_halo_deep(c, m, L, L.rhs, MG_PAD);        // restricted by the level above: valid cells only
+        if (l > 0 && !m->push && !m->pushk) mg_halo_deep(c, m, L, L.rhs, MG_PAD);        // restricted by the level above: valid cells only (peer-memory mode: pushed)
         int rem = c->prm.mg_nu1;
         if (l == 0 && m->first_sweep_done) { --rem; m->first_sweep_done = false; }      // launched ahead by the solve loop
         while (rem > 0) { --rem; wave_launch(c, m, l, 0, rem == 0 ? 2 : 0); }
@@ -843,6 +865,8 @@ int st_mac_solve(vdn_ctx *c, double rel_eps, double abs_eps, int *ncycles, doubl
         VDN_CUDA(cudaStreamSynchronize(c->stream));
         return comm_allreduce_max(c, c->h_pin[0]);
     };
+    // peer-memory mode: the fused launches fill each other's ghost layers; the first one reads what the caller left there (phi = 0: zeros)
+    if ((m->push || m->pushk) && !phi_zero) mg_halo_deep(c, m, m->L[0], m->L[0].phi, PUSH_DEPTH);
     double rn = phi_zero ? bnorm : res_norm();
     int cyc = 0;
     const bool talk = c->prm.mg_verbose && comm_rank(c) == 0;

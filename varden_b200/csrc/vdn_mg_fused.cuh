@@ -25,6 +25,7 @@
 #pragma once
 
 enum : int { M_GHOST = 0, M_NEU = 1, M_DIR = 2, M_WRAP = 3 };
+constexpr int PUSH_DEPTH = 3;          // ghost layers a fused launch may read (H <= 3)
 
 struct WaveArgs {
     int n[3]; long s1, s2, off;
@@ -35,14 +36,20 @@ struct WaveArgs {
     const double *cphi; double *crhs, *czero; long cs1, cs2, coff;   // coarse level (PRE / POST == 2)
     double *nrm;
     int zchunk;
-    // peer-memory mode (levels split across ranks, all arrays in the symmetric heap): the phi planes -- and the coarse correction under them --
-    // of cells that belong to a neighbour rank are read STRAIGHT from that rank's array instead of from a ghost layer filled by a separate
-    // exchange.  peer_in / peer_cphi: base of the same array on the rank at process-grid offset (ox, oy, oz), index (ox+1) + 3 (oy+1) + 9 (oz+1)
-    // ([13] = this rank).  The kernel publishes "my stream has reached launch `epoch`" in its own flag word and the CTAs whose footprint leaves
-    // the rank's region wait for the flags of the neighbours -- interior CTAs start at once, so the wait overlaps with their work.
+    // peer-memory mode (levels split across ranks, all level arrays in the symmetric heap of the peer-memory transport): the kernel PUSHES.
+    // Every value it writes for a cell that lies within PUSH_DEPTH cells of a face shared with another rank -- the new phi, and under POST == 2
+    // the coarse right-hand side and the zeroed coarse phi -- is also stored straight into the ghost layers of the SAME array on the rank(s)
+    // that hold that cell as a ghost (face, edge and corner neighbours: up to 7 copies).  Stores over NVLink are posted (nothing waits for them),
+    // so the exchange of a sweep costs no launch and no exposed latency; the next launch then reads its ghost layers from local memory.
+    // peer_delta[q]: byte distance from this rank's heap to the heap of the rank at process-grid offset (ox, oy, oz), q = (ox+1) + 3 (oy+1) +
+    // 9 (oz+1) -- the heaps have one layout, so local pointer + delta = the same array there.  The kernel publishes "my stream has reached launch
+    // `epoch`" (everything before it is complete) in its own flag word, and the CTAs that read ghost layers or push wait for the flags of the
+    // neighbours: their earlier launches -- which wrote my ghost layers and read the ghost layers I am about to overwrite -- are complete.
+    // Interior CTAs start at once, so the wait overlaps with their work.
     int p2p;
-    const double *peer_in[27], *peer_cphi[27];
+    long peer_delta[27];
     const unsigned long long *peer_flag[27]; unsigned long long *my_flag; unsigned long long epoch;
+    unsigned long long *wait_ns;         // measurement hook (may be null): [0] += ns an edge CTA waited for its first neighbour, [1] = max, [2] += 1
 };
 
 
@@ -82,7 +89,13 @@ __device__ __forceinline__ void sweep_load(SweepCoef &c, const WaveArgs &a, long
     c.dinv = __ldg(a.dinv + g);
 }
 
+#ifndef VDN_EMU
+__device__ __forceinline__ unsigned long long vdn_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 #ifdef VDN_EMU
+inline unsigned long long vdn_globaltimer() { return 0; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T __ldcv(const T *p) { return *p; }
 inline void __threadfence_system() { }
 inline double emu_xor_buf[2048];
@@ -139,17 +152,30 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     }
     const int wyb = ld[0] ? wy[0] : wy[1] - 1;                  // rows of a pair exist together except on the masked outer ring
     const long gofs = a.off + (okx ? wx : 0) + a.s1 * (long)wyb;  // + s1 * row + s2 * plane
-    // peer-memory mode: which rank owns this column (process-grid offset ox, oy) and where it sits in THAT rank's local numbering (the level
-    // sizes are even, so a row pair never straddles a rank boundary)
-    int ox = 0, oy = 0;
+    const long cofs = PRE ? a.coff + ((okx ? wx : 0) >> 1) + a.cs1 * (long)(wyb >> 1) : 0;       // (arithmetic shifts: ghost indices are negative)
+    // peer-memory mode: the ranks (process-grid offsets pox, poy[row]) that hold this column's cells as ghosts.  Fused levels have >= 16 cells
+    // per direction, so a cell is near at most one face of a direction.
+    int pox = 0, poy[2] = { 0, 0 }, cpox = 0, cpoy = 0;
     if (P2P) {
-        if (gx < 0 && mx0 == M_GHOST) ox = -1; else if (gx >= n0 && mx1 == M_GHOST) ox = 1;
-        if (gy0 < 0 && my0 == M_GHOST) oy = -1; else if (gy0 >= n1 && my1 == M_GHOST) oy = 1;
+        if (gx < PUSH_DEPTH && mx0 == M_GHOST) pox = -1; else if (gx >= n0 - PUSH_DEPTH && mx1 == M_GHOST) pox = 1;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { if (gy0 + r < PUSH_DEPTH && my0 == M_GHOST) poy[r] = -1; else if (gy0 + r >= n1 - PUSH_DEPTH && my1 == M_GHOST) poy[r] = 1; }
+        if (POST == 2) {        // the coarse cell under this column
+            if ((gx >> 1) < PUSH_DEPTH && mx0 == M_GHOST) cpox = -1; else if ((gx >> 1) >= (n0 >> 1) - PUSH_DEPTH && mx1 == M_GHOST) cpox = 1;
+            if ((gy0 >> 1) < PUSH_DEPTH && my0 == M_GHOST) cpoy = -1; else if ((gy0 >> 1) >= (n1 >> 1) - PUSH_DEPTH && my1 == M_GHOST) cpoy = 1;
+        }
     }
-    const int wxl = (okx ? wx : 0) - ox * n0, wyl = wyb - oy * n1;
-    const long pofs = a.off + wxl + a.s1 * (long)wyl;
-    const int oxy = (ox + 1) + 3 * (oy + 1);
-    const long cofs = PRE ? a.coff + (wxl >> 1) + a.cs1 * (long)(wyl >> 1) : 0;
+    // store v at element `e` (local numbering of this rank's array `base`) of the same array on every rank that ghosts the cell: the non-empty
+    // subsets of the directions in which the cell is near a shared face.  n?: extent of the array's level in cells (index shift into the peer's numbering)
+    auto push = [&](double *base, long e, long st1, long st2, int e0, int e1, int e2, int ox, int oy, int oz, double v) {
+#pragma unroll
+        for (int m = 1; m < 8; ++m) {
+            const int qx = (m & 1) ? ox : 0, qy = (m & 2) ? oy : 0, qz = (m & 4) ? oz : 0;
+            if (((m & 1) && !ox) || ((m & 2) && !oy) || ((m & 4) && !oz)) continue;
+            double *dst = (double *)((char *)base + a.peer_delta[(qx + 1) + 3 * (qy + 1) + 9 * (qz + 1)]);
+            dst[e - (long)qx * e0 - st1 * (long)(qy * e1) - st2 * (long)(qz * e2)] = v;
+        }
+    };
     const bool anyld = ld[0] || ld[1];
     const bool bndx = (gx == 0 && (mx0 == M_NEU || mx0 == M_DIR)) || (gx == n0 - 1 && (mx1 == M_NEU || mx1 == M_DIR));
     bool bndy[2];
@@ -166,26 +192,10 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     auto fetch = [&](int wz) {
         pf[0] = 0.0; pf[1] = 0.0; pc = 0.0;
         if (wz != WAVE_NONE && anyld) {
-            if (!P2P) {
-                const double *src = a.in + gofs + a.s2 * (long)wz;
-                if (ld[0]) pf[0] = src[0];
-                if (ld[1]) pf[1] = src[a.s1];
-                if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wz >> 1));
-            } else {
-                int oz = 0;
-                if (wz < 0 && mz0 == M_GHOST) oz = -1; else if (wz >= n2 && mz1 == M_GHOST) oz = 1;
-                const int wzl = wz - oz * n2, who = oxy + 9 * (oz + 1);
-                const double *src = a.peer_in[who] + pofs + a.s2 * (long)wzl;
-                if (who == 13) {
-                    if (ld[0]) pf[0] = src[0];
-                    if (ld[1]) pf[1] = src[a.s1];
-                    if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wzl >> 1));
-                } else {                                   // another rank's memory: never through a stale L1 line
-                    if (ld[0]) pf[0] = __ldcv(src);
-                    if (ld[1]) pf[1] = __ldcv(src + a.s1);
-                    if (PRE) pc = __ldcv(a.peer_cphi[who] + cofs + a.cs2 * (long)(wzl >> 1));
-                }
-            }
+            const double *src = a.in + gofs + a.s2 * (long)wz;      // ghost layers included (M_GHOST: filled by the neighbours' pushes / an exchange)
+            if (ld[0]) pf[0] = src[0];
+            if (ld[1]) pf[1] = src[a.s1];
+            if (PRE) pc = __ldg(a.cphi + cofs + a.cs2 * (long)(wz >> 1));
         }
     };
     auto stash = [&](int o) {
@@ -225,15 +235,21 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
 #pragma unroll
     for (int k = 0; k < S + 3 + E; ++k) wzq[k] = zidx(tfirst + 1 - k);
     if (P2P && a.my_flag) {
-        // everything this rank's stream produced before this launch is complete: publish it; CTAs that read a neighbour's cells wait until
-        // the neighbours have published the same launch (their producing kernels are complete as well)
+        // everything this rank's stream produced before this launch is complete: publish it; CTAs that read ghost layers or push wait until
+        // the neighbours have published the same launch (their earlier launches are complete as well)
         if (tid == 0) { __threadfence_system(); *(volatile unsigned long long *)a.my_flag = a.epoch; }
-        const bool edge = (x0 - H < 0 && mx0 == M_GHOST) || (x0 + TX + H > n0 && mx1 == M_GHOST) || (y0 - H < 0 && my0 == M_GHOST) ||
-                          (y0 + TY + H > n1 && my1 == M_GHOST) || (z0 - H < 0 && mz0 == M_GHOST) || (z1 + H > n2 && mz1 == M_GHOST);
+        constexpr int MG = 2 * PUSH_DEPTH;          // footprint of what the CTA reads (H) or pushes (fine cells over PUSH_DEPTH coarse cells)
+        const bool edge = (x0 - MG < 0 && mx0 == M_GHOST) || (x0 + TX + MG > n0 && mx1 == M_GHOST) || (y0 - MG < 0 && my0 == M_GHOST) ||
+                          (y0 + TY + MG > n1 && my1 == M_GHOST) || (z0 - MG < 0 && mz0 == M_GHOST) || (z1 + MG > n2 && mz1 == M_GHOST);
         if (edge && tid < 27 && a.peer_flag[tid]) {
             const volatile unsigned long long *f = (const volatile unsigned long long *)a.peer_flag[tid];
+            const unsigned long long t0 = a.wait_ns ? vdn_globaltimer() : 0ull;
             while (*f < a.epoch) { }
             __threadfence_system();
+            if (a.wait_ns) {
+                const unsigned long long dt = vdn_globaltimer() - t0;
+                atomicAdd(a.wait_ns, dt); atomicMax(a.wait_ns + 1, dt); atomicAdd(a.wait_ns + 2, 1ull);
+            }
         }
         __syncthreads();
     }
@@ -291,9 +307,15 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
         {
             const int r1 = t - S + 1;
             if (core && r1 >= z0 && r1 < z1) {
-                double *dst = a.out + gofs + a.s2 * (long)r1;
-                dst[0] = sm[oP[S] + sid];
-                dst[a.s1] = sm[oP[S] + sid + X];
+                const long e = gofs + a.s2 * (long)r1;
+                const double v0 = sm[oP[S] + sid], v1 = sm[oP[S] + sid + X];
+                a.out[e] = v0;
+                a.out[e + a.s1] = v1;
+                if (P2P) {
+                    const int poz = (r1 < PUSH_DEPTH && mz0 == M_GHOST) ? -1 : (r1 >= n2 - PUSH_DEPTH && mz1 == M_GHOST) ? 1 : 0;
+                    if (pox | poy[0] | poz) push(a.out, e, a.s1, a.s2, n0, n1, n2, pox, poy[0], poz, v0);
+                    if (pox | poy[1] | poz) push(a.out, e + a.s1, a.s1, a.s2, n0, n1, n2, pox, poy[1], poz, v1);
+                }
             }
         }
         // ---- residual of plane t-S: red cells only (the black ones were just relaxed) ----
@@ -314,8 +336,17 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
                     if ((r0 & 1) == 0) acc = s2;
                     else if ((gx & 1) == 0) {
                         const long cc = a.coff + (gx >> 1) + a.cs1 * (long)(gy0 >> 1) + a.cs2 * (long)(r0 >> 1);
-                        a.crhs[cc] = (acc + s2) * 0.125;
+                        const double cr = (acc + s2) * 0.125;
+                        a.crhs[cc] = cr;
                         a.czero[cc] = 0.0;
+                        if (P2P) {
+                            const int cz = r0 >> 1;
+                            const int cpoz = (cz < PUSH_DEPTH && mz0 == M_GHOST) ? -1 : (cz >= (n2 >> 1) - PUSH_DEPTH && mz1 == M_GHOST) ? 1 : 0;
+                            if (cpox | cpoy | cpoz) {
+                                push(a.crhs, cc, a.cs1, a.cs2, n0 >> 1, n1 >> 1, n2 >> 1, cpox, cpoy, cpoz, cr);
+                                push(a.czero, cc, a.cs1, a.cs2, n0 >> 1, n1 >> 1, n2 >> 1, cpox, cpoy, cpoz, 0.0);
+                            }
+                        }
                     }
                 }
             }

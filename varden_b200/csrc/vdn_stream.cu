@@ -223,6 +223,26 @@ Range valid_range(const vdn_ctx *c, int fdir)
 
 } // namespace
 
+// host box (flat on the device, Fortran order with its own ghost width) <-> region array: vdn_ctx.cu box_copy
+__global__ void k_box_copy(BoxCopyArgs a)
+{
+    const long per = (long)a.n[0] * a.n[1] * a.n[2], tot = per * a.ncomp;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int comp = (int)(t / per); const long r = t - (long)comp * per;
+        const int i = (int)(r % a.n[0]), j = (int)((r / a.n[0]) % a.n[1]), k = (int)(r / ((long)a.n[0] * a.n[1]));
+        const long h = (a.hofs[0] + i) + (long)a.hext[0] * ((a.hofs[1] + j) + (long)a.hext[1] * ((a.hofs[2] + k) + (long)a.hext[2] * comp));
+        const long d = (long)comp * a.cs + (a.dofs[0] + i) + (long)a.dext0 * ((a.dofs[1] + j) + (long)a.dext1 * (a.dofs[2] + k));
+        if (a.upload) a.base[d] = a.stage[h]; else a.stage[h] = a.base[d];
+    }
+}
+void st_box_copy(const BoxCopyArgs &a, cudaStream_t stream)
+{
+    const long tot = (long)a.n[0] * a.n[1] * a.n[2] * a.ncomp;
+    if (tot <= 0) return;
+    k_box_copy<<<(unsigned)std::min<long>(148 * 16, (tot + 255) / 256), 256, 0, stream>>>(a);
+    VDN_CUDA(cudaGetLastError());
+}
+
 void st_setval(vdn_ctx *c, int field, double val)
 {
     if (field >= VDN_UMAC_X && field <= VDN_UMAC_Z) ++c->umac_epoch;
