@@ -147,6 +147,16 @@ int vdn_update(vdn_ctx *ctx, int is_vel, double dt);
 /* make_at_halftime (make_at_halftime.f90:18): RHOHALF = 0.5*(SOLD_1 + SNEW_1) + ghost fill */
 int vdn_make_at_halftime(vdn_ctx *ctx);
 
+/* ---- the driver's per-step glue around the path, on the resident fields ----
+ * estdt (estdt.f90:15-87, per-box kernels :89-181): dt for the coming step from UOLD, SOLD (density), GP and EXT_VEL_FORCE -- the advective
+ * limit dx/max|u|, the forcing limit sqrt(2 dx / max|gp/rho - f|) (each only above the reference's single-precision eps 1.0e-8), min(dx) when
+ * nothing limits, times cflfac, capped by max_dt_growth * dtold when dtold > 0.  Reduced over all ranks (the reference's parallel_reduce). */
+int vdn_estdt(vdn_ctx *ctx, double dtold, double cflfac, double max_dt_growth, double *dt);
+/* multifab_copy_c of a whole field on the device, ghost cells included (varden.f90:321-324: uold <- unew, sold <- snew); both fields must
+ * have the same layout.  With vdn_fill_and_physbc (varden.f90:291-300) this keeps a run resident between steps wherever the Fortran driver
+ * does not need the host copy. */
+int vdn_field_copy(vdn_ctx *ctx, int dst_field, int src_field);
+
 /* The whole device-resident path advance_timestep.f90:95-124:
  * advance_premac -> macproject -> scalar_advance -> make_at_halftime -> velocity_advance. */
 int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, double *mac_resnorm);

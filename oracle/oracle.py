@@ -369,6 +369,20 @@ def mk_mac_coeffs(geom, rho, ng_r, beta):
                                 _dp(rho[ib]), C.c_int(ng_r), _ia(lo), _ia(hi), C.c_int(dim))
 
 
+def estdt(geom, u, ng_u, s, ng_s, gp, ng_g, ext_vel_force, ng_f, dtold=-1.0, cflfac=0.5, max_dt_growth=1.1):
+    """estdt.f90:15-87: dt for the next step from the new velocity, density, grad(p) and the external force (probin defaults: cflfac 0.5,
+    max_dt_growth 1.1, src/_parameters)"""
+    dim = geom.dim
+    nb = geom.nboxes
+    blo = (C.c_int * (3 * nb))(*[int(x) for lo, hi in geom.boxes for x in list(lo) + [0] * (3 - len(lo))])
+    bhi = (C.c_int * (3 * nb))(*[int(x) for lo, hi in geom.boxes for x in list(hi) + [0] * (3 - len(hi))])
+    dx = (C.c_double * 3)(*(list(geom.dx) + [1.0] * (3 - len(geom.dx))))
+    f = lib().orc_estdt_mf
+    f.restype = C.c_double
+    return f(_pp(u), C.c_int(ng_u), _pp(s), C.c_int(ng_s), _pp(gp), C.c_int(ng_g), _pp(ext_vel_force), C.c_int(ng_f), blo, bhi, C.c_int(nb),
+             C.c_int(dim), dx, C.c_double(dtold), C.c_double(cflfac), C.c_double(max_dt_growth))
+
+
 def project_with_phi(geom, params, umac_pred, rho, ncomp_s, phi):
     """mk_mac_coeffs + mkumac + fill_boundary(umac) for a GIVEN phi (whose ghost cells get filled here); returns umac."""
     dim = geom.dim

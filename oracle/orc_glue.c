@@ -272,3 +272,50 @@ void orc_make_at_halftime(double *rh_, const double *ro_, const double *rn_, con
     for (int i = lo[0]; i <= hi[0]; ++i)
         AT(rh,i,j,k,0) = HALF * (AT(ro,i,j,k,0) + AT(rn,i,j,k,0));
 }
+
+/* estdt_3d / estdt_2d  (src/estdt.f90:131-181, :89-129): per-box time-step estimate.  dt (in/out) is lowered by the advective limit
+ * dx/max|u_d| and the forcing limit sqrt(2 dx / max|gp_d/rho - f_d|) of every direction whose maximum exceeds eps = 1.0e-8 (a
+ * single-precision literal in the reference).  s is the first scalar (density) only. */
+void orc_estdt(const double *vel_, int ng_u, const double *s_, int ng_s, const double *gp_, int ng_g, const double *f_, int ng_f,
+               const int *lo, const int *hi, int dim, const double *dx, double *dt)
+{
+    V vel = v_box((double*)vel_, lo, hi, ng_u, -1, dim, dim);
+    V s = v_box((double*)s_, lo, hi, ng_s, -1, 1, dim);
+    V gp = v_box((double*)gp_, lo, hi, ng_g, -1, dim, dim);
+    V f = v_box((double*)f_, lo, hi, ng_f, -1, dim, dim);
+    const int k0 = dim == 3 ? lo[2] : 0, k1 = dim == 3 ? hi[2] : 0;
+    const double eps = (double)1.0e-8f;
+    double um[3] = { 0.0, 0.0, 0.0 }, fm[3] = { 0.0, 0.0, 0.0 };
+    for (int k = k0; k <= k1; ++k)
+    for (int j = lo[1]; j <= hi[1]; ++j)
+    for (int i = lo[0]; i <= hi[0]; ++i)
+        for (int d = 0; d < dim; ++d) {
+            um[d] = dmax(um[d], fabs(AT(vel, i, j, k, d)));
+            fm[d] = dmax(fm[d], fabs(AT(gp, i, j, k, d) / AT(s, i, j, k, 0) - AT(f, i, j, k, d)));
+        }
+    /* the reference applies all velocity limits first, then the forcing limits (min is order-independent) */
+    for (int d = 0; d < dim; ++d) if (um[d] > eps) *dt = dmin(*dt, dx[d] / um[d]);
+    for (int d = 0; d < dim; ++d) if (fm[d] > eps) *dt = dmin(*dt, sqrt(2.0 * dx[d] / fm[d]));
+}
+
+/* estdt (src/estdt.f90:15-87): min over the boxes (and, in the reference, over the MPI ranks), the fallback min(dx) when nothing limits,
+ * the CFL factor and the growth limit.  u / s / gp / f: one array per box. */
+double orc_estdt_mf(const double *const *u, int ng_u, const double *const *s, int ng_s, const double *const *gp, int ng_g,
+                    const double *const *f, int ng_f, const int *boxes_lo, const int *boxes_hi, int nboxes, int dim, const double *dx,
+                    double dtold, double cflfac, double max_dt_growth)
+{
+    const double dt_start = 1.e20;
+    double dt = 1.e20;
+    for (int b = 0; b < nboxes; ++b) {
+        double dt_grid = 1.e20;
+        orc_estdt(u[b], ng_u, s[b], ng_s, gp[b], ng_g, f[b], ng_f, boxes_lo + 3 * b, boxes_hi + 3 * b, dim, dx, &dt_grid);
+        dt = dmin(dt_grid, dt);
+    }
+    if (dt == dt_start) {
+        dt = dmin(dx[0], dx[1]);
+        if (dim == 3) dt = dmin(dt, dx[2]);
+    }
+    dt = dt * cflfac;
+    if (dtold > 0.0) dt = dmin(dt, max_dt_growth * dtold);
+    return dt;
+}

@@ -83,11 +83,14 @@ def call(name, *args):
     _, sig = _sigs[name]
     if len(args) != len(sig):
         raise TypeError("%s takes %d arguments (%s), got %d" % (name, len(sig), " ".join(s[0] for s in sig), len(args)))
-    keep, cargs = [], []
+    keep, cargs, ios = [], [], []
     for a, (an, typ, rank) in zip(args, sig):
         rank = int(rank)
         if rank:
             cargs.append(C.byref(_desc(a, typ, rank, keep)))
+        elif typ == "realio":                   # intent(inout) / intent(out) real scalar: by address, value returned
+            ios.append(C.c_double(float(a)))
+            cargs.append(C.byref(ios[-1]))
         elif typ == "real":
             cargs.append(C.c_double(float(a)))
         else:
@@ -96,6 +99,7 @@ def call(name, *args):
     getattr(L, "ref_" + name)(*cargs)
     if C.c_int.in_dll(L, "ref_error_flag").value:
         raise RuntimeError("reference routine %s called bl_error" % name)
+    return [x.value for x in ios]
 
 
 def set_probin(params):
@@ -310,6 +314,23 @@ def make_at_halftime(geom, params, rhohalf, sold, snew):
         lo, hi = _lohi(geom, ib)
         call("make_at_halftime_%dd" % dm, _c1(rhohalf[ib], dm), _c1(sold[ib], dm), _c1(snew[ib], dm), lo, hi, 1, 3)
     restrict_and_fill(geom, params, rhohalf, 1, 1, 1, dm + 1, 1)
+
+
+def estdt(geom, u, ng_u, s, ng_s, gp, ng_g, ext_vel_force, ng_f, dtold=-1.0, cflfac=0.5, max_dt_growth=1.1):
+    """estdt.f90:15-87 around the reference's own estdt_2d / estdt_3d (:89-181)"""
+    dm = geom.dim
+    dt = dt_start = 1.e20
+    for ib in range(geom.nboxes):
+        lo, hi = _lohi(geom, ib)
+        (dt_grid,) = call("estdt_%dd" % dm, _c(u[ib], dm), ng_u, _c1(s[ib], dm), ng_s, _c(gp[ib], dm), ng_g, _c(ext_vel_force[ib], dm), ng_f,
+                          lo, hi, _dx(geom), 1.e20)
+        dt = min(dt_grid, dt)
+    if dt == dt_start:
+        dt = min(_dx(geom)[:dm])
+    dt = dt * cflfac
+    if dtold > 0.0:
+        dt = min(dt, max_dt_growth * dtold)
+    return dt
 
 
 def divumac(geom, umac, mac_rhs, rh):

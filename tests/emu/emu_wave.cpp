@@ -19,7 +19,7 @@ extern "C" int emu_sweep3_p2p(int nsw, int pre, int post, int cfg, const int *n,
     if (nsw != 1) return 1;
     WaveArgs a;
     memset(&a, 0, sizeof a);
-    if (peer_delta) { a.p2p = 1; for (int q = 0; q < 27; ++q) a.peer_delta[q] = peer_delta[q]; }
+    if (peer_delta) { a.p2p = 1; for (int q = 0; q < 27; ++q) { a.peer_delta[q] = peer_delta[q]; if (peer_delta[q] != 0) a.peer_mask |= 1u << q; } }
     for (int d = 0; d < 3; ++d) { a.n[d] = n[d]; a.h2[d] = h2[d]; a.mode[d][0] = mode[2 * d]; a.mode[d][1] = mode[2 * d + 1]; }
     a.s1 = n[0] + 2 * pad; a.s2 = (long)(n[0] + 2 * pad) * (n[1] + 2 * pad); a.off = pad * (1 + a.s1 + a.s2); a.par0 = par0;
     a.rhs = rhs; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.dinv = dinv; a.in = in; a.out = out;

@@ -40,6 +40,11 @@ def main():
         geom, P, st, dt = O.random_state(n, dim=3, max_grid_size=n // 2, phys_bc=[[IN, OUT], [PER, PER], [NS, W]], seed=7)
     elif args.case == "per3d":
         geom, P, st, dt = O.random_state(n, dim=3, max_grid_size=n // 2, phys_bc=[[PER, PER]] * 3, seed=8)
+    elif args.case == "randx3d":
+        # boxes 2 x 1 x 1 (x 2 x 1 at 4 ranks): the process grid splits x FIRST -- inflow / outflow boundaries on a direction that is split
+        # between ranks, which the z-then-y-then-x fill of the cubic cases only reaches at 8 ranks
+        geom, P, st, dt = O.random_state([n, n // 2 * (2 if world >= 4 else 1), n // 2], dim=3, max_grid_size=n // 2,
+                                         phys_bc=[[IN, OUT], [PER, PER], [NS, W]], seed=9)
     elif args.case == "rt2d":
         geom, P, st, dt = O.rt_state(n, dim=2, max_grid_size=n // 2)
     else:

@@ -168,3 +168,33 @@ def test_config1_bubble_2d():
         state = dict(state, uold=ref["unew"], sold=ref["snew"])
     ctx.close()
     assert worst <= 1e-10
+
+
+@pytest.mark.parametrize("case", ["rt3d_8box", "rand3d_inout", "rand2d_4box", "tiny_velocities"])
+def test_estdt_on_device_bit_exact(case):
+    """estdt (estdt.f90:15-181) on the resident fields equals the oracle's dt (itself bit-identical to the reference's own
+    estdt_2d / estdt_3d, tests/test_ref_pin.py) bit for bit -- the maxima are exact, the limits are computed in the reference's order;
+    then the driver's uold <- unew copy (varden.f90:321-324) on the device."""
+    if case == "rt3d_8box":
+        geom, P, st, dt = O.rt_state(32, dim=3, max_grid_size=16)
+    elif case == "rand3d_inout":
+        geom, P, st, dt = O.random_state([24, 16, 20], dim=3, max_grid_size=12, phys_bc=[[IN, OUT], [PER, PER], [NS, W]], seed=21)
+    elif case == "rand2d_4box":
+        geom, P, st, dt = O.random_state([32, 32], dim=2, max_grid_size=16, phys_bc=[[NS, NS], [IN, OUT]], seed=22)
+    else:
+        geom, P, st, dt = O.random_state([16, 16, 16], dim=3, max_grid_size=16, phys_bc=[[W, W]] * 3, seed=23)
+        for k in ("uold", "gp", "ext_vel_force"):
+            st[k] = [a * 1e-12 for a in st[k]]              # everything below the reference's eps: the min(dx) fallback
+    ctx = make_ctx(geom, P)
+    upload_state(ctx, geom, P, st)
+    for dtold in (-1.0, 1e-4):
+        want = O.estdt(geom, st["uold"], 3, st["sold"], 3, st["gp"], 1, st["ext_vel_force"], 1, dtold=dtold)
+        got = ctx.estdt(dtold=dtold)
+        assert got == want, (case, dtold, got, want)
+    ctx.advance(dt)
+    ctx.field_copy("UOLD", "UNEW")
+    unew = download_like(ctx, geom, "UNEW", st["uold"], 3, geom.dim)
+    uold = download_like(ctx, geom, "UOLD", st["uold"], 3, geom.dim)
+    for a, b in zip(unew, uold):
+        assert np.array_equal(a, b)
+    ctx.close()

@@ -35,6 +35,7 @@ def plan(lib, pgrid, pcoord, periodic, n, ng, dmask):
 @pytest.mark.parametrize("pgrid,periodic", [
     ((2, 2, 2), (1, 1, 1)),      # 8 GPUs, all periodic: every diagonal neighbour is the same rank for several offsets
     ((2, 2, 2), (1, 1, 0)),      # bench.py --gpus 8: periodic x,y, walls in z
+    ((2, 2, 2), (0, 1, 0)),      # the rand3d multi-GPU case at 8 ranks: inflow / outflow x, periodic y, walls z
     ((1, 2, 2), (1, 1, 0)),      # bench.py --gpus 4
     ((1, 1, 2), (1, 1, 0)),      # bench.py --gpus 2
     ((1, 1, 2), (1, 1, 1)),      # two ranks along a periodic direction: lo and hi neighbour are the same rank
@@ -64,8 +65,9 @@ def test_single_phase_plan_fills_every_ghost_cell(pgrid, periodic, ng):
         for k in range(n[2] + 1):
             for j in range(n[1] + 1):
                 for i in range(n[0] + 1):
-                    # a rank knows its own cells, and index n only along the directions that are not split
-                    if all(idx < n[d] or (pgrid[d] == 1 and idx == n[d]) for d, idx in enumerate((i, j, k))):
+                    # a rank knows its own cells, and index n (the high-face coefficient) along the directions where no neighbour rank holds it:
+                    # not split, or split with this rank at the physical high end of the domain
+                    if all(idx < n[d] or (idx == n[d] and (pgrid[d] == 1 or (pc[d] == pgrid[d] - 1 and not periodic[d]))) for d, idx in enumerate((i, j, k))):
                         a[k + PAD, j + PAD, i + PAD] = gval(pc[0] * n[0] + i, pc[1] * n[1] + j, pc[2] * n[2] + k)
         loc[r] = a
     plans = {r: plan(lib, pgrid, ranks[r], periodic, n, ng, dmask) for r in range(len(ranks))}
@@ -87,7 +89,7 @@ def test_single_phase_plan_fills_every_ghost_cell(pgrid, periodic, ng):
         for d in range(3):
             if pgrid[d] > 1:
                 lo = -ng if (pc[d] > 0 or periodic[d]) else 0
-                hi = n[d] + ng if (pc[d] < pgrid[d] - 1 or periodic[d]) else n[d]
+                hi = n[d] + ng if (pc[d] < pgrid[d] - 1 or periodic[d]) else n[d] + 1      # physical high end: index n (the boundary face) included
             else:
                 lo, hi = 0, n[d] + 1
             rng.append(range(lo, hi))
@@ -117,6 +119,7 @@ def plan_ex(lib, pgrid, pcoord, periodic, n, ng, dmask, nodal, carry_n):
 
 @pytest.mark.parametrize("pgrid,periodic", [
     ((2, 2, 2), (1, 1, 0)),      # bench.py --gpus 8
+    ((2, 2, 2), (0, 1, 0)),      # rand3d at 8 ranks
     ((1, 2, 2), (1, 1, 0)),      # bench.py --gpus 4
     ((1, 1, 2), (1, 1, 1)),      # lo and hi neighbour are the same rank
     ((2, 2, 2), (1, 1, 1)),

@@ -14,7 +14,7 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("case,n", [("rt3d", 64), ("rand3d", 32), ("per3d", 32), ("rt2d", 64)])
+@pytest.mark.parametrize("case,n", [("rt3d", 64), ("rand3d", 32), ("per3d", 32), ("randx3d", 32), ("rt2d", 64)])
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("smoother", ["plain", "fused", "fused_nccl", "fused_pull", "fused_pushk"])
 def test_multi_gpu_parity(case, n, world, smoother):
@@ -25,6 +25,8 @@ def test_multi_gpu_parity(case, n, world, smoother):
         pytest.skip("needs %d GPUs" % world)
     if case == "rt2d" and (world == 8 or smoother != "plain"):
         pytest.skip("2-D: 4 boxes, plain kernels only")
+    if case == "randx3d" and world == 8:
+        pytest.skip("x-first split: 2 and 4 ranks (8 ranks split x in the cubic cases)")
     env = dict(os.environ)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--case", case, "--size", str(n),

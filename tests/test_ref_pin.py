@@ -124,3 +124,21 @@ def test_physbc_all_types_bitwise():
                                C.c_int(ng), bc3.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(icomp),
                                P.bcval.ctypes.data_as(C.POINTER(C.c_double)))
             assert np.array_equal(a, b), (dim, trial, bc.tolist(), ng, icomp)
+
+
+@pytest.mark.parametrize("name", ["3d_slip_8box", "3d_inout_mix", "3d_aniso_boxes", "2d_walls", "2d_inout"])
+@pytest.mark.parametrize("scale", [1.0, 1e-12])
+def test_estdt_bit_identical(name, scale):
+    """estdt_2d / estdt_3d (estdt.f90:89-181) per box and the driver's min / fallback / cflfac / growth limit (estdt.f90:15-87): the oracle's
+    dt equals the reference routines' dt bit for bit.  scale = 1e-12 pushes every maximum below the reference's single-precision eps = 1.0e-8,
+    which exercises the "nothing limits the step" fallback dt = min(dx)."""
+    geom, P, st, dt = _case(name)
+    u = [a * scale for a in st["uold"]]
+    gp = [a * scale for a in st["gp"]]
+    f = [a * scale for a in st["ext_vel_force"]]
+    for dtold in (-1.0, 1e-4):
+        a = O.estdt(geom, u, 3, st["sold"], 3, gp, 1, f, 1, dtold=dtold)
+        b = R.estdt(geom, u, 3, st["sold"], 3, gp, 1, f, 1, dtold=dtold)
+        assert a == b, (name, scale, dtold, a, b)
+    if scale < 1e-8:
+        assert O.estdt(geom, u, 3, st["sold"], 3, gp, 1, f, 1) == 0.5 * min(geom.dx[:geom.dim])

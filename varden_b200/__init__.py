@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
     "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune", "vdn_device_count", "vdn_comm_bytes",
-    "vdn_debug_counters",
+    "vdn_debug_counters", "vdn_estdt", "vdn_field_copy",
 ]
 
 
@@ -212,6 +212,16 @@ class Context:
         n, r = C.c_int(0), C.c_double(0.0)
         self._chk(self.lib.vdn_mac_solve(self.h, C.c_double(rel_eps), C.c_double(abs_eps), C.byref(n), C.byref(r)))
         return n.value, r.value
+
+    def estdt(self, dtold=-1.0, cflfac=0.5, max_dt_growth=1.1):
+        """estdt.f90:15-87 on the resident UOLD / SOLD / GP / EXT_VEL_FORCE (probin defaults cflfac 0.5, max_dt_growth 1.1)"""
+        dt = C.c_double(0.0)
+        self._chk(self.lib.vdn_estdt(self.h, C.c_double(dtold), C.c_double(cflfac), C.c_double(max_dt_growth), C.byref(dt)))
+        return dt.value
+
+    def field_copy(self, dst, src):
+        """dst <- src on the device, ghost cells included (varden.f90:321-324)"""
+        self._chk(self.lib.vdn_field_copy(self.h, F[dst], F[src]))
 
     def comm_tune(self, mode):
         """measurement hook, before set_comm: transport of the ghost exchanges -- 0 peer memory with the fused sweeps pushing their boundary results

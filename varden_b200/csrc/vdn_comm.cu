@@ -133,8 +133,9 @@ static void ensure_buf(vdn_ctx *c, size_t doubles)
 //   pgrid / pcoord: process grid and this rank's coordinates; periodic[d]: the domain is periodic along d;
 //   coord2rank[x + pgrid[0]*(y + pgrid[1]*z)]: rank at those coordinates; n: local cells; ng: ghost layers to fill;
 //   dmask: split directions to exchange; nodal: direction in which the array is face-centred (-1: cell-centred);
-//   carry_n: multigrid level arrays -- along a direction that is NOT split a slab also carries index n (they keep the coefficient of the
-//            high boundary / periodic-seam face there, and the ghost planes are relaxed with it).
+//   carry_n: multigrid level arrays -- along a direction that is NOT split, or that is split with this rank at the physical high end of the
+//            domain, a slab also carries index n (they keep the coefficient of the high boundary / periodic-seam face there, and the ghost
+//            planes are relaxed with it: a Dirichlet face uses its coefficient).
 // Outputs (up to 26 entries each, in ISSUE order): peer rank, inclusive-lo / extent boxes (local indices) of what is sent and of the ghost
 // region that is received, and for a received box the index shift into the PEER's local numbering (peer index = my index + shift).
 // NCCL matches the messages of a pair of ranks first-in first-out: sends are issued in lexicographic order of the neighbour offset o and
@@ -176,7 +177,10 @@ static int halo_plan_core(int dim, const int *pgrid, const int *pcoord, const in
                 if (d >= dim) { lo[d] = 0; ext[d] = 1; continue; }
                 const int nod = (d == nodal) ? 1 : 0;
                 const bool split = ((dmask >> d) & 1) && pgrid[d] > 1;
-                if (o[d] == 0) { lo[d] = 0; ext[d] = n[d] + nod + ((carry_n && !split) ? 1 : 0); }
+                // index n travels along a direction where no neighbour rank supplies it: not split, or split with this rank at the physical
+                // high end (the peer of a transverse message sits at the same coordinate, so both sides agree on the extent)
+                const bool hi_end = split && pcoord[d] == pgrid[d] - 1 && !periodic[d];
+                if (o[d] == 0) { lo[d] = 0; ext[d] = n[d] + nod + ((carry_n && (!split || hi_end)) ? 1 : 0); }
                 else if (pass == 0) { lo[d] = o[d] < 0 ? nod : n[d] - ng; ext[d] = ng; sh[d] = -o[d] * n[d]; }   // my cells / faces next to that neighbour (its ghosts)
                 else                { lo[d] = o[d] < 0 ? -ng : n[d] + nod; ext[d] = ng; sh[d] = -o[d] * n[d]; }   // my ghosts on that side
             }
@@ -427,14 +431,16 @@ long comm_halo_volume(vdn_ctx *c, const int *n, int dim, int ng, int dmask)
 // (one layout on every rank: local pointer + distance = the same array there) and its flag word; this rank's flag word and the epoch of this
 // launch (one epoch per exchange-like event, the same sequence on every rank).  arrs: the arrays the kernel will push (all must live in the heap).
 // dmask: split directions of the level.  Returns false when the peer-memory transport is not available for these arrays.
-bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask, long *delta27,
-                      const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch)
+constexpr int HDR_REACHED = 64;         // heap header words HDR_REACHED + r: "rank r's stream has reached epoch e", stored there BY rank r
+bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask, long *delta27, unsigned *mask27,
+                      unsigned long long **pub27, const unsigned long long **wait27, unsigned long long **mine, unsigned long long *epoch)
 {
     Comm *cm = c->comm;
     if (!cm) return false;
     for (int q = 0; q < narr; ++q) if (arrs[q] && !in_heap(cm, arrs[q])) return false;
+    *mask27 = 0;
     for (int q = 0; q < 27; ++q) {
-        delta27[q] = 0; f27[q] = nullptr;
+        delta27[q] = 0; pub27[q] = nullptr; wait27[q] = nullptr;
         const int o[3] = { q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1 };
         int pc[3]; bool ok = true;
         for (int d = 0; d < 3; ++d) {
@@ -449,7 +455,11 @@ bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask
         if (!ok) continue;
         const int r = cm->coord2rank[pc[0] + cm->pgrid[0] * (pc[1] + cm->pgrid[1] * pc[2])];
         delta27[q] = (long)(cm->peer_base[r] - cm->heap);
-        if (r != cm->rank) f27[q] = (const unsigned long long *)cm->peer_base[r];
+        if (q != 13) *mask27 |= 1u << q;
+        if (r != cm->rank) {
+            pub27[q] = (unsigned long long *)cm->peer_base[r] + HDR_REACHED + cm->rank;
+            wait27[q] = (const unsigned long long *)cm->heap + HDR_REACHED + r;
+        }
     }
     *mine = (unsigned long long *)cm->heap;
     *epoch = ++cm->epoch;
@@ -621,7 +631,7 @@ static void p2p_setup(vdn_ctx *c)
     }
     cm->heap = heap; cm->heap_bytes = need; cm->heap_used = HEAP_RESERVED; cm->peer_base = peer; cm->p2p = true;
     VDN_CUDA(cudaMemsetAsync(heap, 0, HEAP_RESERVED, c->stream));
-    VDN_REQUIRE(8 * (size_t)(1 + cm->nranks) <= HEAP_RESERVED, "too many ranks for the heap header");
+    VDN_REQUIRE(cm->nranks <= 32 && 8 * (size_t)(HDR_REACHED + cm->nranks) <= HEAP_RESERVED, "too many ranks for the heap header");
     VDN_CUDA(cudaMalloc(&cm->d_push_ctr, 64)); VDN_CUDA(cudaMemsetAsync(cm->d_push_ctr, 0, 64, c->stream));
     VDN_CUDA(cudaMalloc(&cm->d_peer_base, sizeof(char *) * cm->nranks));
     VDN_CUDA(cudaMemcpyAsync(cm->d_peer_base, peer.data(), sizeof(char *) * cm->nranks, cudaMemcpyHostToDevice, c->stream));

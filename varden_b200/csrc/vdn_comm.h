@@ -16,8 +16,8 @@ bool comm_has_neighbor(const vdn_ctx *c, int d, int s);
 void comm_allgather(vdn_ctx *c, const double *send, double *recv, size_t count);
 void comm_coord_of(const vdn_ctx *c, int r, int *pc);
 // peer-memory tables for kernels that write into neighbour ranks' arrays themselves (see vdn_comm.cu); false: not available (NCCL transport)
-bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask, long *delta27,
-                      const unsigned long long **f27, unsigned long long **mine, unsigned long long *epoch);
+bool comm_peer_tables(vdn_ctx *c, const double *const *arrs, int narr, int dmask, long *delta27, unsigned *mask27,
+                      unsigned long long **pub27, const unsigned long long **wait27, unsigned long long **mine, unsigned long long *epoch);
 int comm_mg_xchg(const vdn_ctx *c);                         // exchange style of the fused multigrid levels (vdn_ctx.h: comm_mode)
 // push form of comm_halo for up to 3 level arrays of one level (peer-memory transport): boundary layers stored into the neighbours' ghost layers
 void comm_push(vdn_ctx *c, double *const *arrs, int narr, long off, int sy, int sz, const int *n, int dim, int ng, int dmask);

@@ -505,6 +505,13 @@ static void advance_host_impl(vdn_ctx *c, double dt, double mac_rel_eps, const v
 int vdn_advance_host(vdn_ctx *ctx, double dt, double mac_rel_eps, const vdn_host_state *hs, int *mac_cycles, double *mac_resnorm)
 { VDN_TRY(ctx, advance_host_impl(ctx, dt, mac_rel_eps, hs, mac_cycles, mac_resnorm)) }
 
+int vdn_estdt(vdn_ctx *ctx, double dtold, double cflfac, double max_dt_growth, double *dt)
+{ VDN_TRY(ctx, { ctx_require_comm(ctx); VDN_REQUIRE(dt != nullptr, "dt is null"); *dt = st_estdt(ctx, dtold, cflfac, max_dt_growth); }) }
+
+int vdn_field_copy(vdn_ctx *ctx, int dst_field, int src_field)
+{ VDN_TRY(ctx, { VDN_REQUIRE(dst_field >= 0 && dst_field < VDN_NFIELDS && src_field >= 0 && src_field < VDN_NFIELDS, "bad field id");
+                 st_field_copy(ctx, dst_field, src_field); }) }
+
 int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile)
 { VDN_TRY(ctx, { VDN_REQUIRE(tile >= -1 && tile < 5, "tile shape out of range");
                  VDN_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -85,6 +85,8 @@ void st_setval(vdn_ctx *c, int field, double val);
 // rows of a host box (staged flat on the device) <-> the region array
 struct BoxCopyArgs { double *stage, *base; long cs; int hext[3], hofs[3], n[3], dofs[3], dext0, dext1, ncomp, upload; };
 void st_box_copy(const BoxCopyArgs &a, cudaStream_t stream);
+double st_estdt(vdn_ctx *c, double dtold, double cflfac, double max_dt_growth);   // estdt.f90:15-87 on the resident fields
+void st_field_copy(vdn_ctx *c, int dst, int src);
 double st_absmax_valid(vdn_ctx *c, int field);           // norm_inf over valid cells/faces, all comps
 void mg_destroy(MG *mg);
 void comm_destroy(Comm *cm);

@@ -626,7 +626,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     // peer-memory mode: the kernel stores what it writes near a face shared with another rank into that rank's ghost layers as well (phi, and
     // under post == 2 the coarse right-hand side and the zeroed coarse phi), so the fused levels need no exchange launches inside a V-cycle
     WaveArgs a;
-    a.p2p = 0; a.my_flag = nullptr; a.epoch = 0;
+    a.p2p = 0; a.my_flag = nullptr; a.epoch = 0; a.peer_mask = 0;
     bool peer_mode = false;
     int dmask = 0;
     // the coarse correction under the fine ghost layers: pushed by the last sweep of the level below if that level is fused, exchanged otherwise
@@ -636,7 +636,7 @@ void wave_launch(vdn_ctx *c, MG *m, int l, int pre, int post)
     a.wait_ns = nullptr;
     if (m->push) {
         const double *arrs[4] = { L.phi, L.res, post == 2 ? m->L[l + 1].rhs : nullptr, post == 2 ? m->L[l + 1].phi : nullptr };
-        peer_mode = comm_peer_tables(c, arrs, 4, dmask, a.peer_delta, a.peer_flag, &a.my_flag, &a.epoch);
+        peer_mode = comm_peer_tables(c, arrs, 4, dmask, a.peer_delta, &a.peer_mask, a.pub_flag, a.wait_flag, &a.my_flag, &a.epoch);
         a.p2p = peer_mode ? 1 : 0;
     }
     VDN_REQUIRE(!m->distributed || peer_mode == m->push, "peer-memory mode of the fused smoother changed between launches");

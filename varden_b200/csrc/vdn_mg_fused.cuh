@@ -39,16 +39,21 @@ struct WaveArgs {
     // peer-memory mode (levels split across ranks, all level arrays in the symmetric heap of the peer-memory transport): the kernel PUSHES.
     // Every value it writes for a cell that lies within PUSH_DEPTH cells of a face shared with another rank -- the new phi, and under POST == 2
     // the coarse right-hand side and the zeroed coarse phi -- is also stored straight into the ghost layers of the SAME array on the rank(s)
-    // that hold that cell as a ghost (face, edge and corner neighbours: up to 7 copies).  Stores over NVLink are posted (nothing waits for them),
-    // so the exchange of a sweep costs no launch and no exposed latency; the next launch then reads its ghost layers from local memory.
+    // that hold that cell as a ghost (face, edge and corner neighbours: up to 7 copies) -- by the CTA that produced it, after its march, from its own
+    // L2-hot output.  Stores over NVLink are posted (nothing waits for them), so the exchange of a sweep costs no launch and no exposed latency;
+    // the next launch then reads its ghost layers from local memory.
     // peer_delta[q]: byte distance from this rank's heap to the heap of the rank at process-grid offset (ox, oy, oz), q = (ox+1) + 3 (oy+1) +
     // 9 (oz+1) -- the heaps have one layout, so local pointer + delta = the same array there.  The kernel publishes "my stream has reached launch
     // `epoch`" (everything before it is complete) in its own flag word, and the CTAs that read ghost layers or push wait for the flags of the
     // neighbours: their earlier launches -- which wrote my ghost layers and read the ghost layers I am about to overwrite -- are complete.
     // Interior CTAs start at once, so the wait overlaps with their work.
     int p2p;
+    unsigned peer_mask;                  // bit q: a rank exists at process-grid offset q
     long peer_delta[27];
-    const unsigned long long *peer_flag[27]; unsigned long long *my_flag; unsigned long long epoch;
+    // flags: my_flag = word 0 of this rank's heap header (read remotely by the pull kernels of vdn_comm.cu); pub_flag[q] = the word in the heap
+    // header of the rank at offset q where THIS rank announces its epoch (a posted remote store); wait_flag[q] = the word in this rank's own
+    // header where that rank announces its epoch -- so the wait polls local memory and ends one NVLink latency after the neighbour's store
+    unsigned long long *pub_flag[27]; const unsigned long long *wait_flag[27]; unsigned long long *my_flag; unsigned long long epoch;
     unsigned long long *wait_ns;         // measurement hook (may be null): [0] += ns an edge CTA waited for its first neighbour, [1] = max, [2] += 1
 };
 
@@ -97,6 +102,7 @@ inline unsigned long long vdn_globaltimer() { return 0; }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
 inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T __ldcv(const T *p) { return *p; }
+template <class T> inline T __ldcg(const T *p) { return *p; }
 inline void __threadfence_system() { }
 inline double emu_xor_buf[2048];
 inline double __shfl_xor_sync(unsigned, double v, int m)
@@ -153,29 +159,6 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     const int wyb = ld[0] ? wy[0] : wy[1] - 1;                  // rows of a pair exist together except on the masked outer ring
     const long gofs = a.off + (okx ? wx : 0) + a.s1 * (long)wyb;  // + s1 * row + s2 * plane
     const long cofs = PRE ? a.coff + ((okx ? wx : 0) >> 1) + a.cs1 * (long)(wyb >> 1) : 0;       // (arithmetic shifts: ghost indices are negative)
-    // peer-memory mode: the ranks (process-grid offsets pox, poy[row]) that hold this column's cells as ghosts.  Fused levels have >= 16 cells
-    // per direction, so a cell is near at most one face of a direction.
-    int pox = 0, poy[2] = { 0, 0 }, cpox = 0, cpoy = 0;
-    if (P2P) {
-        if (gx < PUSH_DEPTH && mx0 == M_GHOST) pox = -1; else if (gx >= n0 - PUSH_DEPTH && mx1 == M_GHOST) pox = 1;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) { if (gy0 + r < PUSH_DEPTH && my0 == M_GHOST) poy[r] = -1; else if (gy0 + r >= n1 - PUSH_DEPTH && my1 == M_GHOST) poy[r] = 1; }
-        if (POST == 2) {        // the coarse cell under this column
-            if ((gx >> 1) < PUSH_DEPTH && mx0 == M_GHOST) cpox = -1; else if ((gx >> 1) >= (n0 >> 1) - PUSH_DEPTH && mx1 == M_GHOST) cpox = 1;
-            if ((gy0 >> 1) < PUSH_DEPTH && my0 == M_GHOST) cpoy = -1; else if ((gy0 >> 1) >= (n1 >> 1) - PUSH_DEPTH && my1 == M_GHOST) cpoy = 1;
-        }
-    }
-    // store v at element `e` (local numbering of this rank's array `base`) of the same array on every rank that ghosts the cell: the non-empty
-    // subsets of the directions in which the cell is near a shared face.  n?: extent of the array's level in cells (index shift into the peer's numbering)
-    auto push = [&](double *base, long e, long st1, long st2, int e0, int e1, int e2, int ox, int oy, int oz, double v) {
-#pragma unroll
-        for (int m = 1; m < 8; ++m) {
-            const int qx = (m & 1) ? ox : 0, qy = (m & 2) ? oy : 0, qz = (m & 4) ? oz : 0;
-            if (((m & 1) && !ox) || ((m & 2) && !oy) || ((m & 4) && !oz)) continue;
-            double *dst = (double *)((char *)base + a.peer_delta[(qx + 1) + 3 * (qy + 1) + 9 * (qz + 1)]);
-            dst[e - (long)qx * e0 - st1 * (long)(qy * e1) - st2 * (long)(qz * e2)] = v;
-        }
-    };
     const bool anyld = ld[0] || ld[1];
     const bool bndx = (gx == 0 && (mx0 == M_NEU || mx0 == M_DIR)) || (gx == n0 - 1 && (mx1 == M_NEU || mx1 == M_DIR));
     bool bndy[2];
@@ -237,12 +220,15 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
     if (P2P && a.my_flag) {
         // everything this rank's stream produced before this launch is complete: publish it; CTAs that read ghost layers or push wait until
         // the neighbours have published the same launch (their earlier launches are complete as well)
-        if (tid == 0) { __threadfence_system(); *(volatile unsigned long long *)a.my_flag = a.epoch; }
         constexpr int MG = 2 * PUSH_DEPTH;          // footprint of what the CTA reads (H) or pushes (fine cells over PUSH_DEPTH coarse cells)
         const bool edge = (x0 - MG < 0 && mx0 == M_GHOST) || (x0 + TX + MG > n0 && mx1 == M_GHOST) || (y0 - MG < 0 && my0 == M_GHOST) ||
                           (y0 + TY + MG > n1 && my1 == M_GHOST) || (z0 - MG < 0 && mz0 == M_GHOST) || (z1 + MG > n2 && mz1 == M_GHOST);
-        if (edge && tid < 27 && a.peer_flag[tid]) {
-            const volatile unsigned long long *f = (const volatile unsigned long long *)a.peer_flag[tid];
+        // the CTAs that are dispatched first, and every CTA that is about to wait, announce the epoch to the neighbours
+        const bool announce = edge || (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) < 32u;
+        if (announce && tid == 0) { __threadfence_system(); *(volatile unsigned long long *)a.my_flag = a.epoch; }
+        if (announce && tid < 27 && a.pub_flag[tid]) { __threadfence_system(); *(volatile unsigned long long *)a.pub_flag[tid] = a.epoch; }
+        if (edge && tid < 27 && a.wait_flag[tid]) {
+            const volatile unsigned long long *f = (const volatile unsigned long long *)a.wait_flag[tid];
             const unsigned long long t0 = a.wait_ns ? vdn_globaltimer() : 0ull;
             while (*f < a.epoch) { }
             __threadfence_system();
@@ -311,11 +297,6 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
                 const double v0 = sm[oP[S] + sid], v1 = sm[oP[S] + sid + X];
                 a.out[e] = v0;
                 a.out[e + a.s1] = v1;
-                if (P2P) {
-                    const int poz = (r1 < PUSH_DEPTH && mz0 == M_GHOST) ? -1 : (r1 >= n2 - PUSH_DEPTH && mz1 == M_GHOST) ? 1 : 0;
-                    if (pox | poy[0] | poz) push(a.out, e, a.s1, a.s2, n0, n1, n2, pox, poy[0], poz, v0);
-                    if (pox | poy[1] | poz) push(a.out, e + a.s1, a.s1, a.s2, n0, n1, n2, pox, poy[1], poz, v1);
-                }
             }
         }
         // ---- residual of plane t-S: red cells only (the black ones were just relaxed) ----
@@ -339,14 +320,6 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
                         const double cr = (acc + s2) * 0.125;
                         a.crhs[cc] = cr;
                         a.czero[cc] = 0.0;
-                        if (P2P) {
-                            const int cz = r0 >> 1;
-                            const int cpoz = (cz < PUSH_DEPTH && mz0 == M_GHOST) ? -1 : (cz >= (n2 >> 1) - PUSH_DEPTH && mz1 == M_GHOST) ? 1 : 0;
-                            if (cpox | cpoy | cpoz) {
-                                push(a.crhs, cc, a.cs1, a.cs2, n0 >> 1, n1 >> 1, n2 >> 1, cpox, cpoy, cpoz, cr);
-                                push(a.czero, cc, a.cs1, a.cs2, n0 >> 1, n1 >> 1, n2 >> 1, cpox, cpoy, cpoz, 0.0);
-                            }
-                        }
                     }
                 }
             }
@@ -354,4 +327,42 @@ __global__ void __launch_bounds__(Sweep3Cfg<PRE, POST, TX, TY>::NT, 1) k_sweep3(
         __syncthreads();
     }
     if (POST == 3) block_atomic_max(nmax, a.nrm);
+    if (P2P) {
+        // ---- peer-memory mode: what this CTA wrote within PUSH_DEPTH cells of a face shared with another rank goes into that rank's ghost layers
+        // (face, edge and corner neighbours alike: the part of the CTA's box of cells that lies in the neighbour's ghost region).  Done after the
+        // march, from the CTA's own output (L2-hot), so that the marching loop is the one of the single-GPU kernel. ----
+        __syncthreads();
+        const int cb[3][2] = { { x0, min(x0 + TX, n0) }, { y0, min(y0 + TY, n1) }, { z0, z1 } };
+        for (int lev = 0; lev < (POST == 2 ? 2 : 1); ++lev) {         // 0: phi on this level; 1: coarse rhs and zeroed coarse phi
+            const int nn[3] = { n0 >> lev, n1 >> lev, n2 >> lev };
+            const long st1 = lev ? a.cs1 : a.s1, st2 = lev ? a.cs2 : a.s2, of = lev ? a.coff : a.off;
+#pragma unroll 1
+            for (int q = 0; q < 27; ++q) {
+                if (q == 13 || !((a.peer_mask >> q) & 1)) continue;
+                const int o[3] = { q % 3 - 1, (q / 3) % 3 - 1, q / 9 - 1 };
+                int lo[3], ex[3];
+                bool any = true;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    int l = cb[d][0] >> lev, h = cb[d][1] >> lev;
+                    if (o[d] < 0) h = min(h, PUSH_DEPTH); else if (o[d] > 0) l = max(l, nn[d] - PUSH_DEPTH);
+                    lo[d] = l; ex[d] = h - l;
+                    if (ex[d] <= 0) any = false;
+                }
+                if (!any) continue;
+                const long shift = -(long)o[0] * nn[0] - st1 * (long)(o[1] * nn[1]) - st2 * (long)(o[2] * nn[2]);
+                const int cnt = ex[0] * ex[1] * ex[2];
+                for (int t = tid; t < cnt; t += (int)blockDim.x) {
+                    const int i = lo[0] + t % ex[0], j = lo[1] + (t / ex[0]) % ex[1], k = lo[2] + t / (ex[0] * ex[1]);
+                    const long e = of + i + st1 * (long)j + st2 * (long)k;
+                    if (lev == 0) {
+                        ((double *)((char *)a.out + a.peer_delta[q]))[e + shift] = __ldcg(a.out + e);
+                    } else {
+                        ((double *)((char *)a.crhs + a.peer_delta[q]))[e + shift] = __ldcg(a.crhs + e);
+                        ((double *)((char *)a.czero + a.peer_delta[q]))[e + shift] = 0.0;
+                    }
+                }
+            }
+        }
+    }
 }

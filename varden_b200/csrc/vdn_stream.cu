@@ -215,6 +215,24 @@ __global__ void k_absmax(AmaxArgs a)
     block_atomic_max(m, a.out);
 }
 
+// estdt_2d / estdt_3d (estdt.f90:89-181): max |u_d| and max |gp_d / rho - f_d| over the valid cells, six block reductions + atomics
+struct EstArgs { Range r; int dim; View u, s, gp, f; double *out; };
+__global__ void k_estdt(EstArgs a)
+{
+    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = a.r.lo[2] + blockIdx.z;
+    double um[3] = { ZERO, ZERO, ZERO }, fm[3] = { ZERO, ZERO, ZERO };
+    if (i <= a.r.hi[0] && j <= a.r.hi[1]) {
+        const double rho = a.s(i, j, k, 0);
+        for (int d = 0; d < a.dim; ++d) {
+            um[d] = fabs(a.u(i, j, k, d));
+            fm[d] = fabs(a.gp(i, j, k, d) / rho - a.f(i, j, k, d));
+        }
+    }
+    for (int d = 0; d < a.dim; ++d) { block_atomic_max(um[d], a.out + d); __syncthreads(); block_atomic_max(fm[d], a.out + 3 + d); __syncthreads(); }
+}
+
 Range valid_range(const vdn_ctx *c, int fdir)
 {
     const Geo &g = c->geo;
@@ -251,6 +269,46 @@ void st_setval(vdn_ctx *c, int field, double val)
     SetArgs a; a.p = f.base; a.n = (long)(f.bytes / 8); a.v = val;
     k_setval<<<1184, 256, 0, c->stream>>>(a);
     VDN_CUDA(cudaGetLastError());
+}
+
+// estdt (estdt.f90:15-87) on the resident UOLD / SOLD / GP / EXT_VEL_FORCE: the six maxima are reduced over the whole region at once (the
+// reference reduces per box and takes the minimum dt; the limits depend on the maxima only, so the result is the same number), all-reduced
+// over the ranks (parallel_reduce MPI_MIN of dt == MAX of the maxima), and the driver's fallback / cflfac / growth limit applied on the host.
+double st_estdt(vdn_ctx *c, double dtold, double cflfac, double max_dt_growth)
+{
+    const int dim = c->dim;
+    {
+        LaunchScope ls(c, "estdt", (double)c->ncells() * 8.0 * (3 * dim + 1));
+        VDN_CUDA(cudaMemsetAsync(c->d_red, 0, 6 * 8, c->stream));
+        EstArgs a; a.r = valid_range(c, -1); a.dim = dim;
+        a.u = c->f[VDN_UOLD].view(); a.s = c->f[VDN_SOLD].view(); a.gp = c->f[VDN_GP].view(); a.f = c->f[VDN_EXT_VEL_FORCE].view(); a.out = c->d_red;
+        k_estdt<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    VDN_CUDA(cudaMemcpyAsync(c->h_pin, c->d_red, 6 * 8, cudaMemcpyDeviceToHost, c->stream));
+    VDN_CUDA(cudaStreamSynchronize(c->stream));
+    double m[6];
+    for (int q = 0; q < 6; ++q) m[q] = c->h_pin[q];
+    for (int q = 0; q < 6; ++q) m[q] = comm_allreduce_max(c, m[q]);
+    const double eps = (double)1.0e-8f;           // a single-precision literal in the reference (estdt.f90:104,147)
+    const double dt_start = 1.e20;
+    double dt = dt_start;
+    for (int d = 0; d < dim; ++d) if (m[d] > eps) dt = fmin(dt, c->geo.h[d] / m[d]);
+    for (int d = 0; d < dim; ++d) if (m[3 + d] > eps) dt = fmin(dt, sqrt(2.0 * c->geo.h[d] / m[3 + d]));
+    if (dt == dt_start) { dt = fmin(c->geo.h[0], c->geo.h[1]); if (dim == 3) dt = fmin(dt, c->geo.h[2]); }
+    dt = dt * cflfac;
+    if (dtold > 0.0) dt = fmin(dt, max_dt_growth * dtold);
+    return dt;
+}
+
+// dst = src for two fields of one layout (the driver's uold <- unew, sold <- snew, varden.f90:321-324), ghost cells included
+void st_field_copy(vdn_ctx *c, int dst, int src)
+{
+    DField &d = c->f[dst], &s = c->f[src];
+    VDN_REQUIRE(d.base && s.base && d.bytes == s.bytes && d.ng == s.ng && d.nc == s.nc && d.fdir == s.fdir, "vdn_field_copy: the two fields have different layouts");
+    if (dst >= VDN_UMAC_X && dst <= VDN_UMAC_Z) ++c->umac_epoch;
+    LaunchScope ls(c, "field_copy", 2.0 * (double)d.bytes);
+    VDN_CUDA(cudaMemcpyAsync(d.base, s.base, d.bytes, cudaMemcpyDeviceToDevice, c->stream));
 }
 
 double st_absmax_valid(vdn_ctx *c, int field)
