@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--xchg", default="push", choices=["push", "nccl", "pull", "pushk"],
                     help="A/B: ghost exchange of the fused multigrid levels -- push: stored by the sweep kernel itself (default); nccl; pull / pushk: a pull kernel "
                          "before / a push kernel after every sweep")
+    ap.add_argument("--fuse-min", type=int, default=0, help="A/B: smallest multigrid level the fused smoother runs on (library default: 128, 64 on rank-split levels)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--global-n", type=int, default=0, help="configs 3/5: global cells per direction (default 2 x --n)")
@@ -221,6 +222,9 @@ def main():
         ctx.comm_tune({"push": 0, "nccl": 1, "pull": 2, "pushk": 3}[args.xchg])
         PAR.init_comm(ctx, rank, world, rlo, rhi)
 
+    if args.fuse_min:
+        ctx.mg_tune(args.fuse_min, -1)
+
     # ---- pinned host buffers = what the Fortran driver would hand over (ghosts filled as varden.f90:291-300) ----
     spec_in = [("UOLD", "uold", 3, dim), ("SOLD", "sold", 3, nscal), ("GP", "gp", 1, dim),
                ("EXT_VEL_FORCE", "ext_vel_force", 1, dim), ("EXT_SCAL_FORCE", "ext_scal_force", 1, nscal)]
@@ -263,9 +267,6 @@ def main():
     for _ in range(max(args.warmup, 3)):
         cyc, res = step_resident()
     ctx.sync()
-    ctx.prof_enable(True)
-    if world > 1:
-        ctx.debug_counters()                                 # switch the flag-wait accounting of the fused smoother on
     l0 = ctx.launch_count()
     cb0 = ctx.comm_bytes()
     sampler = ClockSampler(local); sampler.start()
@@ -295,6 +296,20 @@ def main():
     wall_host = time.perf_counter() - t0
     wall = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)       # device time by CUDA events on the launching stream, max over ranks
     launches = ctx.launch_count() - l0
+    comm_bytes = (ctx.comm_bytes() - cb0) / args.steps
+    # ---- the same K steps once more with the library's per-launch CUDA events on: the per-kernel-family table, the phases and the roofline
+    # (kept out of the pass above so that `value` does not pay two event records per launch) ----
+    ctx.prof_enable(True)
+    if world > 1:
+        ctx.debug_counters()                                 # switch the flag-wait accounting of the fused smoother on
+    barrier()
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evp0.record(xs)
+    for _ in range(args.steps):
+        cyc, res = step_resident()
+    evp1.record(xs)
+    barrier()
+    wall_prof = max_over_ranks(evp0.elapsed_time(evp1) / 1e3)
     prof = ctx.prof_report()
     ctx.prof_enable(False)
     waits, by_rank = None, None
@@ -312,7 +327,6 @@ def main():
     ms_per_step = 1e3 * wall / args.steps
     value = ncells_global * args.steps / wall / 1e9
 
-    comm_bytes = (ctx.comm_bytes() - cb0) / args.steps
     # ---- e2e timing (host buffers, copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
@@ -391,6 +405,9 @@ def main():
                                        % (pgrid, {"nccl": "NCCL send/recv", "push": "peer-memory (CUDA-IPC; fused MG sweeps push their boundary results)", "pull": "peer-memory (pull kernel per exchange)", "pushk": "peer-memory (push kernel per MG sweep)"}[args.xchg])) if world > 1 else "single GPU",
                        "l2_policy": "inputs (%.1f GB of fields per GPU) exceed the 126 MB L2; no explicit flush" % (45 * 8 * geom.nboxes * (n + 6) ** 3 / 1e9),
                        "mac_vcycles_per_step": cyc, "mac_resnorm": res, "kernel_ms_sum_per_step": dev_ms / args.steps,
+                       "ms_per_step_with_per_launch_events": 1e3 * wall_prof / args.steps,
+                       "timing": "value / ms_per_step: K steps, CUDA events on the library's stream, no per-launch events; kernels / phases / roofline: "
+                                 "the same K steps run once more with the library's per-launch CUDA events on",
                        "host_wall_ms_per_step": 1e3 * wall_host / args.steps},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "phases_ms_per_step": phases, "nvlink": nvlink,

@@ -150,6 +150,19 @@ module vdn_iso_c
      end function vdn_make_at_halftime
 
      ! multi-rank: one context per MPI rank, NCCL communicator from a unique id created on rank 0 and broadcast by the caller
+     ! SURVEY 8(f) row 3: the driver's per-step glue on the resident fields (include/vdn.h: vdn_estdt, vdn_field_copy)
+     integer(c_int) function vdn_estdt(ctx, dtold, cflfac, max_dt_growth, dt) bind(c, name='vdn_estdt')
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), value :: dtold, cflfac, max_dt_growth
+       real(c_double), intent(out) :: dt
+     end function vdn_estdt
+     integer(c_int) function vdn_field_copy(ctx, dst_field, src_field) bind(c, name='vdn_field_copy')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: dst_field, src_field
+     end function vdn_field_copy
+
      integer(c_int) function vdn_device_count() bind(c, name='vdn_device_count')
        import :: c_int
      end function vdn_device_count
@@ -181,7 +194,7 @@ module vdn_path_module
 
   implicit none
   private
-  public :: vdn_advance_path, vdn_path_finalize, vdn_ctx_for, vdn_put, vdn_get, vdn_check
+  public :: vdn_advance_path, vdn_path_finalize, vdn_ctx_for, vdn_ctx_current, vdn_put, vdn_get, vdn_check
 
   type(c_ptr), save :: ctx = c_null_ptr      ! one context per MPI rank; rebuilt after regrid (call vdn_path_finalize)
   type(c_ptr), allocatable, target, save :: fab_tab(:,:)   ! (local fab, multifab slot): host pointers handed to vdn_advance_host
@@ -220,6 +233,14 @@ contains
     if (.not. c_associated(ctx)) call vdn_path_init(mla, mf, dx)
     c = ctx
   end function vdn_ctx_for
+
+  ! the context that an earlier path call created (estdt has no ml_layout argument; the driver first calls it at istep = 2,
+  ! varden.f90:302, after the first advance_timestep has built the context)
+  function vdn_ctx_current() result(c)
+    type(c_ptr) :: c
+    if (.not. c_associated(ctx)) call bl_error('libvdn: no context yet (estdt before the first advance_timestep)')
+    c = ctx
+  end function vdn_ctx_current
 
   subroutine vdn_path_init(mla, mf, dx)
     use probin_module, only: nscal, slope_order, use_minion, boussinesq, stencil_order, mg_verbose, visc_coef, diff_coef, &

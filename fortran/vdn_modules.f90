@@ -5,6 +5,7 @@
 !     update_module         :: update         (replaces src/update.f90:16-17)
 !     macproject_module     :: macproject     (replaces src/macproject.f90:20)
 !     mac_multigrid_module  :: mac_multigrid  (replaces src/mac_multigrid.f90:19-20)
+!     estdt_module          :: estdt          (replaces src/estdt.f90:15; SURVEY 8(f) row 3)
 !
 ! A maintainer removes velpred.f90, mkflux.f90, update.f90, macproject.f90, mac_multigrid.f90 from src/GPackage.mak and adds
 ! vdn_iso_c.f90 + this file; every caller (advance_premac.f90:51, scalar_advance.f90:102,118, velocity_advance.f90:76,92,
@@ -366,3 +367,52 @@ contains
   end subroutine macproject
 
 end module macproject_module
+
+
+module estdt_module
+
+  use bl_types
+  use multifab_module
+  use vdn_iso_c
+  use vdn_path_module, only : vdn_ctx_current, vdn_put, vdn_check
+
+  implicit none
+  private
+  public :: estdt
+
+contains
+
+  ! estdt.f90:15 -- argument list unchanged.  The six maxima are reduced on the device over the rank's boxes and all-reduced over the ranks
+  ! inside the library (the reference's parallel_reduce(dt, dt_proc, MPI_MIN), estdt.f90:68).  u, s, gp and ext_vel_force are what the driver
+  ! hands to advance_timestep a few lines later (varden.f90:302-316), so the copies made here are the ones the path needs anyway: a driver
+  ! that uses the fused vdn_advance_path can skip its own upload of these four fields for this step.
+  subroutine estdt (lev, u, s, gp, ext_vel_force, dx, dtold, dt)
+
+    use probin_module, only: max_dt_growth, cflfac, verbose
+
+    type(multifab) , intent( in) :: u,s,gp,ext_vel_force
+    real(kind=dp_t), intent( in) :: dx(:)
+    real(kind=dp_t), intent( in) :: dtold
+    real(kind=dp_t), intent(out) :: dt
+    integer        , intent( in) :: lev
+
+    type(c_ptr) :: ctx
+    real(c_double) :: dt_c
+    type(bl_prof_timer), save :: bpt
+
+    call build(bpt,"estdt")
+    if (lev /= 1) call bl_error('estdt (libvdn): single-level only')
+    ctx = vdn_ctx_current()
+    call vdn_put(ctx, VDN_UOLD, u)
+    call vdn_put(ctx, VDN_SOLD, s)
+    call vdn_put(ctx, VDN_GP, gp)
+    call vdn_put(ctx, VDN_EXT_VEL_FORCE, ext_vel_force)
+    call vdn_check(ctx, vdn_estdt(ctx, real(dtold,c_double), real(cflfac,c_double), real(max_dt_growth,c_double), dt_c))
+    dt = dt_c
+    if (parallel_IOProcessor() .and. verbose .ge. 1) write(6,1000) lev,dt
+1000 format("Computing dt at level ",i2," to be ... ",e15.8)
+    call destroy(bpt)
+
+  end subroutine estdt
+
+end module estdt_module

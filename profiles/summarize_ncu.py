@@ -62,6 +62,11 @@ def family(kname, grid):
         a = [x.strip() for x in m.group(2).split(",")]
         pre, post = (int(a[0]), int(a[1])) if m.group(1) in ("sweep2", "sweep3") else (int(a[1]), int(a[2]))
         return {2: "mg_wave_down_l0", 3: "mg_wave_up_l0"}.get(post, "mg_wave_pro_l0" if pre else "mg_wave_smooth_l0")
+    if "k_velpred_march" in kname:
+        return "velpred"
+    m = re.search(r"k_mkflux_march<\s*\d+\s*,\s*(\d+)", kname)
+    if m:       # <NC, CONSMASK, ...>: the conservative (density) launch is a scalar one; non-conservative launches are velocity components or the tracer
+        return "mkflux_scal" if int(m.group(1)) else "mkflux_vel"
     for k, f in (("k_gsrb", "mg_gsrb_l0"), ("k_residual", "mg_residual_l0"), ("k_mf_normal3", "mf_normal3"), ("k_mf_trans6", "mf_trans6"),
                  ("k_mf_final3", "mf_final3"), ("k_vp_normal3", "vp_normal3"), ("k_vp_trans6", "vp_trans6"), ("k_vp_final3", "vp_final3"),
                  ("k_mkvelforce", "mkvelforce")):

@@ -83,5 +83,27 @@ def main():
         print("%-22s %6.1f KB  %d arrays" % (name, os.path.getsize(path) / 1024.0, len(arrs)))
 
 
+def main_estdt():
+    """tests/golden/estdt.json: the reference's own estdt_2d / estdt_3d (estdt.f90:89-181) inside the driver logic of estdt.f90:15-87, on the stored
+    inputs of every fixture (and on a copy scaled below the reference's eps: the min(dx) fallback), as hexadecimal floats"""
+    if not R.available():
+        raise SystemExit("oracle/_ref/libref.so missing: run `make -C oracle ref` (needs /root/reference)")
+    out = {"reference_routines": {k: R.where(k) for k in ("estdt_2d", "estdt_3d")}, "cases": {}}
+    for name in CASES:
+        geom, P, st, dt = build_case(name)
+        rows = []
+        for scale in (1.0, 1e-12):
+            u = [a * scale for a in st["uold"]]; gp = [a * scale for a in st["gp"]]; f = [a * scale for a in st["ext_vel_force"]]
+            for dtold in (-1.0, 1e-4):
+                rows.append(dict(scale=scale, dtold=dtold, dt=float(R.estdt(geom, u, 3, st["sold"], 3, gp, 1, f, 1, dtold=dtold)).hex()))
+        out["cases"][name] = rows
+    with open(os.path.join(HERE, "estdt.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print("estdt.json: %d cases" % len(out["cases"]))
+
+
 if __name__ == "__main__":
-    main()
+    if "--estdt" in sys.argv:
+        main_estdt()
+    else:
+        main()

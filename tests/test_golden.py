@@ -152,3 +152,38 @@ def test_cuda_matches_reference_golden(path):
     print(os.path.basename(path), {k: "%.1e" % v for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not (v <= TOL_EDGE)}
     assert not bad, bad
+
+
+def _estdt_gold():
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "estdt.json")
+    return json.load(open(p))["cases"]
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_estdt_matches_reference_golden(path):
+    """estdt (estdt.f90:15-181): tests/golden/estdt.json holds the reference routines' dt on the fixture inputs"""
+    g = Gold(path)
+    st = g.state()
+    for row in _estdt_gold()[g.meta["name"]]:
+        sc = row["scale"]
+        u = [a * sc for a in st["uold"]]; gp = [a * sc for a in st["gp"]]; f = [a * sc for a in st["ext_vel_force"]]
+        got = O.estdt(g.geom, u, 3, st["sold"], 3, gp, 1, f, 1, dtold=row["dtold"])
+        assert got == float.fromhex(row["dt"]), (g.meta["name"], row, got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_cuda_estdt_matches_reference_golden(path):
+    from util import make_ctx, upload_state
+    g = Gold(path)
+    st = g.state()
+    ctx = make_ctx(g.geom, g.P)
+    for row in _estdt_gold()[g.meta["name"]]:
+        sc = row["scale"]
+        s2 = dict(st)
+        for k in ("uold", "gp", "ext_vel_force"):
+            s2[k] = [np.asfortranarray(a * sc) for a in st[k]]
+        upload_state(ctx, g.geom, g.P, s2)
+        got = ctx.estdt(dtold=row["dtold"])
+        assert got == float.fromhex(row["dt"]), (g.meta["name"], row, got)
+    ctx.close()
