@@ -157,6 +157,17 @@ int vdn_estdt(vdn_ctx *ctx, double dtold, double cflfac, double max_dt_growth, d
  * does not need the host copy. */
 int vdn_field_copy(vdn_ctx *ctx, int dst_field, int src_field);
 
+/* ---- the implicit viscous / diffusive solves that follow the path (single-rank contexts in this version) ----
+ * visc_solve (viscsolve.f90:19): for every velocity component d, (RHOHALF - mu div grad) u_d = RHOHALF u_d [+ mu LAPU_d] + (1/3) visc_mu_dt
+ * d(MAC_RHS)/dx_d on UNEW, boundary types of component d (define_bc_tower.f90:254-340), Dirichlet data from UNEW's ghost cells, initial
+ * guess UNEW, rel. tolerance 1.d-12 (viscsolve.f90:88); then UNEW's ghost cells are refilled (:105).  mu = (1/2) dt visc_coef with
+ * diffusion_type 1 (Crank-Nicolson; needs LAPU) or dt visc_coef with diffusion_type 2 (velocity_advance.f90:105-111).  ncycles: V-cycles
+ * summed over the components; resnorm: the largest final relative residual.  Returns 2 when the V-cycle cap is hit. */
+int vdn_visc_solve(vdn_ctx *ctx, double mu, int diffusion_type, int *ncycles, double *resnorm);
+/* diff_scalar_solve (viscsolve.f90:310): (1 - mu div grad) s = s on component icomp (0-based) of SNEW, boundary types of that scalar;
+ * diffusion_type 2 only in this version (the Crank-Nicolson form needs the explicit term laps, for which the context has no field yet). */
+int vdn_diff_scalar_solve(vdn_ctx *ctx, double mu, int icomp, int diffusion_type, int *ncycles, double *resnorm);
+
 /* The whole device-resident path advance_timestep.f90:95-124:
  * advance_premac -> macproject -> scalar_advance -> make_at_halftime -> velocity_advance. */
 int vdn_advance(vdn_ctx *ctx, double dt, double mac_rel_eps, int *mac_cycles, double *mac_resnorm);

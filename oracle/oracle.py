@@ -383,6 +383,122 @@ def estdt(geom, u, ng_u, s, ng_s, gp, ng_g, ext_vel_force, ng_f, dtold=-1.0, cfl
              C.c_int(dim), dx, C.c_double(dtold), C.c_double(cflfac), C.c_double(max_dt_growth))
 
 
+# ---------------------------------------------------------------------------------------------
+# visc_solve / diff_scalar_solve (viscsolve.f90) -- ** parity unpinned ** like the MAC solve (F_MG absent)
+# ---------------------------------------------------------------------------------------------
+def _gather(geom, mf, ng, comp, grow=0):
+    """whole-domain array of one component: valid cells of every box, plus `grow` layers around the domain taken from the boxes' ghost cells"""
+    dim = geom.dim
+    N = [geom.n_cell[d] for d in range(3)]
+    G = np.full([N[d] + (2 * grow if d < dim else 0) for d in range(3)], np.nan)
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        a = mf[ib][..., comp]
+        src, dst = [], []
+        for d in range(3):
+            if d >= dim:
+                src.append(slice(None)); dst.append(slice(None)); continue
+            g0 = grow if lo[d] == geom.dlo[d] else 0
+            g1 = grow if hi[d] == geom.dhi[d] else 0
+            src.append(slice(ng - g0, a.shape[d] - ng + g1))
+            dst.append(slice(lo[d] + grow - g0, hi[d] + 1 + grow + g1))
+        G[tuple(dst)] = a[tuple(src)]
+    return G
+
+
+def _scatter(geom, G, mf, ng, comp):
+    for ib, (lo, hi) in enumerate(geom.boxes):
+        sl = tuple(slice(lo[d], hi[d] + 1) if d < geom.dim else slice(None) for d in range(3))
+        valid(geom, mf[ib], ib, ng)[..., comp] = G[sl]
+
+
+def helm_ell_bc(geom, comp_is_vel, comp):
+    """ell_bc_level_build (define_bc_tower.f90:254-340) for a velocity component / a scalar on the domain faces"""
+    ell = np.zeros((3, 2), dtype=np.int32)
+    ELL_PER, ELL_DIR, ELL_NEU = -1, 1, 2
+    for d in range(geom.dim):
+        for s in range(2):
+            p = int(geom.phys_bc[d, s])
+            if p == PERIODIC:
+                ell[d, s] = ELL_PER
+            elif p in (SLIP_WALL, SYMMETRY):
+                ell[d, s] = ELL_DIR if (comp_is_vel and comp == d) else ELL_NEU
+            elif p == NO_SLIP_WALL:
+                ell[d, s] = ELL_DIR if comp_is_vel else ELL_NEU
+            elif p == INLET:
+                ell[d, s] = ELL_DIR
+            elif p == OUTLET:
+                ell[d, s] = ELL_NEU
+            else:
+                raise ValueError(p)
+    return ell
+
+
+def _helm_component(geom, params, mf, ng, comp, comp_is_vel, rho, lap, mac_rhs, mu, diffusion_type, rel_eps=1e-12):
+    """one Helmholtz solve (alpha - mu div grad) phi = rh on component comp of mf: mkrhs_2d/3d (viscsolve.f90:193-299 / :464-513), the Dirichlet
+    data folded into rh (a ghost cell of an EXT_DIR face holds the boundary value: + 8/3 mu phi_b / h^2, the inhomogeneous part of the
+    stencil_order-2 boundary stencil), initial guess = the current field"""
+    dim = geom.dim
+    N = [geom.n_cell[d] for d in range(3)]
+    ug = _gather(geom, mf, ng, comp, grow=1)
+    V = tuple(slice(1, N[d] + 1) if d < dim else slice(None) for d in range(3))
+    u = ug[V]
+    alpha = _gather(geom, rho, 1, 0) if comp_is_vel else np.ones(N)
+    rh = u * alpha if comp_is_vel else u.copy()
+    if diffusion_type == 1:
+        rh = rh + mu * _gather(geom, lap, 0, comp)
+    if comp_is_vel:
+        visc_mu_dt = 2.0 * mu if diffusion_type == 1 else mu
+        mg = _gather(geom, mac_rhs, 1, 0, grow=1)
+        hi = [slice(None)] * 3; lo = [slice(None)] * 3
+        for d in range(dim):
+            hi[d] = slice(2, N[d] + 2) if d == comp else slice(1, N[d] + 1)
+            lo[d] = slice(0, N[d]) if d == comp else slice(1, N[d] + 1)
+        rh = rh + (1.0 / 3.0) * visc_mu_dt * (mg[tuple(hi)] - mg[tuple(lo)]) / geom.dx[comp]
+    ell = helm_ell_bc(geom, comp_is_vel, comp)
+    for d in range(dim):
+        h2 = 1.0 / geom.dx[d] ** 2
+        for s in range(2):
+            if ell[d, s] != 1:
+                continue
+            cell = [slice(None)] * 3; ghost = list(V)
+            cell[d] = 0 if s == 0 else N[d] - 1
+            ghost[d] = 0 if s == 0 else N[d] + 1
+            rh[tuple(cell)] = rh[tuple(cell)] + ((8.0 / 3.0) * mu * h2) * ug[tuple(ghost)]
+    nn = (C.c_int * 3)(*N)
+    hh = (C.c_double * 3)(*[geom.dx[d] if d < dim else 1.0 for d in range(3)])
+    eb = (C.c_int * 6)(*[int(x) for x in ell.ravel()])
+    b = [np.full([N[t] + (1 if t == d else 0) for t in range(3)], mu, order="F") for d in range(dim)]
+    phi = np.zeros([N[d] + 2 if d < dim else 1 for d in range(3)], order="F")
+    F = lambda a: np.asfortranarray(a, dtype=np.float64)
+    rhF, alF, u0F = F(rh), F(alpha), F(u)
+    res = C.c_double(0.0)
+    f = lib().orc_mg_solve_ex
+    f.restype = C.c_int
+    cyc = f(C.c_int(dim), nn, hh, eb, _dp(rhF), _dp(b[0]), _dp(b[1]), _dp(b[2]) if dim == 3 else None, _dp(alF), _dp(u0F), _dp(phi),
+            C.c_double(rel_eps), C.c_int(params.mg_max_cycles), C.c_int(params.mg_nu1), C.c_int(params.mg_nu2), C.c_double(1e-3),
+            C.c_int(params.mg_verbose), C.byref(res))
+    PV = tuple(slice(1, N[d] + 1) if d < dim else slice(None) for d in range(3))
+    _scatter(geom, phi[PV], mf, ng, comp)
+    return cyc, res.value
+
+
+def visc_solve(geom, params, unew, lapu, rho, mac_rhs, mu, diffusion_type=1):
+    """viscsolve.f90:19-146: unew (ng 3, ghost cells filled) is solved component by component in place, then refilled (:105)"""
+    tot, rmax = 0, 0.0
+    for d in range(geom.dim):
+        cyc, res = _helm_component(geom, params, unew, 3, d, True, rho, lapu, mac_rhs, mu, diffusion_type)
+        tot += cyc; rmax = max(rmax, res)
+    fill_and_physbc(geom, params, unew, 3, geom.dim, 0, 0, geom.dim)
+    return tot, rmax
+
+
+def diff_scalar_solve(geom, params, snew, laps, mu, icomp, diffusion_type=2):
+    """viscsolve.f90:310-423 on component icomp (0-based) of snew, then fill_boundary + physbc of the scalars (:379-382)"""
+    cyc, res = _helm_component(geom, params, snew, 3, icomp, False, None, laps, None, mu, diffusion_type)
+    fill_and_physbc(geom, params, snew, 3, params.nscal, 0, geom.dim, params.nscal)
+    return cyc, res
+
+
 def project_with_phi(geom, params, umac_pred, rho, ncomp_s, phi):
     """mk_mac_coeffs + mkumac + fill_boundary(umac) for a GIVEN phi (whose ghost cells get filled here); returns umac."""
     dim = geom.dim

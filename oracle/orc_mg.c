@@ -22,6 +22,7 @@ typedef struct {
     long ntot;
     double h[3];
     double *phi, *rhs, *res, *b[3];
+    double *alpha;       /* Helmholtz solves (alpha - div beta grad): cell coefficient, NULL for the MAC projection */
 } mglev;
 
 typedef struct {
@@ -43,10 +44,11 @@ static void lev_alloc(mglev *L, int nx, int ny, int nz, const double *h, int dim
     L->rhs = (double*)calloc(L->ntot, sizeof(double));
     L->res = (double*)calloc(L->ntot, sizeof(double));
     for (int d = 0; d < 3; ++d) L->b[d] = (d < dim) ? (double*)calloc(L->ntot, sizeof(double)) : NULL;
+    L->alpha = NULL;
 }
 static void lev_free(mglev *L)
 {
-    free(L->phi); free(L->rhs); free(L->res);
+    free(L->phi); free(L->rhs); free(L->res); free(L->alpha);
     for (int d = 0; d < 3; ++d) free(L->b[d]);
 }
 
@@ -74,6 +76,7 @@ static inline void op_cell(const mgtower *T, const mglev *L, const double *x, in
     const long c = IDX(L,i,j,k);
     const int ix[3] = { i, j, k };
     double a = 0.0, dg = 0.0;
+    if (L->alpha) { a = L->alpha[c]*x[c]; dg = L->alpha[c]; }
     for (int d = 0; d < T->dim; ++d) {
         const long st = L->s[d];
         const double h2 = 1.0/(L->h[d]*L->h[d]);
@@ -231,14 +234,17 @@ static void vcycle(const mgtower *T, int l, int nu1, int nu2, double bottom_eps)
  * hold periodic images (physical-boundary ghosts are left 0).  Returns the number of V-cycles;
  * *resnorm = final |r|_inf / |rh|_inf.
  */
-int orc_mg_solve(int dim, const int *n, const double *h, const int *ell_bc /* [3][2] */,
-                 const double *rh, const double *bx, const double *by, const double *bz,
-                 double *phi, double rel_eps, int max_cycles, int nu1, int nu2, double bottom_eps,
-                 int verbose, double *resnorm)
+/* alpha, phi0: NULL, or nx*ny*nz cell arrays (no ghosts) -- the Helmholtz form (alpha - div beta grad) phi = rh of viscsolve.f90
+ * (visc_solve: alpha = rho, diff_scalar_solve: alpha = 1) and its initial guess (the current field).  Dirichlet DATA is not handled here:
+ * the caller folds 8/3 beta phi_b / h^2 into rh (see orc_helm_rhs in orc_glue.c). */
+int orc_mg_solve_ex(int dim, const int *n, const double *h, const int *ell_bc /* [3][2] */,
+                    const double *rh, const double *bx, const double *by, const double *bz, const double *alpha, const double *phi0,
+                    double *phi, double rel_eps, int max_cycles, int nu1, int nu2, double bottom_eps,
+                    int verbose, double *resnorm)
 {
     mgtower T; T.dim = dim;
     for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) T.bc[d][s] = (d < dim) ? ell_bc[d*2+s] : ELL_NEU;
-    T.singular = 1;
+    T.singular = alpha ? 0 : 1;
     for (int d = 0; d < dim; ++d) for (int s = 0; s < 2; ++s) if (T.bc[d][s] == ELL_DIR) T.singular = 0;
 
     int nn[3] = { n[0], n[1], dim == 3 ? n[2] : 1 };
@@ -263,6 +269,24 @@ int orc_mg_solve(int dim, const int *n, const double *h, const int *ell_bc /* [3
         long m0 = nn[0]+e[0], m1 = nn[1]+e[1];
         for (int k = 0; k < nn[2]+e[2]; ++k) for (int j = 0; j < nn[1]+e[1]; ++j) for (int i = 0; i < nn[0]+e[0]; ++i)
             F->b[d][IDX(F,i,j,k)] = bsrc[d][(long)i + m0*(j + m1*k)];
+    }
+    if (phi0)
+        for (int k = 0; k < nn[2]; ++k) for (int j = 0; j < nn[1]; ++j) for (int i = 0; i < nn[0]; ++i)
+            F->phi[IDX(F,i,j,k)] = phi0[(long)i + (long)nn[0]*(j + (long)nn[1]*k)];
+    if (alpha) {
+        for (int l = 0; l < nlev; ++l) T.L[l].alpha = (double*)calloc(T.L[l].ntot, sizeof(double));
+        for (int k = 0; k < nn[2]; ++k) for (int j = 0; j < nn[1]; ++j) for (int i = 0; i < nn[0]; ++i)
+            F->alpha[IDX(F,i,j,k)] = alpha[(long)i + (long)nn[0]*(j + (long)nn[1]*k)];
+        for (int l = 1; l < nlev; ++l) {        /* coarse alpha = average of the fine cells it covers */
+            mglev *f = &T.L[l-1], *c = &T.L[l];
+            const int rz = dim == 3 ? 2 : 1;
+            for (int k = 0; k < c->n[2]; ++k) for (int j = 0; j < c->n[1]; ++j) for (int i = 0; i < c->n[0]; ++i) {
+                double s = 0.0;
+                for (int kk = 0; kk < rz; ++kk) for (int jj = 0; jj < 2; ++jj) for (int ii = 0; ii < 2; ++ii)
+                    s += f->alpha[IDX(f, 2*i+ii, 2*j+jj, rz*k+kk)];
+                c->alpha[IDX(c,i,j,k)] = s/(4.0*rz);
+            }
+        }
     }
     /* coarsen coefficients: arithmetic average of the fine faces covering the coarse face */
     for (int l = 1; l < nlev; ++l) {
@@ -300,4 +324,12 @@ int orc_mg_solve(int dim, const int *n, const double *h, const int *ell_bc /* [3
     for (int l = 0; l < nlev; ++l) lev_free(&T.L[l]);
     free(T.L);
     return cycles;
+}
+
+int orc_mg_solve(int dim, const int *n, const double *h, const int *ell_bc /* [3][2] */,
+                 const double *rh, const double *bx, const double *by, const double *bz,
+                 double *phi, double rel_eps, int max_cycles, int nu1, int nu2, double bottom_eps,
+                 int verbose, double *resnorm)
+{
+    return orc_mg_solve_ex(dim, n, h, ell_bc, rh, bx, by, bz, NULL, NULL, phi, rel_eps, max_cycles, nu1, nu2, bottom_eps, verbose, resnorm);
 }

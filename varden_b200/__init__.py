@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "vdn_macproject", "vdn_mkflux", "vdn_update", "vdn_make_at_halftime", "vdn_advance", "vdn_advance_host",
     "vdn_divumac", "vdn_mk_mac_coeffs", "vdn_mac_solve", "vdn_mkumac",
     "vdn_prof_enable", "vdn_prof_count", "vdn_prof_get", "vdn_launch_count", "vdn_mg_tune", "vdn_device_count", "vdn_comm_bytes",
-    "vdn_debug_counters", "vdn_estdt", "vdn_field_copy",
+    "vdn_debug_counters", "vdn_estdt", "vdn_field_copy", "vdn_visc_solve", "vdn_diff_scalar_solve",
 ]
 
 
@@ -222,6 +222,18 @@ class Context:
     def field_copy(self, dst, src):
         """dst <- src on the device, ghost cells included (varden.f90:321-324)"""
         self._chk(self.lib.vdn_field_copy(self.h, F[dst], F[src]))
+
+    def visc_solve(self, mu, diffusion_type=1):
+        """viscsolve.f90:19 on UNEW (alpha = RHOHALF, LAPU, MAC_RHS resident) -> (V-cycles summed over the components, largest rel. residual)"""
+        n, r = C.c_int(0), C.c_double(0.0)
+        self._chk(self.lib.vdn_visc_solve(self.h, C.c_double(mu), int(diffusion_type), C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def diff_scalar_solve(self, mu, icomp, diffusion_type=2):
+        """viscsolve.f90:310 on component icomp (0-based) of SNEW"""
+        n, r = C.c_int(0), C.c_double(0.0)
+        self._chk(self.lib.vdn_diff_scalar_solve(self.h, C.c_double(mu), int(icomp), int(diffusion_type), C.byref(n), C.byref(r)))
+        return n.value, r.value
 
     def comm_tune(self, mode):
         """measurement hook, before set_comm: transport of the ghost exchanges -- 0 peer memory with the fused sweeps pushing their boundary results

@@ -207,6 +207,7 @@ static void ctx_free(vdn_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->mg) mg_destroy(c->mg);
+    if (c->mgh) mg_destroy(c->mgh);
     if (c->comm) comm_destroy(c->comm);
     for (int i = 0; i < VDN_NFIELDS; ++i) {
         if (i >= VDN_SEDGE_X && i <= VDN_SEDGE_Z) continue;      // aliases UEDGE
@@ -511,6 +512,14 @@ int vdn_estdt(vdn_ctx *ctx, double dtold, double cflfac, double max_dt_growth, d
 int vdn_field_copy(vdn_ctx *ctx, int dst_field, int src_field)
 { VDN_TRY(ctx, { VDN_REQUIRE(dst_field >= 0 && dst_field < VDN_NFIELDS && src_field >= 0 && src_field < VDN_NFIELDS, "bad field id");
                  st_field_copy(ctx, dst_field, src_field); }) }
+
+int vdn_visc_solve(vdn_ctx *ctx, double mu, int diffusion_type, int *ncycles, double *resnorm)
+{ VDN_TRY(ctx, { int rc = st_visc_solve(ctx, mu, diffusion_type, ncycles, resnorm);
+                 if (rc) { ctx->err = "Helmholtz multigrid (visc_solve) did not converge within mg_max_cycles"; return 2; } }) }
+
+int vdn_diff_scalar_solve(vdn_ctx *ctx, double mu, int icomp, int diffusion_type, int *ncycles, double *resnorm)
+{ VDN_TRY(ctx, { int rc = st_diff_scalar_solve(ctx, mu, icomp, diffusion_type, ncycles, resnorm);
+                 if (rc) { ctx->err = "Helmholtz multigrid (diff_scalar_solve) did not converge within mg_max_cycles"; return 2; } }) }
 
 int vdn_mg_tune(vdn_ctx *ctx, int fuse_min, int tile)
 { VDN_TRY(ctx, { VDN_REQUIRE(tile >= -1 && tile < 5, "tile shape out of range");

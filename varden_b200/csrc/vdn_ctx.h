@@ -44,6 +44,7 @@ struct vdn_ctx {
     std::map<std::string, int> prof_idx;
     std::vector<cudaEvent_t> ev_pool;
     MG *mg = nullptr;
+    MG *mgh = nullptr;                                  // Helmholtz hierarchy (visc_solve / diff_scalar_solve), built on first use
     Comm *comm = nullptr;
     long long umac_epoch = 0, eps_epoch = -1;          // UMAC_* write counter / counter value the per-box umac eps was computed at
     // vdn_advance_host: copy streams + per-field events (uploaded / final on the device)
@@ -89,6 +90,13 @@ double st_estdt(vdn_ctx *c, double dtold, double cflfac, double max_dt_growth); 
 void st_field_copy(vdn_ctx *c, int dst, int src);
 double st_absmax_valid(vdn_ctx *c, int field);           // norm_inf over valid cells/faces, all comps
 void mg_destroy(MG *mg);
+// Helmholtz solves (vdn_mg.cu): level-0 arrays of the separate hierarchy, and the solve on them
+enum : int { VDN_MODE_NEU = 1, VDN_MODE_DIR = 2, VDN_MODE_WRAP = 3 };      // = M_NEU / M_DIR / M_WRAP of vdn_mg_fused.cuh (checked in vdn_mg.cu)
+struct HelmLev0 { double *phi, *rhs, *alpha, *b[3]; long off, sy, sz, ntot; };
+void mg_helm_level0(vdn_ctx *c, HelmLev0 *out);
+int  st_helm_solve(vdn_ctx *c, const int (*mode)[2], double rel_eps, double abs_eps, int *ncycles, double *resnorm);
+int  st_visc_solve(vdn_ctx *c, double mu, int diffusion_type, int *ncycles, double *resnorm);          // viscsolve.f90:19
+int  st_diff_scalar_solve(vdn_ctx *c, double mu, int icomp, int diffusion_type, int *ncycles, double *resnorm);   // viscsolve.f90:310
 void comm_destroy(Comm *cm);
 void comm_exchange_field(vdn_ctx *c, int field);          // ghost cells owned by neighbour ranks, every split direction at once (vdn_comm.cu)
 const int *comm_pgrid_or_null(const vdn_ctx *c);

@@ -26,6 +26,7 @@ struct Lev {
     int par0;               // parity of the global index of local cell (0,0,0)
     double *phi, *rhs, *res, *b[3];
     double *dinv;           // 1 / diagonal (fused smoother levels), recomputed with the coefficients at every solve
+    double *alpha;          // Helmholtz solves (alpha - div beta grad) phi = rhs: the cell coefficient; null for the MAC projection
 };
 
 struct MG {
@@ -54,17 +55,21 @@ struct MG {
     bool first_sweep_done = false;              // the first smoothing sweep of level 0 of the coming V-cycle has been launched already
     cudaEvent_t ev_norm = nullptr;              // the residual norm of the last V-cycle has reached the pinned host word
     int sm_count = 148;
+    bool helm = false;                          // Helmholtz hierarchy (visc_solve / diff_scalar_solve): plain kernels with the alpha term
 };
 
 namespace {
 
 const dim3 BLK(64, 4, 1);
 
-template <int DIM>
+// HELM: the operator is alpha - div(beta grad) (viscsolve.f90:98-100 -> mac_multigrid with alpha = rho or 1); the MAC projection
+// instantiates HELM = false and its code is unchanged
+template <int DIM, bool HELM = false>
 __device__ __forceinline__ void cell_op(const Lev &L, const double *__restrict__ x, long c, const int (&ix)[3], double &Ax, double &dg)
 {
     const double x0 = x[c];
     double a = 0.0, g = 0.0;
+    if (HELM) { const double al = L.alpha[c]; a = al * x0; g = al; }
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         const long st = L.s[d];
@@ -83,7 +88,7 @@ __device__ __forceinline__ void cell_op(const Lev &L, const double *__restrict__
 }
 
 // one colour half-sweep; thread per colour cell
-template <int DIM>
+template <int DIM, bool HELM = false>
 __global__ void k_gsrb(Lev L, int color)
 {
     const int i2 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,12 +99,12 @@ __global__ void k_gsrb(Lev L, int color)
     if (i >= L.n[0]) return;
     const long c = L.off + i + L.s[1] * j + L.s[2] * k;
     const int ix[3] = { i, j, k };
-    double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+    double Ax, dg; cell_op<DIM, HELM>(L, L.phi, c, ix, Ax, dg);
     if (dg != 0.0) L.phi[c] += (L.rhs[c] - Ax) / dg;
 }
 
 // res = rhs - A phi; optional inf-norm via atomicMax on the bit pattern
-template <int DIM>
+template <int DIM, bool HELM = false>
 __global__ void k_residual(Lev L, double *nrm)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,7 +114,7 @@ __global__ void k_residual(Lev L, double *nrm)
     if (i < L.n[0] && j < L.n[1]) {
         const long c = L.off + i + L.s[1] * j + L.s[2] * k;
         const int ix[3] = { i, j, k };
-        double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+        double Ax, dg; cell_op<DIM, HELM>(L, L.phi, c, ix, Ax, dg);
         r = L.rhs[c] - Ax;
         L.res[c] = r;
         r = fabs(r);
@@ -204,7 +209,7 @@ __device__ double block_sum(double v, double *sm)
 }
 struct BotVec { double *r, *rh, *p, *v, *s, *t; };
 
-template <int DIM>
+template <int DIM, bool HELM = false>
 __device__ void bottom_solve(const Lev &L, const BotVec &w, int maxit, double eps, int singular, double *sm)
 {
     const long nc = (long)L.n[0] * L.n[1] * L.n[2];
@@ -233,7 +238,7 @@ __device__ void bottom_solve(const Lev &L, const BotVec &w, int maxit, double ep
         }
         __syncthreads();
         double den = 0.0;
-        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) double Ax, dg; cell_op<DIM>(L, w.p, c, ix, Ax, dg); w.v[c] = Ax; den += w.rh[c] * Ax; }
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) double Ax, dg; cell_op<DIM, HELM>(L, w.p, c, ix, Ax, dg); w.v[c] = Ax; den += w.rh[c] * Ax; }
         den = block_sum(den, sm);
         if (den == 0.0) break;
         alpha = rho1 / den;
@@ -243,7 +248,7 @@ __device__ void bottom_solve(const Lev &L, const BotVec &w, int maxit, double ep
         if (sn <= eps * bn) { for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] += alpha * w.p[c]; } break; }
         __syncthreads();
         double ts = 0.0, tt = 0.0;
-        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) double Ax, dg; cell_op<DIM>(L, w.s, c, ix, Ax, dg); w.t[c] = Ax; ts += Ax * w.s[c]; tt += Ax * Ax; }
+        for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) double Ax, dg; cell_op<DIM, HELM>(L, w.s, c, ix, Ax, dg); w.t[c] = Ax; ts += Ax * w.s[c]; tt += Ax * Ax; }
         ts = block_sum(ts, sm); tt = block_sum(tt, sm);
         if (tt == 0.0) { for (long q = tid; q < nc; q += nt) { CELL(q, c, ix) (void)ix; L.phi[c] += alpha * w.p[c]; } break; }
         omega = ts / tt;
@@ -263,11 +268,11 @@ __device__ void bottom_solve(const Lev &L, const BotVec &w, int maxit, double ep
     }
 #undef CELL
 }
-template <int DIM>
+template <int DIM, bool HELM = false>
 __global__ void __launch_bounds__(1024) k_bottom(Lev L, BotVec w, int maxit, double eps, int singular)
 {
     __shared__ double sm[32];
-    bottom_solve<DIM>(L, w, maxit, eps, singular, sm);
+    bottom_solve<DIM, HELM>(L, w, maxit, eps, singular, sm);
 }
 
 // ---- the tail of a V-cycle in ONE CTA: every level of at most TAIL_CELLS cells (8^3) -- smoothing, residual, restriction, the BiCGStab
@@ -282,7 +287,7 @@ __device__ __forceinline__ void tail_cell(const Lev &L, long q, long &c, int (&i
     ix[0] = (int)(q % L.n[0]); ix[1] = (int)((q / L.n[0]) % L.n[1]); ix[2] = (int)(q / ((long)L.n[0] * L.n[1]));
     c = L.off + ix[0] + L.s[1] * ix[1] + L.s[2] * ix[2];
 }
-template <int DIM>
+template <int DIM, bool HELM = false>
 __device__ void tail_smooth(const Lev &L, int sweeps)
 {
     const long nc = (long)L.n[0] * L.n[1] * L.n[2];
@@ -291,23 +296,23 @@ __device__ void tail_smooth(const Lev &L, int sweeps)
             for (long q = threadIdx.x; q < nc; q += blockDim.x) {
                 long c; int ix[3]; tail_cell<DIM>(L, q, c, ix);
                 if (((ix[0] + ix[1] + ix[2] + color + L.par0) & 1) != 0) continue;
-                double Ax, dg; cell_op<DIM>(L, L.phi, c, ix, Ax, dg);
+                double Ax, dg; cell_op<DIM, HELM>(L, L.phi, c, ix, Ax, dg);
                 if (dg != 0.0) L.phi[c] += (L.rhs[c] - Ax) / dg;
             }
             __syncthreads();
         }
 }
-template <int DIM>
+template <int DIM, bool HELM = false>
 __global__ void __launch_bounds__(1024) k_tail(TailArgs a)
 {
     __shared__ double sm[32];
     for (int l = 0; l + 1 < a.nl; ++l) {
         const Lev &F = a.L[l], &C = a.L[l + 1];
-        tail_smooth<DIM>(F, a.nu1);
+        tail_smooth<DIM, HELM>(F, a.nu1);
         const long nf = (long)F.n[0] * F.n[1] * F.n[2];
         for (long q = threadIdx.x; q < nf; q += blockDim.x) {
             long c; int ix[3]; tail_cell<DIM>(F, q, c, ix);
-            double Ax, dg; cell_op<DIM>(F, F.phi, c, ix, Ax, dg);
+            double Ax, dg; cell_op<DIM, HELM>(F, F.phi, c, ix, Ax, dg);
             F.res[c] = F.rhs[c] - Ax;
         }
         __syncthreads();
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(1024) k_tail(TailArgs a)
         }
         __syncthreads();
     }
-    bottom_solve<DIM>(a.L[a.nl - 1], a.w, a.maxit, a.eps, a.singular, sm);
+    bottom_solve<DIM, HELM>(a.L[a.nl - 1], a.w, a.maxit, a.eps, a.singular, sm);
     __syncthreads();
     for (int l = a.nl - 2; l >= 0; --l) {
         const Lev &F = a.L[l], &C = a.L[l + 1];
@@ -333,11 +338,17 @@ __global__ void __launch_bounds__(1024) k_tail(TailArgs a)
             F.phi[c] += C.phi[cc];
         }
         __syncthreads();
-        tail_smooth<DIM>(F, a.nu2);
+        tail_smooth<DIM, HELM>(F, a.nu2);
     }
 }
 
 template <class F> void for_dim(int dim, F f) { if (dim == 3) f(std::integral_constant<int, 3>()); else f(std::integral_constant<int, 2>()); }
+// (dimension, Helmholtz) dispatch of the plain kernels
+template <class F> void for_dim_h(int dim, bool helm, F f)
+{
+    if (helm) { if (dim == 3) f(std::integral_constant<int, 3>(), std::true_type()); else f(std::integral_constant<int, 2>(), std::true_type()); }
+    else      { if (dim == 3) f(std::integral_constant<int, 3>(), std::false_type()); else f(std::integral_constant<int, 2>(), std::false_type()); }
+}
 
 dim3 cgrid(int nx, int ny, int nz) { return dim3(cdiv(nx, BLK.x), cdiv(ny, BLK.y), nz); }
 
@@ -374,9 +385,10 @@ __global__ void k_blk_extract(ExtArgs a)        // local phi <- my block of the 
 
 // Build a hierarchy for a grid of n cells (spacing h, global index origin glo) with per-face modes.
 // alias0: level 0 uses the context's PHI / RH / BETA_* storage.  max_levels < 0: coarsen as far as possible.
-MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, const int (*mode)[2], bool alias0, int max_levels)
+MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, const int (*mode)[2], bool alias0, int max_levels, bool helm = false)
 {
     MG *m = new MG();
+    m->helm = helm;
     bool sym = false;                                    // any face shared with another rank
     for (int d = 0; d < c->dim; ++d) for (int s = 0; s < 2; ++s) if (mode[d][s] == M_GHOST) sym = true;
     m->dim = c->dim;
@@ -390,7 +402,7 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         ++nlev;
     }
     m->nlev = nlev; m->L.resize(nlev);
-    m->singular = true;
+    m->singular = !helm;                                 // alpha > 0: never singular
     for (int d = 0; d < c->dim; ++d) for (int s = 0; s < 2; ++s) if (c->dom_bc[d][s] == BC_OUTLET) m->singular = false;
     int n[3] = { n_in[0], n_in[1], n_in[2] };
     double h[3] = { h_in[0], h_in[1], h_in[2] };
@@ -420,7 +432,8 @@ MG *mg_make(vdn_ctx *c, const int *n_in, const double *h_in, const int *glo_in, 
         }
         for (int d = c->dim; d < 3; ++d) L.b[d] = nullptr;
         L.res = dalloc(L.ntot);
-        L.dinv = c->dim == 3 ? dalloc(L.ntot) : nullptr;
+        L.dinv = (c->dim == 3 && !helm) ? dalloc(L.ntot) : nullptr;
+        L.alpha = helm ? dalloc(L.ntot) : nullptr;
         for (int d = 0; d < c->dim; ++d) { n[d] /= 2; h[d] *= 2.0; glo[d] /= 2; }
     }
     if (!m->distributed)
@@ -560,7 +573,7 @@ void smooth(vdn_ctx *c, MG *m, int l, int sweeps)
             // one colour half-sweep = R phi 8 + rhs 4 + beta 24 (3-D), W phi 4 = 40 B/cell
             LaunchScope ls(c, l == 0 ? "mg_gsrb_l0" : "mg_gsrb_coarse", cells * (m->dim == 3 ? 40.0 : 32.0));
             dim3 gr(cdiv((L.n[0] + 1) / 2, BLK.x), cdiv(L.n[1], BLK.y), L.n[2]);
-            for_dim(m->dim, [&](auto D) { k_gsrb<decltype(D)::value><<<gr, BLK, 0, c->stream>>>(L, color); });
+            for_dim_h(m->dim, m->helm, [&](auto D, auto H) { k_gsrb<decltype(D)::value, decltype(H)::value><<<gr, BLK, 0, c->stream>>>(L, color); });
         }
 }
 void residual(vdn_ctx *c, MG *m, int l, double *nrm)
@@ -570,7 +583,7 @@ void residual(vdn_ctx *c, MG *m, int l, double *nrm)
     mg_halo(c, m, L, L.phi);
     LaunchScope ls(c, l == 0 ? "mg_residual_l0" : "mg_residual_coarse", cells * (m->dim == 3 ? 48.0 : 40.0));
     if (nrm) VDN_CUDA(cudaMemsetAsync(nrm, 0, 8, c->stream));
-    for_dim(m->dim, [&](auto D) { k_residual<decltype(D)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, nrm); });
+    for_dim_h(m->dim, m->helm, [&](auto D, auto H) { k_residual<decltype(D)::value, decltype(H)::value><<<cgrid(L.n[0], L.n[1], L.n[2]), BLK, 0, c->stream>>>(L, nrm); });
 }
 
 
@@ -730,7 +743,7 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         for (int q = 0; q < a.nl; ++q) a.L[q] = m->L[l + q];
         a.w = { m->bot[0], m->bot[1], m->bot[2], m->bot[3], m->bot[4], m->bot[5] };
         a.nu1 = c->prm.mg_nu1; a.nu2 = c->prm.mg_nu2; a.maxit = c->prm.mg_max_bottom_iter; a.eps = c->prm.mg_bottom_eps; a.singular = m->singular ? 1 : 0;
-        for_dim(m->dim, [&](auto D) { k_tail<decltype(D)::value><<<1, 1024, 0, c->stream>>>(a); });
+        for_dim_h(m->dim, m->helm, [&](auto D, auto H) { k_tail<decltype(D)::value, decltype(H)::value><<<1, 1024, 0, c->stream>>>(a); });
         return;
     }
     if (l == m->nlev - 1) {
@@ -738,7 +751,7 @@ void vcycle(vdn_ctx *c, MG *m, int l)
         BotVec w = { m->bot[0], m->bot[1], m->bot[2], m->bot[3], m->bot[4], m->bot[5] };
         long nc = (long)L.n[0] * L.n[1] * L.n[2];
         int nt = nc >= 1024 ? 1024 : (int)std::max<long>(32, ((nc + 31) / 32) * 32);
-        for_dim(m->dim, [&](auto D) { k_bottom<decltype(D)::value><<<1, nt, 0, c->stream>>>(L, w, c->prm.mg_max_bottom_iter, c->prm.mg_bottom_eps, m->singular ? 1 : 0); });
+        for_dim_h(m->dim, m->helm, [&](auto D, auto H) { k_bottom<decltype(D)::value, decltype(H)::value><<<1, nt, 0, c->stream>>>(L, w, c->prm.mg_max_bottom_iter, c->prm.mg_bottom_eps, m->singular ? 1 : 0); });
         return;
     }
     Lev &C = m->L[l + 1];
@@ -807,6 +820,90 @@ void coarsen_coefficients(vdn_ctx *c, MG *m)
 }
 
 } // namespace
+
+// ---- the Helmholtz solves of viscsolve.f90 (visc_solve :19, diff_scalar_solve :310), which reach the same
+// mac_multigrid -> ml_cc_solve with alpha = rho (or 1) and beta = mu.  A separate hierarchy with its own level-0 arrays, the plain
+// per-colour kernels with the alpha term (HELM instantiations), boundary modes per solved component, a non-zero initial guess. ----
+namespace {
+template <int DIM>
+__global__ void k_coarsen_alpha(Lev F, Lev C)          // coarse alpha = average of the fine cells it covers (cell-average restriction)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= C.n[0] || j >= C.n[1]) return;
+    const long cf = F.off + 2 * i + F.s[1] * (2 * j) + F.s[2] * (DIM == 3 ? 2 * k : 0);
+    double s = F.alpha[cf] + F.alpha[cf + 1] + F.alpha[cf + F.s[1]] + F.alpha[cf + F.s[1] + 1];
+    if (DIM == 3) s += F.alpha[cf + F.s[2]] + F.alpha[cf + F.s[2] + 1] + F.alpha[cf + F.s[2] + F.s[1]] + F.alpha[cf + F.s[2] + F.s[1] + 1];
+    C.alpha[C.off + i + C.s[1] * j + C.s[2] * k] = s * (DIM == 3 ? 0.125 : 0.25);
+}
+__global__ void k_lev_absmax(Lev L, const double *x, double *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    double v = 0.0;
+    if (i < L.n[0] && j < L.n[1]) v = fabs(x[L.off + i + L.s[1] * j + L.s[2] * k]);
+    block_atomic_max(v, out);
+}
+} // namespace
+
+static_assert((int)M_NEU == (int)VDN_MODE_NEU && (int)M_DIR == (int)VDN_MODE_DIR && (int)M_WRAP == (int)VDN_MODE_WRAP, "boundary mode codes");
+// level-0 arrays of the Helmholtz hierarchy (built on first use): vdn_stream.cu fills them (st_helm_fill) and reads phi back
+void mg_helm_level0(vdn_ctx *c, HelmLev0 *out)
+{
+    VDN_REQUIRE(!c->comm, "the Helmholtz solves (visc_solve / diff_scalar_solve) run on single-rank contexts only in this version");
+    if (!c->mgh) {
+        int mode[3][2];
+        for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) mode[d][s] = M_NEU;
+        c->mgh = mg_make(c, c->geo.n, c->geo.h, c->rlo, mode, false, -1, true);
+    }
+    const Lev &L = c->mgh->L[0];
+    out->phi = L.phi; out->rhs = L.rhs; out->alpha = L.alpha;
+    for (int d = 0; d < 3; ++d) out->b[d] = L.b[d];
+    out->off = L.off; out->sy = L.s[1]; out->sz = L.s[2]; out->ntot = L.ntot;
+}
+
+// Solve with the level-0 arrays as filled by the caller; mode[d][side]: M_NEU / M_DIR / M_WRAP of the solved component.
+int st_helm_solve(vdn_ctx *c, const int (*mode)[2], double rel_eps, double abs_eps, int *ncycles, double *resnorm)
+{
+    MG *m = c->mgh;
+    VDN_REQUIRE(m != nullptr, "st_helm_solve before mg_helm_level0");
+    for (int l = 0; l < m->nlev; ++l)
+        for (int d = 0; d < 3; ++d) for (int s = 0; s < 2; ++s) m->L[l].mode[d][s] = d < m->dim ? mode[d][s] : M_NEU;
+    coarsen_coefficients(c, m);
+    for (int l = 1; l < m->nlev; ++l) {
+        Lev &F = m->L[l - 1], &C = m->L[l];
+        LaunchScope ls(c, "mg_coarsen_beta", 0.0);
+        for_dim(m->dim, [&](auto D) { k_coarsen_alpha<decltype(D)::value><<<cgrid(C.n[0], C.n[1], C.n[2]), BLK, 0, c->stream>>>(F, C); });
+    }
+    VDN_CUDA(cudaGetLastError());
+    Lev &L0 = m->L[0];
+    auto pull_norm = [&]() {
+        VDN_CUDA(cudaMemcpyAsync(c->h_pin, m->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
+        VDN_CUDA(cudaStreamSynchronize(c->stream));
+        return c->h_pin[0];
+    };
+    VDN_CUDA(cudaMemsetAsync(m->d_norm, 0, 8, c->stream));
+    k_lev_absmax<<<cgrid(L0.n[0], L0.n[1], L0.n[2]), BLK, 0, c->stream>>>(L0, L0.rhs, m->d_norm);
+    const double bnorm = pull_norm();
+    auto res_norm = [&]() { residual(c, m, 0, m->d_norm); return pull_norm(); };
+    double rn = res_norm();
+    int cyc = 0;
+    const bool talk = c->prm.mg_verbose != 0;
+    if (talk) printf("vdn_mg (Helmholtz): levels %d  |rh| = %.6e  initial |r| = %.6e\n", m->nlev, bnorm, rn);
+    auto converged = [&](double r) { return r <= rel_eps * bnorm || r <= abs_eps; };
+    while (bnorm > 0.0 && !converged(rn) && cyc < c->prm.mg_max_cycles) {
+        vcycle(c, m, 0);
+        VDN_CUDA(cudaGetLastError());
+        ++cyc;
+        rn = res_norm();
+        if (talk) printf("vdn_mg (Helmholtz): cycle %2d  |r|/|rh| = %.6e\n", cyc, rn / bnorm);
+    }
+    if (ncycles) *ncycles = cyc;
+    if (resnorm) *resnorm = bnorm > 0.0 ? rn / bnorm : 0.0;
+    return (bnorm > 0.0 && !converged(rn)) ? 1 : 0;
+}
 
 void mg_destroy(MG *m)
 {

@@ -311,6 +311,135 @@ void st_field_copy(vdn_ctx *c, int dst, int src)
     VDN_CUDA(cudaMemcpyAsync(d.base, s.base, d.bytes, cudaMemcpyDeviceToDevice, c->stream));
 }
 
+// ---- visc_solve / diff_scalar_solve (viscsolve.f90) around the Helmholtz multigrid of vdn_mg.cu ----
+// mkrhs_2d / mkrhs_3d (viscsolve.f90:193-299 for a velocity component, :464-513 for a scalar), the initial guess phi = the current field,
+// alpha = rho (or 1), and the boundary data: a Dirichlet face whose ghost cell holds the boundary VALUE (multifab_physbc EXT_DIR) enters the
+// stencil_order-2 operator as  beta (3 phi_0 - phi_1/3 - 8/3 phi_b) / h^2 ; the homogeneous part lives in the operator, the 8/3 beta phi_b / h^2
+// part is folded into the right-hand side here, once.
+namespace {
+struct HelmFillArgs {
+    Range r; int dim, comp, visc, cn;            // visc: velocity component (mac_rhs gradient term, alpha = rho); cn: Crank-Nicolson (+ mu * lap)
+    View u, lap, rho, mrhs;
+    double mu, visc_mu_dt, dx[3], h2[3];
+    int dirbc[3][2], n[3];
+    double *phi, *rhs, *alpha; long off, sy, sz;
+};
+__global__ void k_helm_fill(HelmFillArgs a)
+{
+    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = a.r.lo[2] + blockIdx.z;
+    if (i > a.r.hi[0] || j > a.r.hi[1]) return;
+    const int ix[3] = { i, j, k };
+    const double u = a.u(i, j, k, a.comp);
+    const double rho = a.visc ? a.rho(i, j, k, 0) : 1.0;
+    double rh = a.visc ? u * rho : u;
+    if (a.cn) rh = rh + a.mu * a.lap(i, j, k, a.comp);
+    if (a.visc) {
+        const int e0 = a.comp == 0, e1 = a.comp == 1, e2 = a.comp == 2;
+        rh = rh + (1.0 / 3.0) * a.visc_mu_dt * (a.mrhs(i + e0, j + e1, k + e2, 0) - a.mrhs(i - e0, j - e1, k - e2, 0)) / a.dx[a.comp];
+    }
+    for (int d = 0; d < a.dim; ++d) {
+        const int o0 = d == 0, o1 = d == 1, o2 = d == 2;
+        if (ix[d] == 0 && a.dirbc[d][0])            rh = rh + ((8.0 / 3.0) * a.mu * a.h2[d]) * a.u(i - o0, j - o1, k - o2, a.comp);
+        if (ix[d] == a.n[d] - 1 && a.dirbc[d][1])   rh = rh + ((8.0 / 3.0) * a.mu * a.h2[d]) * a.u(i + o0, j + o1, k + o2, a.comp);
+    }
+    const long c = a.off + i + a.sy * j + a.sz * k;
+    a.rhs[c] = rh; a.phi[c] = u; a.alpha[c] = rho;
+}
+struct HelmStoreArgs { Range r; int comp; View u; const double *phi; long off, sy, sz; };
+__global__ void k_helm_store(HelmStoreArgs a)
+{
+    const int i = a.r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = a.r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = a.r.lo[2] + blockIdx.z;
+    if (i > a.r.hi[0] || j > a.r.hi[1]) return;
+    a.u(i, j, k, a.comp) = a.phi[a.off + i + a.sy * j + a.sz * k];
+}
+
+// ell_bc_level_build (define_bc_tower.f90:254-340): elliptic boundary type of a velocity component (comp < dim) or a scalar on a domain face
+int helm_mode(int phys, int comp_is_vel, int comp, int d)
+{
+    switch (phys) {
+    case BC_PERIODIC:     return VDN_MODE_WRAP;
+    case BC_SLIP_WALL:
+    case BC_SYMMETRY:     return (comp_is_vel && comp == d) ? VDN_MODE_DIR : VDN_MODE_NEU;
+    case BC_NO_SLIP_WALL: return comp_is_vel ? VDN_MODE_DIR : VDN_MODE_NEU;
+    case BC_INLET:        return VDN_MODE_DIR;
+    case BC_OUTLET:       return VDN_MODE_NEU;
+    default: throw VdnError("Helmholtz solve: unsupported boundary type on a domain face");
+    }
+}
+
+int helm_component(vdn_ctx *c, int field, int comp, bool visc, double mu, int diffusion_type, int *ncycles, double *resnorm)
+{
+    const int dim = c->dim;
+    VDN_REQUIRE(diffusion_type == 1 || diffusion_type == 2, "diffusion_type must be 1 (Crank-Nicolson) or 2 (backward Euler)");
+    HelmLev0 L;
+    mg_helm_level0(c, &L);
+    int mode[3][2];
+    HelmFillArgs a;
+    a.r = valid_range(c, -1); a.dim = dim; a.comp = comp; a.visc = visc ? 1 : 0; a.cn = diffusion_type == 1 ? 1 : 0;
+    a.u = c->f[field].view(); a.lap = c->f[VDN_LAPU].view(); a.rho = c->f[VDN_RHOHALF].view(); a.mrhs = c->f[VDN_MAC_RHS].view();
+    a.mu = mu; a.visc_mu_dt = diffusion_type == 1 ? 2.0 * mu : mu;
+    for (int d = 0; d < 3; ++d) {
+        a.dx[d] = c->geo.h[d < dim ? d : 0]; a.h2[d] = 1.0 / (a.dx[d] * a.dx[d]); a.n[d] = c->geo.n[d];
+        for (int s = 0; s < 2; ++s) {
+            mode[d][s] = d < dim ? helm_mode(c->dom_bc[d][s], visc ? 1 : 0, comp, d) : VDN_MODE_NEU;
+            a.dirbc[d][s] = mode[d][s] == VDN_MODE_DIR;
+        }
+    }
+    a.phi = L.phi; a.rhs = L.rhs; a.alpha = L.alpha; a.off = L.off; a.sy = L.sy; a.sz = L.sz;
+    {
+        LaunchScope ls(c, "helm_mkrhs", (double)c->ncells() * 8.0 * 7.0, 1 + dim);
+        for (int d = 0; d < dim; ++d) {         // beta = mu on every face (viscsolve.f90:59-61)
+            SetArgs sa; sa.p = L.b[d]; sa.n = L.ntot; sa.v = mu;
+            k_setval<<<1184, 256, 0, c->stream>>>(sa);
+        }
+        k_helm_fill<<<grid3(a.r, BLK), BLK, 0, c->stream>>>(a);
+        VDN_CUDA(cudaGetLastError());
+    }
+    // rel_solver_eps = 1.d-12, abs_solver_eps = -1 (viscsolve.f90:88-89)
+    const int rc = st_helm_solve(c, mode, 1.0e-12, -1.0, ncycles, resnorm);
+    {
+        LaunchScope ls(c, "helm_store", (double)c->ncells() * 16.0);
+        HelmStoreArgs sa; sa.r = a.r; sa.comp = comp; sa.u = a.u; sa.phi = L.phi; sa.off = L.off; sa.sy = L.sy; sa.sz = L.sz;
+        k_helm_store<<<grid3(sa.r, BLK), BLK, 0, c->stream>>>(sa);
+        VDN_CUDA(cudaGetLastError());
+    }
+    return rc;
+}
+} // namespace
+
+// visc_solve (viscsolve.f90:19-146): one Helmholtz solve per velocity component on UNEW with alpha = RHOHALF, beta = mu, LAPU (Crank-Nicolson)
+// and MAC_RHS; then ml_restrict_and_fill(unew) (:105).  mu is (1/2) dt visc_coef (Crank-Nicolson) or dt visc_coef (velocity_advance.f90:105-111).
+int st_visc_solve(vdn_ctx *c, double mu, int diffusion_type, int *ncycles, double *resnorm)
+{
+    VDN_REQUIRE(diffusion_type != 1 || c->lapu_set, "visc_solve with diffusion_type = 1 needs the LAPU field (vdn_field_upload)");
+    int rc = 0, cyc = 0, ctot = 0; double res = 0.0, rmax = 0.0;
+    for (int d = 0; d < c->dim; ++d) {
+        rc |= helm_component(c, VDN_UNEW, d, true, mu, diffusion_type, &cyc, &res);
+        ctot += cyc; rmax = fmax(rmax, res);
+    }
+    st_fill_boundary(c, VDN_UNEW);
+    st_physbc(c, VDN_UNEW, 0, false);
+    if (ncycles) *ncycles = ctot;
+    if (resnorm) *resnorm = rmax;
+    return rc;
+}
+
+// diff_scalar_solve (viscsolve.f90:310-423): alpha = 1, beta = mu on component icomp of SNEW, then fill_boundary + physbc of that component
+// (:379-382; bc_comp = dm + icomp).  diffusion_type = 1 would need the explicit term laps, for which the context has no field yet.
+int st_diff_scalar_solve(vdn_ctx *c, double mu, int icomp, int diffusion_type, int *ncycles, double *resnorm)
+{
+    VDN_REQUIRE(icomp >= 0 && icomp < c->prm.nscal, "scalar component out of range");
+    VDN_REQUIRE(diffusion_type == 2, "diff_scalar_solve: only diffusion_type = 2 (backward Euler) in this version (no LAPS field yet)");
+    const int rc = helm_component(c, VDN_SNEW, icomp, false, mu, diffusion_type, ncycles, resnorm);
+    st_fill_boundary(c, VDN_SNEW);
+    st_physbc(c, VDN_SNEW, c->dim, false);
+    return rc;
+}
+
 double st_absmax_valid(vdn_ctx *c, int field)
 {
     DField &f = c->f[field];
