@@ -163,6 +163,24 @@ module vdn_iso_c
        integer(c_int), value :: dst_field, src_field
      end function vdn_field_copy
 
+     ! SURVEY 8(f) row 2: the implicit viscous / diffusive solves (include/vdn.h: vdn_visc_solve, vdn_diff_scalar_solve)
+     integer(c_int) function vdn_visc_solve(ctx, mu, diffusion_type, ncycles, resnorm) bind(c, name='vdn_visc_solve')
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), value :: mu
+       integer(c_int), value :: diffusion_type
+       integer(c_int), intent(out) :: ncycles
+       real(c_double), intent(out) :: resnorm
+     end function vdn_visc_solve
+     integer(c_int) function vdn_diff_scalar_solve(ctx, mu, icomp, diffusion_type, ncycles, resnorm) bind(c, name='vdn_diff_scalar_solve')
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), value :: mu
+       integer(c_int), value :: icomp, diffusion_type
+       integer(c_int), intent(out) :: ncycles
+       real(c_double), intent(out) :: resnorm
+     end function vdn_diff_scalar_solve
+
      integer(c_int) function vdn_device_count() bind(c, name='vdn_device_count')
        import :: c_int
      end function vdn_device_count

@@ -6,6 +6,7 @@
 !     macproject_module     :: macproject     (replaces src/macproject.f90:20)
 !     mac_multigrid_module  :: mac_multigrid  (replaces src/mac_multigrid.f90:19-20)
 !     estdt_module          :: estdt          (replaces src/estdt.f90:15; SURVEY 8(f) row 3)
+!     viscous_module        :: visc_solve, diff_scalar_solve   (replaces src/viscsolve.f90:19,310; SURVEY 8(f) row 2; single MPI rank)
 !
 ! A maintainer removes velpred.f90, mkflux.f90, update.f90, macproject.f90, mac_multigrid.f90 from src/GPackage.mak and adds
 ! vdn_iso_c.f90 + this file; every caller (advance_premac.f90:51, scalar_advance.f90:102,118, velocity_advance.f90:76,92,
@@ -416,3 +417,86 @@ contains
   end subroutine estdt
 
 end module estdt_module
+
+
+module viscous_module
+
+  use bl_types
+  use multifab_module
+  use ml_layout_module
+  use define_bc_module
+  use vdn_iso_c
+  use vdn_path_module, only : vdn_ctx_for, vdn_put, vdn_get, vdn_check
+
+  implicit none
+  private
+  public :: visc_solve, diff_scalar_solve
+
+contains
+
+  ! viscsolve.f90:19 -- argument list unchanged.  One Helmholtz solve per velocity component on the device (alpha = rho, beta = mu,
+  ! boundary types of the component, Dirichlet data from unew's ghost cells, rel. tolerance 1.d-12), then unew's ghost cells refilled.
+  subroutine visc_solve(mla,unew,lapu,rho,mac_rhs,dx,mu,the_bc_tower)
+
+    use probin_module, only : diffusion_type
+
+    type(ml_layout), intent(in   ) :: mla
+    type(multifab ), intent(inout) :: unew(:)
+    type(multifab ), intent(in   ) :: lapu(:)
+    type(multifab ), intent(in   ) :: rho(:)
+    real(dp_t)     , intent(in   ) :: dx(:,:),mu
+    type(bc_tower ), intent(in   ) :: the_bc_tower
+    type(multifab ), intent(in   ) :: mac_rhs(:)
+
+    type(c_ptr) :: ctx
+    integer(c_int) :: ncyc, rc
+    real(c_double) :: res
+    type(bl_prof_timer), save :: bpt
+
+    call build(bpt,"visc_solve")
+    if (mla%nlevel /= 1) call bl_error('visc_solve (libvdn): single-level only')
+    if (parallel_nprocs() /= 1) call bl_error('visc_solve (libvdn): single MPI rank only in this version')
+    ctx = vdn_ctx_for(mla, unew(1), dx)
+    call vdn_put(ctx, VDN_UNEW, unew(1))
+    call vdn_put(ctx, VDN_RHOHALF, rho(1), 1)             ! rhohalf: component 1 (velocity_advance.f90:117)
+    call vdn_put(ctx, VDN_MAC_RHS, mac_rhs(1))
+    if (diffusion_type == 1) call vdn_put(ctx, VDN_LAPU, lapu(1))
+    rc = vdn_visc_solve(ctx, real(mu,c_double), int(diffusion_type,c_int), ncyc, res)
+    call vdn_check(ctx, rc)
+    call vdn_get(ctx, VDN_UNEW, unew(1))
+    call destroy(bpt)
+
+  end subroutine visc_solve
+
+  ! viscsolve.f90:310 -- argument list unchanged; backward Euler (diffusion_type = 2) only in this version
+  subroutine diff_scalar_solve(mla,snew,laps,dx,mu,the_bc_tower,icomp,bc_comp)
+
+    use probin_module, only : diffusion_type
+
+    type(ml_layout), intent(in   ) :: mla
+    type(multifab ), intent(inout) :: snew(:)
+    type(multifab ), intent(in   ) :: laps(:)
+    real(dp_t)     , intent(in   ) :: dx(:,:)
+    real(dp_t)     , intent(in   ) :: mu
+    type(bc_tower ), intent(in   ) :: the_bc_tower
+    integer        , intent(in   ) :: icomp,bc_comp
+
+    type(c_ptr) :: ctx
+    integer(c_int) :: ncyc, rc
+    real(c_double) :: res
+    type(bl_prof_timer), save :: bpt
+
+    call build(bpt,"diff_scalar_solve")
+    if (mla%nlevel /= 1) call bl_error('diff_scalar_solve (libvdn): single-level only')
+    if (parallel_nprocs() /= 1) call bl_error('diff_scalar_solve (libvdn): single MPI rank only in this version')
+    if (diffusion_type /= 2) call bl_error('diff_scalar_solve (libvdn): diffusion_type = 2 only in this version')
+    ctx = vdn_ctx_for(mla, snew(1), dx)
+    call vdn_put(ctx, VDN_SNEW, snew(1))
+    rc = vdn_diff_scalar_solve(ctx, real(mu,c_double), int(icomp-1,c_int), int(diffusion_type,c_int), ncyc, res)
+    call vdn_check(ctx, rc)
+    call vdn_get(ctx, VDN_SNEW, snew(1))
+    call destroy(bpt)
+
+  end subroutine diff_scalar_solve
+
+end module viscous_module
