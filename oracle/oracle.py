@@ -433,10 +433,11 @@ def helm_ell_bc(geom, comp_is_vel, comp):
     return ell
 
 
-def _helm_component(geom, params, mf, ng, comp, comp_is_vel, rho, lap, mac_rhs, mu, diffusion_type, rel_eps=1e-12):
-    """one Helmholtz solve (alpha - mu div grad) phi = rh on component comp of mf: mkrhs_2d/3d (viscsolve.f90:193-299 / :464-513), the Dirichlet
-    data folded into rh (a ghost cell of an EXT_DIR face holds the boundary value: + 8/3 mu phi_b / h^2, the inhomogeneous part of the
-    stencil_order-2 boundary stencil), initial guess = the current field"""
+def helm_rhs(geom, mf, ng, comp, comp_is_vel, rho, lap, mac_rhs, mu, diffusion_type, fold=True):
+    """right-hand side of one Helmholtz solve on the whole domain: mkrhs_2d/3d (viscsolve.f90:193-299 for a velocity component, :464-513 for a
+    scalar) in the reference's operation order, and -- fold=True -- the Dirichlet data: a ghost cell of an EXT_DIR face holds the boundary value,
+    which contributes 8/3 mu phi_b / h^2 (the inhomogeneous part of the stencil_order-2 boundary stencil).
+    -> (rh, field with one ghost layer, alpha, elliptic boundary types)"""
     dim = geom.dim
     N = [geom.n_cell[d] for d in range(3)]
     ug = _gather(geom, mf, ng, comp, grow=1)
@@ -458,12 +459,21 @@ def _helm_component(geom, params, mf, ng, comp, comp_is_vel, rho, lap, mac_rhs, 
     for d in range(dim):
         h2 = 1.0 / geom.dx[d] ** 2
         for s in range(2):
-            if ell[d, s] != 1:
+            if ell[d, s] != 1 or not fold:
                 continue
             cell = [slice(None)] * 3; ghost = list(V)
             cell[d] = 0 if s == 0 else N[d] - 1
             ghost[d] = 0 if s == 0 else N[d] + 1
             rh[tuple(cell)] = rh[tuple(cell)] + ((8.0 / 3.0) * mu * h2) * ug[tuple(ghost)]
+    return rh, ug, alpha, ell
+
+
+def _helm_component(geom, params, mf, ng, comp, comp_is_vel, rho, lap, mac_rhs, mu, diffusion_type, rel_eps=1e-12):
+    """one Helmholtz solve (alpha - mu div grad) phi = rh on component comp of mf, initial guess = the current field"""
+    dim = geom.dim
+    N = [geom.n_cell[d] for d in range(3)]
+    rh, ug, alpha, ell = helm_rhs(geom, mf, ng, comp, comp_is_vel, rho, lap, mac_rhs, mu, diffusion_type)
+    u = ug[tuple(slice(1, N[d] + 1) if d < dim else slice(None) for d in range(3))]
     nn = (C.c_int * 3)(*N)
     hh = (C.c_double * 3)(*[geom.dx[d] if d < dim else 1.0 for d in range(3)])
     eb = (C.c_int * 6)(*[int(x) for x in ell.ravel()])

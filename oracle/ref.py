@@ -106,7 +106,7 @@ def set_probin(params):
     """probin_module values the per-box routines read (src/_parameters, probin.template:21-23)."""
     L = lib()
     for k, v in (("slope_order", params.slope_order), ("use_minion", params.use_minion), ("boussinesq", params.boussinesq),
-                 ("nscal", params.nscal)):
+                 ("nscal", params.nscal), ("diffusion_type", getattr(params, "diffusion_type", 1))):
         C.c_int.in_dll(L, k).value = int(v)
     C.c_double.in_dll(L, "visc_coef").value = params.visc_coef
     C.c_double.in_dll(L, "diff_coef").value = params.diff_coef
@@ -331,6 +331,28 @@ def estdt(geom, u, ng_u, s, ng_s, gp, ng_g, ext_vel_force, ng_f, dtold=-1.0, cfl
     if dtold > 0.0:
         dt = min(dt, max_dt_growth * dtold)
     return dt
+
+
+def visc_mkrhs(geom, unew, lapu, rho, mac_rhs, mu, comp, diffusion_type):
+    """visc_solve's internal mkrhs (viscsolve.f90:147-191) around the reference's own mkrhs_2d / mkrhs_3d (:193-299): per box rh (no ghost
+    cells) and phi (one ghost layer) for velocity component comp (0-based)"""
+    dm = geom.dim
+    C.c_int.in_dll(lib(), "diffusion_type").value = int(diffusion_type)
+    rh, phi = O.mf_alloc(geom, 0, 1), O.mf_alloc(geom, 1, 1)
+    for ib in range(geom.nboxes):
+        call("visc_mkrhs_%dd" % dm, _c1(rh[ib], dm), _c1(unew[ib], dm, comp), _c1(lapu[ib], dm, comp), _c1(rho[ib], dm), _c1(phi[ib], dm),
+             _c1(mac_rhs[ib], dm), mu, _dx(geom), 3, 1, 1, comp + 1)
+    return rh, phi
+
+
+def scal_mkrhs(geom, snew, laps, mu, comp, diffusion_type):
+    """diff_scalar_solve's internal mkrhs (viscsolve.f90:426-462) around the reference's own mkrhs_2d / mkrhs_3d (:464-513)"""
+    dm = geom.dim
+    C.c_int.in_dll(lib(), "diffusion_type").value = int(diffusion_type)
+    rh, phi = O.mf_alloc(geom, 0, 1), O.mf_alloc(geom, 1, 1)
+    for ib in range(geom.nboxes):
+        call("scal_mkrhs_%dd" % dm, _c1(rh[ib], dm), _c1(snew[ib], dm, comp), _c1(laps[ib], dm, comp), _c1(phi[ib], dm), mu, 3)
+    return rh, phi
 
 
 def divumac(geom, umac, mac_rhs, rh):

@@ -142,3 +142,39 @@ def test_estdt_bit_identical(name, scale):
         assert a == b, (name, scale, dtold, a, b)
     if scale < 1e-8:
         assert O.estdt(geom, u, 3, st["sold"], 3, gp, 1, f, 1) == 0.5 * min(geom.dx[:geom.dim])
+
+
+@pytest.mark.parametrize("name", ["3d_slip_8box", "3d_inout_mix", "2d_walls", "2d_inout"])
+@pytest.mark.parametrize("diffusion_type", [1, 2])
+def test_helmholtz_rhs_bit_identical(name, diffusion_type):
+    """the right-hand sides and initial guesses of visc_solve / diff_scalar_solve -- the reference's own mkrhs_2d / mkrhs_3d
+    (viscsolve.f90:193-299, :464-513; two internal procedures of each name, transpiled separately) against the oracle's restatement, bit
+    for bit on every box.  (The Dirichlet-data term the oracle then folds into the right-hand side belongs to F_MG's boundary stencil and is
+    not part of these routines: compared with fold=False.)"""
+    geom, P, st, dt = _case(name)
+    dim = geom.dim
+    rng = np.random.default_rng(5)
+    rho = O.mf_alloc(geom, 1, 1)
+    for ib in range(geom.nboxes):
+        sl = tuple(slice(2, -2) if d < dim else slice(None) for d in range(3))
+        rho[ib][..., 0] = st["sold"][ib][sl + (0,)]
+    lapu = [np.asfortranarray(rng.standard_normal(a.shape)) for a in O.mf_alloc(geom, 0, dim)]
+    laps = [np.asfortranarray(rng.standard_normal(a.shape)) for a in O.mf_alloc(geom, 0, P.nscal)]
+    mac_rhs = [np.asfortranarray(rng.standard_normal(a.shape)) for a in O.mf_alloc(geom, 1, 1)]
+    O.fill_boundary(geom, mac_rhs, 1, 1)                    # neighbouring boxes agree on the cells they share
+    mu = 3.7e-3
+    for comp in range(dim):
+        rh, phi = R.visc_mkrhs(geom, st["uold"], lapu, rho, mac_rhs, mu, comp, diffusion_type)
+        want, ug, alpha, ell = O.helm_rhs(geom, st["uold"], 3, comp, True, rho, lapu, mac_rhs, mu, diffusion_type, fold=False)
+        for ib, (lo, hi) in enumerate(geom.boxes):
+            sl = tuple(slice(lo[d], hi[d] + 1) if d < dim else slice(None) for d in range(3))
+            assert np.array_equal(rh[ib][..., 0], want[sl]), (name, comp, ib)
+            gl = tuple(slice(lo[d], hi[d] + 3) if d < dim else slice(None) for d in range(3))
+            inner = tuple(slice(1, -1) if d < dim else slice(None) for d in range(3))
+            assert np.array_equal(phi[ib][..., 0][inner], ug[gl][inner])          # initial guess = the current field
+    for comp in range(P.nscal):
+        rh, phi = R.scal_mkrhs(geom, st["sold"], laps, mu, comp, diffusion_type)
+        want, ug, alpha, ell = O.helm_rhs(geom, st["sold"], 3, comp, False, None, laps, None, mu, diffusion_type, fold=False)
+        for ib, (lo, hi) in enumerate(geom.boxes):
+            sl = tuple(slice(lo[d], hi[d] + 1) if d < dim else slice(None) for d in range(3))
+            assert np.array_equal(rh[ib][..., 0], want[sl]), (name, "scalar", comp, ib)
