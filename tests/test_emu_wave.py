@@ -149,6 +149,14 @@ GM_PER = ((M_WRAP, M_WRAP),) * 3
 GM_MIX = ((M_NEU, M_DIR), (M_WRAP, M_WRAP), (M_NEU, M_NEU))        # inflow / outflow x, periodic y, walls z (the rand3d multi-GPU case)
 
 
+@pytest.mark.parametrize("cfg,pre,post", [(1, 0, 0), (1, 1, 0), (4, 0, 3), (2, 0, 2)])
+def test_wave_rank_ghost_layers_production_tiles(emu, cfg, pre, post):
+    """the tile shapes the launcher picks on a 16^3 rank-local level (64x16 plain / prolongating sweeps, 32x24 sweep + norm, 32x16 sweep +
+    residual + restriction): one ragged CTA whose tile is larger than the level, ghost layers on every shared face, mixed physical boundaries,
+    2 x 2 x 2 ranks in peer-memory mode -- the configuration of the 8-GPU rand3d parity case"""
+    test_wave_rank_ghost_layers(emu, pre, post, (0, 1, 2), GM_MIX, (32, 32, 32), cfg, 1)
+
+
 @pytest.mark.parametrize("p2p", [0, 1])
 @pytest.mark.parametrize("cfg", [5, 2])
 @pytest.mark.parametrize("pre,post", [(0, 0), (1, 0), (0, 2), (1, 3)])
